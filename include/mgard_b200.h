@@ -1,0 +1,196 @@
+/*
+ * mgard_b200 — C ABI of the B200-native MGARD-X hot path.
+ *
+ * Plain C: pointers, sizes and status codes only.  This is the drop-in
+ * boundary: every entry point names the reference interface it replaces
+ * (paths under /root/reference).  The C++ mirror of the reference API
+ * (mgard_x::compress / mgard_x::decompress, include/compress_x.hpp:31-178) is
+ * include/mgard_b200/compress_x.hpp and is a thin inline wrapper over these.
+ *
+ * All `d_*` pointers are CUDA device pointers on the current device; `stream`
+ * is a cudaStream_t passed as void* (NULL = default stream).  Functions are
+ * asynchronous on `stream` unless stated; they return 0 (MGB_SUCCESS) or a
+ * status mirroring mgard_x::compress_status_type
+ * (include/mgard-x/Utilities/Types.h:56-63).  No exceptions cross this ABI,
+ * and there is no CPU fallback: without a CUDA device every compute call
+ * returns MGB_BACKEND_NOT_AVAILABLE.
+ */
+#ifndef MGARD_B200_H
+#define MGARD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* mgard_x::compress_status_type (Types.h:56-63), same numeric values */
+enum {
+  MGB_SUCCESS = 0,
+  MGB_FAILURE = 1,
+  MGB_OUTPUT_TOO_LARGE = 2,
+  MGB_TOO_MANY_DIMS = 3,
+  MGB_BAD_DTYPE = 4,
+  MGB_BACKEND_NOT_AVAILABLE = 5,
+  /* extensions (argument / stream-format errors) */
+  MGB_BAD_ARGUMENT = 16,
+  MGB_BAD_STREAM = 17,
+  MGB_CUDA_ERROR = 18
+};
+
+/* mgard_x::data_type (Types.h:38) */
+enum { MGB_F32 = 0, MGB_F64 = 1 };
+/* mgard_x::error_bound_type (Types.h:30) */
+enum { MGB_REL = 0, MGB_ABS = 1 };
+
+#define MGB_MAX_DIMS 5
+
+/* Subset of mgard_x::Config (include/mgard-x/Config/Config.h:10-42) that the
+ * hot path reads; defaults as src/mgard-x/Config/Config.cpp:14-43. */
+typedef struct mgb_config {
+  int32_t dev_id;          /* Config::dev_id */
+  int32_t huff_dict_size;  /* 8192 */
+  int32_t huff_block_size; /* 20480 */
+  int32_t domain_decomposition_dim;   /* -1: largest dim (MaxDim) */
+  uint64_t domain_decomposition_size; /* 0: do not decompose */
+  int32_t normalize_coordinates;      /* 1 (only value supported) */
+  int32_t reserved;
+} mgb_config;
+
+void mgb_config_default(mgb_config *cfg);
+
+/* ---- plan = mgard_x::Hierarchy<D,T> + Compressor<D,T> workspaces ----------
+ * replaces Hierarchy ctor (include/mgard-x/Hierarchy/Hierarchy.hpp:193-418,
+ * 737-800) and Compressor ctor (CompressionLowLevel/Compressor.hpp:31-57). */
+typedef struct mgb_plan mgb_plan;
+
+/* coords: NULL for a uniform grid, else ndim host arrays (dtype T) of length
+ * shape[d] (slowest dim first), strictly increasing. */
+int mgb_plan_create(int ndim, const uint64_t *shape, int dtype,
+                    const void *const *coords, const mgb_config *cfg,
+                    mgb_plan **plan);
+void mgb_plan_destroy(mgb_plan *plan);
+int mgb_plan_l_target(const mgb_plan *plan);
+uint64_t mgb_plan_num_elems(const mgb_plan *plan);
+/* level_shape(l, d), Hierarchy.hpp:560-577 */
+uint64_t mgb_plan_level_shape(const mgb_plan *plan, int level, int dim);
+/* Host copy of one hierarchy table; which: 0 dist, 1 ratio, 2 am, 3 bm
+ * (Hierarchy.hpp:23-162).  Writes `count` values of dtype T to out; returns
+ * the table length (n for dist/ratio, n+1 for am/bm). */
+uint64_t mgb_plan_table(const mgb_plan *plan, int which, int level, int dim,
+                        void *out, uint64_t count);
+
+/* ---- stage entry points (device resident, used by the parity tests) ------ */
+
+/* data_refactoring::multi_dimension::decompose / recompose
+ * (DataRefactoring/MultiDimension/DataRefactoring.hpp:25-177,180-317).
+ * d_in: dense row-major field (not modified); d_out: coefficients in the
+ * reference's in-place "coarse nodes first along every dimension" layout. */
+int mgb_decompose(mgb_plan *plan, const void *d_in, void *d_out, void *stream);
+int mgb_recompose(mgb_plan *plan, const void *d_in, void *d_out, void *stream);
+
+/* norm_calculator (CompressionLowLevel/NormCalculator.hpp:13-83): max|u| for
+ * s = +inf, else sqrt(sum u^2 / N).  Synchronises the stream. */
+int mgb_norm(mgb_plan *plan, const void *d_in, double s, double *norm);
+/* Partial reductions for the sharded path (max|u| and sum u^2 as doubles). */
+int mgb_norm_partials(mgb_plan *plan, const void *d_in, double *absmax,
+                      double *sumsq);
+
+/* LevelwiseLinearQuantizerKernel<QUANTIZE> fused with the Huffman histogram
+ * (Quantization/LinearQuantization.hpp:148-266,495-545 +
+ * Lossless/ParallelHuffman/Histogram.hpp).  d_sym: uint16 symbols (dictionary
+ * shifted, outliers = 0); d_hist: uint32[dict] (zeroed by the call);
+ * outliers appended to (d_oidx, d_oval); *d_ocount device counter. */
+int mgb_quantize(mgb_plan *plan, const void *d_coef, int ebtype, double tol,
+                 double s, double norm, uint16_t *d_sym, uint32_t *d_hist,
+                 unsigned long long *d_ocount, uint64_t *d_oidx,
+                 int64_t *d_oval, uint64_t outlier_cap, void *stream);
+/* OutlierRestore + LevelwiseLinearQuantizerKernel<DEQUANTIZE>
+ * (LinearQuantization.hpp:251-264,304-350). */
+int mgb_dequantize(mgb_plan *plan, const uint16_t *d_sym, uint64_t ocount,
+                   const uint64_t *d_oidx, const int64_t *d_oval, int ebtype,
+                   double tol, double s, double norm, void *d_coef,
+                   void *stream);
+
+/* GetCodebook (Lossless/ParallelHuffman/GetCodebook.hpp:23-146): histogram ->
+ * codebook[dict] (len<<56|code) and decodebook (first[64] entry[64]
+ * keys[dict], all uint64).  Device resident. */
+int mgb_codebook(mgb_plan *plan, const uint32_t *d_hist, uint64_t *d_codebook,
+                 uint64_t *d_decodebook, void *stream);
+
+/* Huffman::CompressPrimary + Serialize (ParallelHuffman/Huffman.hpp:61-262):
+ * writes the serialised Huffman block to d_out (capacity cap bytes) and its
+ * size to *size (host).  Synchronises the stream. */
+int mgb_huffman_compress(mgb_plan *plan, const uint16_t *d_sym, uint64_t n,
+                         const uint32_t *d_hist, uint64_t ocount,
+                         const uint64_t *d_oidx, const int64_t *d_oval,
+                         uint8_t *d_out, uint64_t cap, uint64_t *size,
+                         void *stream);
+/* Huffman::Deserialize + DecompressPrimary (Huffman.hpp:264-362).  Outlier
+ * arrays are returned as pointers into d_in. */
+int mgb_huffman_decompress(mgb_plan *plan, const uint8_t *d_in, uint64_t size,
+                           uint16_t *d_sym, uint64_t n, uint64_t *ocount,
+                           const uint64_t **d_oidx, const int64_t **d_oval,
+                           void *stream);
+
+/* ---- low level: Compressor<D,T>::Compress / Decompress --------------------
+ * (CompressionLowLevel/Compressor.hpp:193-272) on one sub-domain.  `norm` is
+ * in/out exactly as the reference's `T &norm`.  Synchronous. */
+int mgb_compress_lowlevel(mgb_plan *plan, const void *d_in, int ebtype,
+                          double tol, double s, double *norm, uint8_t *d_out,
+                          uint64_t cap, uint64_t *size, void *stream);
+int mgb_decompress_lowlevel(mgb_plan *plan, const uint8_t *d_in, uint64_t size,
+                            int ebtype, double tol, double s, double norm,
+                            void *d_out, void *stream);
+
+/* ---- high level: mgard_x::compress / mgard_x::decompress ------------------
+ * (include/compress_x.hpp:54-86,120-146; CompressionHighLevel.hpp:49-314,
+ * 379-594).  `in` and `*out` may be host or device pointers; the output is
+ * allocated in the memory space of the input (malloc / cudaMalloc) unless
+ * output_pre_allocated, in which case *out_size carries the capacity in.
+ * Writes/reads the reference's self-describing stream (Metadata.cpp). */
+int mgb_compress(int ndim, int dtype, const uint64_t *shape, double tol,
+                 double s, int ebtype, const void *in, void **out,
+                 size_t *out_size, const void *const *coords,
+                 const mgb_config *cfg, int output_pre_allocated);
+int mgb_decompress(const void *in, size_t in_size, void **out,
+                   const mgb_config *cfg, int output_pre_allocated,
+                   int *ndim, uint64_t *shape, int *dtype);
+/* Parse only the header (Metadata.cpp:475-739 infer_* helpers). */
+int mgb_peek_header(const void *in, size_t in_size, int *ndim, uint64_t *shape,
+                    int *dtype, int *ebtype, double *tol, double *s,
+                    double *norm, uint64_t *header_bytes);
+/* mgard_x::release_cache (compress_x.hpp:159) */
+void mgb_release_cache(void);
+
+/* sharded variant for one-process-per-GPU runs (no reference counterpart; the
+ * reference processes sub-domains serially, GPUPipelines.hpp:88-207).  Each
+ * rank compresses sub-domains [first, first+count) of the MaxDim partition
+ * with the caller-supplied global norm; the container of `u64 size|payload`
+ * records is written to d_out. */
+int mgb_compress_subdomains(int ndim, int dtype, const uint64_t *shape,
+                            double tol, double s, int ebtype, double norm,
+                            const void *d_in_first, uint64_t first,
+                            uint64_t count, const mgb_config *cfg,
+                            uint8_t *d_out, uint64_t cap, uint64_t *size);
+/* Serialised metadata for the whole (decomposed) domain, host buffer. */
+int mgb_write_header(int ndim, int dtype, const uint64_t *shape, double tol,
+                     double s, int ebtype, double norm,
+                     const void *const *coords, const mgb_config *cfg,
+                     uint8_t *out, uint64_t cap, uint64_t *size);
+
+/* kernel launch counter (bench.py's gpu_launches) */
+uint64_t mgb_launch_count(void);
+/* Per-kernel-family timing with CUDA events on the launching stream
+ * (bench.py's roofline leg).  enable(1) clears and starts, enable(0) stops;
+ * report(id) returns MGB_BAD_ARGUMENT past the last family. */
+void mgb_profile_enable(int on);
+int mgb_profile_report(int id, const char **name, unsigned long long *launches,
+                       double *total_ms, double *max_ms);
+const char *mgb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGARD_B200_H */

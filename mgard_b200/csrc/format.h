@@ -1,0 +1,22 @@
+// Internal: parsed / to-be-written stream header (host side).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "../../include/mgard_b200.h"
+
+struct mgb_header {
+  int ndim = 0;
+  int dtype = MGB_F32;
+  uint64_t shape[MGB_MAX_DIMS] = {1, 1, 1, 1, 1};
+  int ebtype = MGB_ABS;
+  double tol = 0, s = 0, norm = 0;
+  bool decomposed = false;
+  uint64_t dd_dim = 0, dd_size = 0;
+  int dict_size = 8192, block_size = 20480;
+  std::vector<std::vector<double>> coords; // empty: uniform grid
+};
+
+std::vector<uint8_t> mgb_encode_stream_header(const mgb_header &h);
+int mgb_parse_stream_header(const uint8_t *data, size_t size, mgb_header &h,
+                            uint64_t &total_bytes);

@@ -1,0 +1,847 @@
+// GPU Huffman: codebook construction, chunked encode, serialisation, decode
+// (sm_100a).  Stream format and code assignment are those of the reference
+// (include/mgard-x/Lossless/ParallelHuffman/*), so the bytes are identical
+// given identical symbols:
+//   codebook   GetCodebook.hpp:23-146, GenerateCL.hpp:29-520, GenerateCW.hpp:38-218
+//   encode     EncodeFixedLen.hpp:22-92 + Deflate.hpp:21-77 + Condense.hpp:14-86
+//   serialise  Huffman.hpp:130-262 (field order / alignment: RuntimeX/Utilities/Serializer.hpp:13-23)
+//   decode     Decode.hpp:66-116, Huffman.hpp:264-362
+//
+// Structure here: 16-bit symbols; the code-length generation runs in ONE
+// thread block (no cooperative grid syncs, no host round trips); encoding
+// computes every chunk's bit count, scans the word offsets on the device and
+// packs each chunk straight into its final place in the serialised block
+// (no fixed-length intermediate, no separate condense pass).
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+
+#include "plan.h"
+
+namespace {
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+// ------------------------------- codebook ----------------------------------
+struct CbWork {
+  // all arrays sized dict (global scratch)
+  u64 *keys_sorted;  // (freq << 32 | symbol), padded to pow2
+  unsigned *lfreq;   // non-zero freqs ascending
+  unsigned *CL;
+  int *lleader;
+  unsigned *ifreq;
+  int *ileader;
+  unsigned *tfreq; // temp (merged) arrays
+  int *tindex;
+  int *tleaf;
+  u64 *cw; // codewords in ascending-length order
+};
+
+__device__ __forceinline__ int modn(int a, int n) {
+  int r = a % n;
+  return r < 0 ? r + n : r;
+}
+
+// Single-block kernel.  d_codebook[dict], d_decodebook = first[64] entry[64] keys[dict].
+__global__ void __launch_bounds__(1024)
+codebook_kernel(const unsigned *__restrict__ hist, int dict, int npow2, CbWork w,
+                u64 *__restrict__ codebook, u64 *__restrict__ decodebook,
+                int *__restrict__ status_out) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ int s_front, s_rear, s_lcur, s_isize, s_curleaves, s_mfront, s_mrear,
+      s_templen, s_first_nz, s_continue;
+  __shared__ unsigned s_minfreq;
+  __shared__ int s_gs[66], s_ge[66], s_gl[66]; // CW groups
+  __shared__ u64 s_gbase[66];
+  __shared__ int s_ngroups;
+
+  // 1. sort (freq, symbol) ascending: bitonic sort in global scratch
+  u64 *key = w.keys_sorted;
+  for (int i = tid; i < npow2; i += nt)
+    key[i] = i < dict ? (((u64)hist[i] << 32) | (unsigned)i) : ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= npow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < npow2; i += nt) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          u64 a = key[i], b = key[ixj];
+          bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            key[i] = b;
+            key[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // 2. first non-zero index (GetFirstNonzeroIndex.hpp)
+  if (tid == 0)
+    s_first_nz = dict;
+  __syncthreads();
+  for (int i = tid; i < dict; i += nt) {
+    bool nzv = (key[i] >> 32) != 0;
+    bool prev_zero = i == 0 || (key[i - 1] >> 32) == 0;
+    if (nzv && prev_zero)
+      s_first_nz = i;
+  }
+  __syncthreads();
+  const int first_nz = s_first_nz;
+  const int n = dict - first_nz;
+  u64 *first = decodebook, *entry = decodebook + 64, *qkeys = decodebook + 128;
+  // keys: symbols by descending frequency (ReverseArray of the sorted qcode)
+  for (int i = tid; i < dict; i += nt) {
+    qkeys[i] = (unsigned)(key[dict - 1 - i] & 0xffffffffu);
+    codebook[i] = 0;
+  }
+  for (int i = tid; i < 64; i += nt) {
+    first[i] = ~0ull;
+    entry[i] = ~0ull;
+  }
+  if (n == 0) {
+    if (tid == 0)
+      *status_out = 1;
+    return;
+  }
+  // 3. GenerateCL
+  for (int i = tid; i < n; i += nt) {
+    w.lfreq[i] = (unsigned)(key[first_nz + i] >> 32);
+    w.CL[i] = 0;
+    w.lleader[i] = -1;
+  }
+  if (tid == 0) {
+    s_front = s_rear = s_lcur = s_isize = 0;
+    s_continue = 1;
+  }
+  __syncthreads();
+  while (s_continue) {
+    if (tid == 0) {
+      int lcur = s_lcur, front = s_front, rear = s_rear, isize = s_isize;
+      // Operation2 (GenerateCL.hpp:96-219)
+      unsigned mf[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      int ml[4] = {0, 0, 0, 0};
+      if (lcur < n) { mf[0] = w.lfreq[lcur]; ml[0] = 1; }
+      if (lcur < n - 1) { mf[1] = w.lfreq[lcur + 1]; ml[1] = 1; }
+      if (isize >= 1) { mf[2] = w.ifreq[front]; ml[2] = 0; }
+      if (isize >= 2) { mf[3] = w.ifreq[modn(front + 1, n)]; ml[3] = 0; }
+#define CSWAP(a, b)                                                            \
+  if (mf[a] > mf[b]) {                                                         \
+    unsigned tf = mf[a]; mf[a] = mf[b]; mf[b] = tf;                            \
+    int tl = ml[a]; ml[a] = ml[b]; ml[b] = tl;                                 \
+  }
+      CSWAP(1, 3) CSWAP(0, 2) CSWAP(0, 1) CSWAP(2, 3) CSWAP(1, 2)
+#undef CSWAP
+      unsigned minfreq = mf[0];
+      if (mf[1] < 0xffffffffu)
+        minfreq += mf[1];
+      w.ifreq[rear] = minfreq;
+      w.ileader[rear] = -1;
+      for (int k = 0; k < 2; k++) {
+        if (mf[k] < 0xffffffffu) {
+          if (ml[k]) {
+            w.lleader[lcur] = rear;
+            w.CL[lcur] += 1;
+            lcur++;
+          } else {
+            w.ileader[front] = rear;
+            front = modn(front + 1, n);
+          }
+        }
+      }
+      isize = modn(rear - front, n);
+      // Operation3: leaves (from lcur) with freq <= minFreq  (sorted => prefix)
+      int lo = lcur, hi = n;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (w.lfreq[mid] <= minfreq) lo = mid + 1; else hi = mid;
+      }
+      int curleaves = lo - lcur;
+      // Operation5 (GenerateCL.hpp:237-281)
+      int mrear = rear, mfront = front;
+      if ((curleaves + isize) % 2 == 0) {
+        front = rear;
+      } else {
+        // histogram[lNodesCur + curLeavesNum]: the reference reads one past
+        // the end of the frequency array when every remaining leaf was taken;
+        // the word that follows (the zero-initialised codebook on the device
+        // layout) is defined here as 0.
+        unsigned nextleaf = (lcur + curleaves < n) ? w.lfreq[lcur + curleaves] : 0u;
+        if (isize != 0 &&
+            (curleaves == 0 || nextleaf <= w.ifreq[modn(rear - 1, n)])) {
+          mrear = modn(mrear - 1, n);
+          front = modn(rear - 1, n);
+        } else {
+          front = rear;
+          --curleaves;
+        }
+      }
+      s_mfront = mfront;
+      s_mrear = mrear;
+      s_curleaves = curleaves;
+      s_minfreq = minfreq;
+      // leaves to merge start at the pre-advance lcur
+      s_lcur = lcur; // merge phase uses s_lcur as copy base
+      s_front = front;
+      s_rear = modn(rear + 1, n);
+      s_templen = curleaves + modn(mrear - mfront, n);
+    }
+    __syncthreads();
+    const int A = s_curleaves, cbase = s_lcur, mfront = s_mfront;
+    const int B = modn(s_mrear - mfront, n);
+    const int templen = s_templen;
+    const int rear = s_rear;
+    if (templen > 0) {
+      // merge by rank (leaf first on ties, GenerateCL.hpp:484)
+      for (int k = tid; k < A; k += nt) {
+        unsigned f = w.lfreq[cbase + k];
+        int lo = 0, hi = B; // number of inodes with freq < f
+        while (lo < hi) {
+          int mid = (lo + hi) >> 1;
+          if (w.ifreq[modn(mfront + mid, n)] < f) lo = mid + 1; else hi = mid;
+        }
+        int pos = k + lo;
+        w.tfreq[pos] = f;
+        w.tindex[pos] = cbase + k;
+        w.tleaf[pos] = 1;
+      }
+      for (int m = tid; m < B; m += nt) {
+        int bi = modn(mfront + m, n);
+        unsigned f = w.ifreq[bi];
+        int lo = 0, hi = A; // number of leaves with freq <= f
+        while (lo < hi) {
+          int mid = (lo + hi) >> 1;
+          if (w.lfreq[cbase + mid] <= f) lo = mid + 1; else hi = mid;
+        }
+        int pos = m + lo;
+        w.tfreq[pos] = f;
+        w.tindex[pos] = bi;
+        w.tleaf[pos] = 0;
+      }
+      __syncthreads();
+      // Operation12: meld
+      for (int i = tid; i < templen / 2; i += nt) {
+        int ind = modn(rear + i, n);
+        w.ifreq[ind] = w.tfreq[2 * i] + w.tfreq[2 * i + 1];
+        w.ileader[ind] = -1;
+        for (int c = 0; c < 2; c++) {
+          int ti = w.tindex[2 * i + c];
+          if (w.tleaf[2 * i + c]) {
+            w.lleader[ti] = ind;
+            w.CL[ti] += 1;
+          } else {
+            w.ileader[ti] = ind;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // Operation14: update leaders
+    for (int i = tid; i < n; i += nt) {
+      int ll = w.lleader[i];
+      if (ll != -1) {
+        int il = w.ileader[ll];
+        if (il != -1) {
+          w.lleader[i] = il;
+          w.CL[i] += 1;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      s_lcur = s_lcur + s_curleaves;
+      s_rear = modn(s_rear + templen / 2, n);
+      s_isize = modn(s_rear - s_front, n);
+      s_continue = (s_lcur < n) || (s_isize > 1);
+    }
+    __syncthreads();
+  }
+  // 4. GenerateCW.  Work in ascending-length order: r = n-1-k (k ascending freq)
+  // groups of equal length
+  if (tid == 0) {
+    int ng = 0;
+    int start = 0;
+    int ok = 0;
+    unsigned maxcl = w.CL[0]; // least frequent symbol has the longest code
+    if (maxcl > 56)
+      ok = 2; // GetCodebook.hpp:111-121: cannot store the codeword
+    for (int r = 0; r < n; r++) {
+      unsigned cl = w.CL[n - 1 - r];
+      bool last = (r == n - 1) || (w.CL[n - 1 - (r + 1)] != cl);
+      if (last) {
+        if (ng < 66) {
+          s_gs[ng] = start;
+          s_ge[ng] = r;
+          s_gl[ng] = (int)cl;
+        }
+        ng++;
+        start = r + 1;
+      }
+    }
+    if (ng > 64)
+      ok = 2;
+    s_ngroups = ng > 64 ? 0 : ng;
+    u64 base = 0;
+    for (int gi = 0; gi < s_ngroups; gi++) {
+      s_gbase[gi] = base;
+      if (gi + 1 < s_ngroups) {
+        u64 top = base + (u64)(s_ge[gi] - s_gs[gi]);
+        base = (top + 1) << (s_gl[gi + 1] - s_gl[gi]);
+      }
+    }
+    // first / entry
+    if (s_ngroups > 0) {
+      int L0 = s_gl[0];
+      for (int i = 0; i < L0; i++) {
+        first[i] = ~0ull;
+        entry[i] = 0;
+      }
+      entry[L0] = 0;
+      if (n == 1) {
+        // the loop of GenerateCW never runs: Operation2 only
+        first[L0] = 0ull ^ ((1ull << L0) - 1);
+        if (L0 + 1 < 64)
+          entry[L0 + 1] = 1;
+      } else {
+        u64 cum = 0;
+        for (int gi = 0; gi < s_ngroups; gi++) {
+          int Lg = s_gl[gi];
+          int Lnext = gi + 1 < s_ngroups ? s_gl[gi + 1] : 64;
+          u64 top = s_gbase[gi] + (u64)(s_ge[gi] - s_gs[gi]);
+          first[Lg] = top ^ ((1ull << Lg) - 1);
+          cum += (u64)(s_ge[gi] - s_gs[gi] + 1);
+          for (int i = Lg + 1; i < Lnext; i++) {
+            first[i] = ~0ull;
+            entry[i] = cum;
+          }
+          if (Lnext < 64)
+            entry[Lnext] = cum;
+        }
+      }
+    }
+    *status_out = ok;
+  }
+  __syncthreads();
+  for (int gi = 0; gi < s_ngroups; gi++) {
+    const int gs = s_gs[gi], ge = s_ge[gi], Lg = s_gl[gi];
+    const u64 base = s_gbase[gi];
+    for (int r = gs + tid; r <= ge; r += nt) {
+      u64 code = base + (u64)(ge - r);
+      u64 cwv = (code | ((u64)(Lg & 0xff) << 56)) ^ ((1ull << Lg) - 1);
+      // r-th most frequent symbol
+      unsigned symbol = (unsigned)(key[dict - 1 - r] & 0xffffffffu);
+      codebook[symbol] = cwv;
+    }
+  }
+}
+
+// ------------------------------- encode ------------------------------------
+
+// bits per chunk (sum of code lengths) and words per chunk
+__global__ void __launch_bounds__(256)
+chunk_bits_kernel(const uint16_t *__restrict__ sym, u64 n, int chunk,
+                  const u64 *__restrict__ codebook, int dict,
+                  u64 *__restrict__ bits) {
+  extern __shared__ unsigned char s_len[];
+  for (int i = threadIdx.x; i < dict; i += blockDim.x)
+    s_len[i] = (unsigned char)(codebook[i] >> 56);
+  __syncthreads();
+  const u64 nchunk = (n - 1) / chunk + 1;
+  for (u64 c = blockIdx.x; c < nchunk; c += gridDim.x) {
+    u64 lo = c * (u64)chunk;
+    u64 hi = min(n, lo + (u64)chunk);
+    unsigned total = 0; // <= 65536 * 56 fits; chunk may be larger: use u64 below
+    u64 tot64 = 0;
+    for (u64 i = lo + threadIdx.x; i < hi; i += blockDim.x)
+      total += s_len[sym[i]];
+    tot64 = total;
+    for (int o = 16; o > 0; o >>= 1)
+      tot64 += __shfl_xor_sync(0xffffffffu, tot64, o);
+    __shared__ u64 s_part[8];
+    if ((threadIdx.x & 31) == 0)
+      s_part[threadIdx.x >> 5] = tot64;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      u64 t = 0;
+      for (int k = 0; k < 8; k++)
+        t += s_part[k];
+      bits[c] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// exclusive scan of words per chunk; writes the serialised metadata too.
+// scal[1] = total words, scal[2] = overflow flag
+__global__ void __launch_bounds__(1024)
+chunk_scan_kernel(const u64 *__restrict__ bits, u64 nchunk, u64 *__restrict__ woff,
+                  u64 *__restrict__ scal, u64 fixed_bytes, u64 cap,
+                  const u64 *__restrict__ ocount_ptr, u64 ocount_fixed, u64 ocap) {
+  __shared__ u64 s_warp[32];
+  __shared__ u64 s_carry;
+  if (threadIdx.x == 0)
+    s_carry = 0;
+  __syncthreads();
+  for (u64 base = 0; base < nchunk; base += blockDim.x) {
+    u64 i = base + threadIdx.x;
+    u64 wv = 0;
+    if (i < nchunk) {
+      u64 b = bits[i];
+      wv = (b - 1) / 64 + 1; // Huffman.hpp:150 (wraps for b == 0 like the reference)
+    }
+    u64 x = wv;
+    for (int o = 1; o < 32; o <<= 1) {
+      u64 y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o)
+        x += y;
+    }
+    if ((threadIdx.x & 31) == 31)
+      s_warp[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      u64 v = s_warp[threadIdx.x];
+      for (int o = 1; o < 32; o <<= 1) {
+        u64 y = __shfl_up_sync(0xffffffffu, v, o);
+        if (threadIdx.x >= o)
+          v += y;
+      }
+      s_warp[threadIdx.x] = v;
+    }
+    __syncthreads();
+    u64 wprefix = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0;
+    u64 incl = s_carry + wprefix + x;
+    if (i < nchunk)
+      woff[i] = incl - wv;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1)
+      s_carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    u64 total = s_carry;
+    u64 oc = ocount_ptr ? *ocount_ptr : ocount_fixed;
+    scal[1] = total;
+    u64 need = fixed_bytes + 8 * total + 8 + 16 * oc;
+    // 1: output too small; 2: the outlier buffer overflowed (the caller grows
+    // it and quantizes again) -- either way nothing more is written
+    scal[2] = oc > ocap ? 2 : (need > cap ? 1 : 0);
+    scal[3] = need;
+    woff[nchunk] = total;
+  }
+}
+
+template <bool CB_SHARED>
+__global__ void __launch_bounds__(256)
+encode_kernel(const uint16_t *__restrict__ sym, u64 n, int chunk,
+              const u64 *__restrict__ codebook, int dict,
+              const u64 *__restrict__ woff, const u64 *__restrict__ scal,
+              u64 *__restrict__ ddata) {
+  constexpr int PER = 8, NT = 256, TILE = PER * NT;
+  constexpr int TILE_WORDS = TILE * 56 / 64 + 4;
+  extern __shared__ u64 smem[];
+  u64 *s_cb = smem;                         // dict (if CB_SHARED)
+  u64 *s_out = smem + (CB_SHARED ? dict : 0); // TILE_WORDS
+  __shared__ unsigned s_scan[8];
+  __shared__ unsigned s_tilebits;
+  if (scal[2])
+    return; // output too small: nothing is written
+  if (CB_SHARED) {
+    for (int i = threadIdx.x; i < dict; i += NT)
+      s_cb[i] = codebook[i];
+  }
+  const u64 *cb = CB_SHARED ? s_cb : codebook;
+  const u64 nchunk = (n - 1) / chunk + 1;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (u64 c = blockIdx.x; c < nchunk; c += gridDim.x) {
+    const u64 lo = c * (u64)chunk;
+    const u64 hi = min(n, lo + (u64)chunk);
+    u64 *dst = ddata + woff[c];
+    for (int i = tid; i < TILE_WORDS; i += NT)
+      s_out[i] = 0;
+    __syncthreads();
+    unsigned carry_bits = 0; // bits already in s_out[0]
+    u64 wdone = 0;
+    for (u64 t0 = lo; t0 < hi; t0 += TILE) {
+      // load up to PER symbols
+      u64 s0 = t0 + (u64)tid * PER;
+      u64 cw[PER];
+      unsigned mybits = 0;
+#pragma unroll
+      for (int k = 0; k < PER; k++) {
+        u64 idx = s0 + k;
+        cw[k] = idx < hi ? cb[sym[idx]] : 0ull;
+        mybits += (unsigned)(cw[k] >> 56);
+      }
+      // block exclusive scan of mybits
+      unsigned x = mybits;
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o)
+          x += y;
+      }
+      if (lane == 31)
+        s_scan[wid] = x;
+      __syncthreads();
+      unsigned wpre = 0, tot = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        unsigned v = s_scan[k];
+        if (k < wid)
+          wpre += v;
+        tot += v;
+      }
+      unsigned pos = carry_bits + wpre + x - mybits;
+      // pack
+#pragma unroll
+      for (int k = 0; k < PER; k++) {
+        unsigned len = (unsigned)(cw[k] >> 56);
+        if (len) {
+          u64 code = cw[k] & 0x00ffffffffffffffull;
+          unsigned wi = pos >> 6, off = pos & 63;
+          unsigned room = 64 - off;
+          if (len <= room) {
+            atomicOr(&s_out[wi], code << (room - len));
+          } else {
+            atomicOr(&s_out[wi], code >> (len - room));
+            atomicOr(&s_out[wi + 1], code << (64 - (len - room)));
+          }
+          pos += len;
+        }
+      }
+      __syncthreads();
+      unsigned tile_bits = carry_bits + tot;
+      unsigned nfull = tile_bits >> 6;
+      for (unsigned i = tid; i < nfull; i += NT)
+        dst[wdone + i] = s_out[i];
+      u64 partial = s_out[nfull];
+      __syncthreads();
+      for (unsigned i = tid; i <= nfull + 1 && i < (unsigned)TILE_WORDS; i += NT)
+        s_out[i] = 0;
+      __syncthreads();
+      if (tid == 0)
+        s_out[0] = partial;
+      wdone += nfull;
+      carry_bits = tile_bits & 63;
+      __syncthreads();
+    }
+    if (carry_bits && tid == 0)
+      dst[wdone] = s_out[0];
+    __syncthreads();
+  }
+}
+
+// serialised scalar fields + chunk metadata (Huffman.hpp:163-239)
+__global__ void serialize_meta_kernel(unsigned char *__restrict__ out, u64 n, int dict,
+                                      int chunk, u64 nchunk,
+                                      const u64 *__restrict__ bits,
+                                      const u64 *__restrict__ woff,
+                                      const u64 *__restrict__ decodebook,
+                                      const u64 *__restrict__ scal, u64 off_ddata,
+                                      const u64 *__restrict__ ocount_ptr, u64 ocount_fixed,
+                                      const uint64_t *__restrict__ oidx,
+                                      const i64 *__restrict__ oval) {
+  if (scal[2])
+    return;
+  u64 *o64 = (u64 *)out;
+  const u64 gt = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 gs = (u64)gridDim.x * blockDim.x;
+  const u64 total_words = scal[1];
+  const u64 oc = ocount_ptr ? *ocount_ptr : ocount_fixed;
+  if (gt == 0) {
+    o64[0] = n;
+    ((int *)out)[2] = dict;
+    ((int *)out)[3] = chunk;
+    o64[2] = 2 * nchunk;
+    o64[3 + 2 * nchunk] = 8ull * 128 + 8ull * dict;
+    o64[off_ddata / 8 - 1] = total_words;
+    o64[off_ddata / 8 + total_words] = oc;
+  }
+  for (u64 i = gt; i < nchunk; i += gs) {
+    o64[3 + i] = bits[i];
+    o64[3 + nchunk + i] = woff[i];
+  }
+  u64 *db = o64 + 4 + 2 * nchunk;
+  for (u64 i = gt; i < 128 + (u64)dict; i += gs)
+    db[i] = decodebook[i];
+  u64 *oo = o64 + off_ddata / 8 + total_words + 1;
+  for (u64 i = gt; i < oc; i += gs) {
+    oo[i] = oidx[i];
+    oo[oc + i] = (u64)oval[i];
+  }
+}
+
+// ------------------------------- decode ------------------------------------
+// One thread per chunk (the stream is sequential inside a chunk); canonical
+// decode with first/entry/keys exactly as Decode.hpp:66-116.
+__global__ void __launch_bounds__(128)
+decode_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__restrict__ bits,
+              const u64 *__restrict__ woff, u64 nchunk, int chunk, u64 n,
+              const u64 *__restrict__ decodebook, int dict, uint16_t *__restrict__ out) {
+  extern __shared__ u64 s_db[]; // first[64] entry[64] + keys (u16) packed after
+  u64 *s_first = s_db, *s_entry = s_db + 64;
+  uint16_t *s_keys = (uint16_t *)(s_db + 128);
+  for (int i = threadIdx.x; i < 128; i += blockDim.x)
+    s_db[i] = decodebook[i];
+  for (int i = threadIdx.x; i < dict; i += blockDim.x)
+    s_keys[i] = (uint16_t)decodebook[128 + i];
+  __syncthreads();
+  int lmin = 1;
+  while (lmin < 63 && s_first[lmin] == ~0ull)
+    lmin++;
+  u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchunk)
+    return;
+  const u64 total_bw = bits[c];
+  const u64 w0 = woff[c];
+  const u64 nw = (total_bw - 1) / 64 + 1;
+  const u64 *src = ddata + w0;
+  uint16_t *dst = out + c * (u64)chunk;
+  u64 nsym_max = min((u64)chunk, n - c * (u64)chunk);
+  u64 wi = 0;
+  u64 cur = src[0];
+  u64 nxt = (1 < nw) ? src[1] : 0ull;
+  unsigned used = 0;
+  u64 consumed = 0, produced = 0;
+  while (consumed < total_bw && produced < nsym_max) {
+    u64 window = used ? ((cur << used) | (nxt >> (64 - used))) : cur;
+    int l = lmin;
+    u64 v = window >> (64 - l);
+    while (v < s_first[l] && l < 63) {
+      l++;
+      v = window >> (64 - l);
+    }
+    u64 ki = s_entry[l] + v - s_first[l];
+    dst[produced++] = ki < (u64)dict ? s_keys[ki] : (uint16_t)0;
+    consumed += l;
+    used += l;
+    if (used >= 64) {
+      used -= 64;
+      wi++;
+      cur = nxt;
+      nxt = (wi + 1 < nw) ? src[wi + 1] : 0ull;
+    }
+  }
+}
+
+// decodebook_size, ddata word count and outlier count of a serialised block
+// (Huffman.hpp:293-312); ~0 marks a truncated stream.
+__global__ void parse_sizes_kernel(const unsigned char *__restrict__ p, u64 off, u64 size,
+                                   u64 dict, u64 *__restrict__ dst) {
+  dst[0] = dst[1] = dst[2] = ~0ull;
+  if (off + 8 > size)
+    return;
+  u64 db = *(const u64 *)(p + off);
+  dst[0] = db;
+  if (db != 1024 + 8 * dict || off + 8 + db + 8 > size)
+    return;
+  u64 o2 = off + 8 + db;
+  u64 tw = *(const u64 *)(p + o2);
+  if (tw > (size - o2 - 8) / 8 || o2 + 8 + 8 * tw + 8 > size)
+    return;
+  dst[1] = tw;
+  dst[2] = *(const u64 *)(p + o2 + 8 + 8 * tw);
+}
+
+int ensure_huff_workspace(mgb_plan *p) {
+  if (p->d_codebook)
+    return MGB_SUCCESS;
+  const int dict = p->cfg.huff_dict_size;
+  const u64 nchunk = (p->N - 1) / p->cfg.huff_block_size + 1;
+  int npow2 = 1;
+  while (npow2 < dict)
+    npow2 <<= 1;
+  MGB_CUDA_CHECK(cudaMalloc(&p->d_codebook, dict * sizeof(u64)));
+  MGB_CUDA_CHECK(cudaMalloc(&p->d_decodebook, (128 + dict) * sizeof(u64)));
+  MGB_CUDA_CHECK(cudaMalloc(&p->d_chunk_bits, nchunk * sizeof(u64)));
+  MGB_CUDA_CHECK(cudaMalloc(&p->d_chunk_woff, (nchunk + 1) * sizeof(u64)));
+  MGB_CUDA_CHECK(cudaMalloc(&p->d_scalars, 16 * sizeof(u64)));
+  MGB_CUDA_CHECK(cudaMemset(p->d_scalars, 0, 16 * sizeof(u64)));
+  size_t cbw = npow2 * sizeof(u64) + (size_t)dict * (9 * 4 + 8) + 256;
+  MGB_CUDA_CHECK(cudaMalloc(&p->d_cbwork, cbw));
+  MGB_CUDA_CHECK(cudaMallocHost(&p->h_pinned, 16 * sizeof(u64)));
+  return MGB_SUCCESS;
+}
+
+} // namespace
+
+int mgb_huff_workspace(mgb_plan *p) { return ensure_huff_workspace(p); }
+
+extern "C" int mgb_codebook(mgb_plan *p, const uint32_t *d_hist, uint64_t *d_codebook,
+                            uint64_t *d_decodebook, void *stream) {
+  if (!p || !d_hist || !d_codebook || !d_decodebook)
+    return MGB_BAD_ARGUMENT;
+  int rc = ensure_huff_workspace(p);
+  if (rc)
+    return rc;
+  const int dict = p->cfg.huff_dict_size;
+  int npow2 = 1;
+  while (npow2 < dict)
+    npow2 <<= 1;
+  CbWork w;
+  unsigned char *b = p->d_cbwork;
+  w.keys_sorted = (u64 *)b; b += (size_t)npow2 * 8;
+  w.cw = (u64 *)b; b += (size_t)dict * 8;
+  w.lfreq = (unsigned *)b; b += (size_t)dict * 4;
+  w.CL = (unsigned *)b; b += (size_t)dict * 4;
+  w.lleader = (int *)b; b += (size_t)dict * 4;
+  w.ifreq = (unsigned *)b; b += (size_t)dict * 4;
+  w.ileader = (int *)b; b += (size_t)dict * 4;
+  w.tfreq = (unsigned *)b; b += (size_t)dict * 4;
+  w.tindex = (int *)b; b += (size_t)dict * 4;
+  w.tleaf = (int *)b; b += (size_t)dict * 4;
+  MGB_LAUNCH(MGB_K_CODEBOOK, (cudaStream_t)stream,
+             (codebook_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+                 d_hist, dict, npow2, w, (u64 *)d_codebook, (u64 *)d_decodebook,
+                 (int *)(p->d_scalars + 8))));
+  MGB_CUDA_CHECK(cudaGetLastError());
+  return MGB_SUCCESS;
+}
+
+// Internal: everything up to (not including) the final size read-back.
+// ocount is read from d_ocount_ptr on the device when non-null.
+int mgb_huffman_compress_async(mgb_plan *p, const uint16_t *d_sym, uint64_t n,
+                               const uint32_t *d_hist,
+                               const unsigned long long *d_ocount_ptr,
+                               uint64_t ocount_fixed, const uint64_t *d_oidx,
+                               const int64_t *d_oval, uint8_t *d_out, uint64_t cap,
+                               cudaStream_t st) {
+  int rc = ensure_huff_workspace(p);
+  if (rc)
+    return rc;
+  const int dict = p->cfg.huff_dict_size, chunk = p->cfg.huff_block_size;
+  const u64 nchunk = (n - 1) / chunk + 1;
+  rc = mgb_codebook(p, d_hist, (uint64_t *)p->d_codebook, (uint64_t *)p->d_decodebook, st);
+  if (rc)
+    return rc;
+  const u64 fixed = 8 + 4 + 4 + 8 + 16 * nchunk + 8 + (1024 + 8ull * dict) + 8;
+  u64 *scal = (u64 *)p->d_scalars;
+  unsigned gb = (unsigned)std::min<u64>(nchunk, 148 * 8);
+  MGB_LAUNCH(MGB_K_CHUNK_BITS, st,
+             (chunk_bits_kernel<<<gb, 256, dict, st>>>(d_sym, n, chunk, p->d_codebook, dict,
+                                                      (u64 *)p->d_chunk_bits)));
+  MGB_LAUNCH(MGB_K_CHUNK_SCAN, st,
+             (chunk_scan_kernel<<<1, 1024, 0, st>>>((u64 *)p->d_chunk_bits, nchunk,
+                                                   (u64 *)p->d_chunk_woff, scal, fixed, cap,
+                                                   (const u64 *)d_ocount_ptr, ocount_fixed,
+                                                   d_ocount_ptr ? p->outlier_cap : ~0ull)));
+  u64 *ddata = (u64 *)(d_out + fixed);
+  constexpr int TILE_WORDS = 8 * 256 * 56 / 64 + 4;
+  if (dict <= 16384) {
+    size_t smem = ((size_t)dict + TILE_WORDS) * 8;
+    cudaFuncSetAttribute(encode_kernel<true>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    MGB_LAUNCH(MGB_K_ENCODE, st,
+               (encode_kernel<true><<<gb, 256, smem, st>>>(d_sym, n, chunk, p->d_codebook, dict,
+                                                          (u64 *)p->d_chunk_woff, scal, ddata)));
+  } else {
+    size_t smem = (size_t)TILE_WORDS * 8;
+    MGB_LAUNCH(MGB_K_ENCODE, st,
+               (encode_kernel<false><<<gb, 256, smem, st>>>(d_sym, n, chunk, p->d_codebook, dict,
+                                                           (u64 *)p->d_chunk_woff, scal, ddata)));
+  }
+  MGB_LAUNCH(MGB_K_SERIALIZE, st,
+             (serialize_meta_kernel<<<148, 256, 0, st>>>(
+                 d_out, n, dict, chunk, nchunk, (u64 *)p->d_chunk_bits, (u64 *)p->d_chunk_woff,
+                 p->d_decodebook, scal, fixed, (const u64 *)d_ocount_ptr, ocount_fixed, d_oidx,
+                 (const i64 *)d_oval)));
+  MGB_CUDA_CHECK(cudaGetLastError());
+  return MGB_SUCCESS;
+}
+
+// reads back {need bytes, overflow flag, codebook status}; synchronises.
+int mgb_huffman_finish(mgb_plan *p, uint64_t *size, cudaStream_t st) {
+  MGB_CUDA_CHECK(cudaMemcpyAsync(p->h_pinned, p->d_scalars, 16 * sizeof(u64),
+                                 cudaMemcpyDeviceToHost, st));
+  MGB_CUDA_CHECK(cudaStreamSynchronize(st));
+  int cbstatus = (int)(p->h_pinned[8] & 0xffffffffu);
+  if (cbstatus == 2)
+    return MGB_FAILURE;
+  *size = p->h_pinned[3];
+  if (p->h_pinned[2] == 1)
+    return MGB_OUTPUT_TOO_LARGE;
+  if (p->h_pinned[2] == 2)
+    return MGB_FAILURE; // outlier buffer overflow: see mgb_compress_lowlevel
+  return MGB_SUCCESS;
+}
+
+extern "C" int mgb_huffman_compress(mgb_plan *p, const uint16_t *d_sym, uint64_t n,
+                                    const uint32_t *d_hist, uint64_t ocount,
+                                    const uint64_t *d_oidx, const int64_t *d_oval,
+                                    uint8_t *d_out, uint64_t cap, uint64_t *size,
+                                    void *stream) {
+  if (!p || !d_sym || !d_hist || !d_out || !size || n == 0)
+    return MGB_BAD_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = mgb_huffman_compress_async(p, d_sym, n, d_hist, nullptr, ocount, d_oidx,
+                                      d_oval, d_out, cap, st);
+  if (rc)
+    return rc;
+  return mgb_huffman_finish(p, size, st);
+}
+
+extern "C" int mgb_huffman_decompress(mgb_plan *p, const uint8_t *d_in, uint64_t size,
+                                      uint16_t *d_sym, uint64_t n, uint64_t *ocount,
+                                      const uint64_t **d_oidx, const int64_t **d_oval,
+                                      void *stream) {
+  if (!p || !d_in || !d_sym || size < 32)
+    return MGB_BAD_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_huff_workspace(p);
+  if (rc)
+    return rc;
+  // Huffman.hpp:264-320: scalar fields come back to the host to size the views
+  unsigned char head[24];
+  MGB_CUDA_CHECK(cudaMemcpyAsync(head, d_in, 24, cudaMemcpyDeviceToHost, st));
+  MGB_CUDA_CHECK(cudaStreamSynchronize(st));
+  u64 primary_count, huffmeta;
+  int dict, chunk;
+  memcpy(&primary_count, head, 8);
+  memcpy(&dict, head + 8, 4);
+  memcpy(&chunk, head + 12, 4);
+  memcpy(&huffmeta, head + 16, 8);
+  if (primary_count != n || dict < 2 || dict > 65536 || chunk < 1)
+    return MGB_BAD_STREAM;
+  const u64 nchunk = (n - 1) / chunk + 1;
+  if (huffmeta != 2 * nchunk)
+    return MGB_BAD_STREAM;
+  u64 off = 24;
+  const u64 *bits = (const u64 *)(d_in + off);
+  off += 8 * nchunk;
+  const u64 *woff = (const u64 *)(d_in + off);
+  off += 8 * nchunk;
+  if (off + 8 > size)
+    return MGB_BAD_STREAM;
+  // remaining size fields are read on the device in one go
+  u64 *tmp = (u64 *)p->d_scalars + 12;
+  MGB_LAUNCH(MGB_K_PARSE, st, (parse_sizes_kernel<<<1, 1, 0, st>>>(d_in, off, size, (u64)dict, tmp)));
+  u64 hs[3];
+  MGB_CUDA_CHECK(cudaMemcpyAsync(hs, tmp, 24, cudaMemcpyDeviceToHost, st));
+  MGB_CUDA_CHECK(cudaStreamSynchronize(st));
+  const u64 dbsize = hs[0], total_words = hs[1], oc = hs[2];
+  if (dbsize != 1024 + 8ull * dict || total_words == ~0ull || oc == ~0ull)
+    return MGB_BAD_STREAM;
+  off += 8;
+  const u64 *decodebook = (const u64 *)(d_in + off);
+  off += dbsize + 8;
+  const u64 *ddata = (const u64 *)(d_in + off);
+  off += 8 * total_words + 8;
+  if (off + 16 * oc > size)
+    return MGB_BAD_STREAM;
+  if (ocount)
+    *ocount = oc;
+  if (d_oidx)
+    *d_oidx = (const uint64_t *)(d_in + off);
+  if (d_oval)
+    *d_oval = (const int64_t *)(d_in + off + 8 * oc);
+  size_t smem = 128 * 8 + (size_t)dict * 2;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+  unsigned blocks = (unsigned)((nchunk + 127) / 128);
+  MGB_LAUNCH(MGB_K_DECODE, st,
+             (decode_kernel<<<blocks, 128, smem, st>>>(ddata, total_words, bits, woff, nchunk,
+                                                      chunk, n, decodebook, dict, d_sym)));
+  MGB_CUDA_CHECK(cudaGetLastError());
+  return MGB_SUCCESS;
+}

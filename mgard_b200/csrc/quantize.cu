@@ -1,0 +1,515 @@
+// Norms, level-weighted quantizer fused with the Huffman histogram, and the
+// inverse (sm_100a).  Compile with -fmad=false (bit-exact contract).
+//
+//   norm        reference norm_calculator            (CompressionLowLevel/NormCalculator.hpp:13-83)
+//   quantizers  reference LinearQuantizer::CalcQuantizers (Quantization/LinearQuantization.hpp:495-545)
+//   quantize    reference LevelwiseLinearQuantizerKernel<QUANTIZE>   (:148-248)
+//               + HistogramKernel (Lossless/ParallelHuffman/Histogram.hpp:15-118)
+//   dequantize  reference OutlierRestoreKernel + <DEQUANTIZE>       (:251-264,304-350)
+//
+// Differences in shape, not in results: symbols are 16 bit (dictionary <= 65536)
+// instead of int64, the histogram is accumulated by the same pass that
+// quantizes, and nothing round-trips through the host.
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "plan.h"
+
+namespace {
+
+typedef long long i64;
+
+struct QParams {
+  int D;
+  int dict;
+  int calc_level;
+  int L;
+  unsigned n[5];
+  unsigned rows;
+  const int *marks;
+  unsigned long long marks_width;
+  // per level: quantizer (reciprocal for quantize), volume factor
+  double q[MGB_MAX_LEVELS];
+  double vol[MGB_MAX_LEVELS];
+};
+
+template <typename T> struct Tables {
+  T q[MGB_MAX_LEVELS];
+  T vol[MGB_MAX_LEVELS];
+};
+
+template <typename T> __device__ __forceinline__ T absT(T x) { return fabs(x); }
+template <> __device__ __forceinline__ float absT<float>(float x) { return fabsf(x); }
+
+template <typename T>
+__device__ __forceinline__ long long quantize_one(T t, T q, T vol, int dict) {
+  // LinearQuantization.hpp:203-208
+  T x = copysign((T)0.5 + absT(t * q * vol), t);
+  long long qi = (long long)x;
+  return qi + dict / 2;
+}
+
+// shared-memory histogram add with warp aggregation of equal bins
+__device__ __forceinline__ void hist_add(unsigned *sh, unsigned bin, bool valid) {
+  unsigned active = __ballot_sync(0xffffffffu, valid);
+  if (!valid)
+    return;
+  unsigned peers = __match_any_sync(active, bin);
+  int leader = __ffs(peers) - 1;
+  if ((threadIdx.x & 31) == leader)
+    atomicAdd(&sh[bin], (unsigned)__popc(peers));
+}
+
+// warp-aggregated append of outliers (one atomic per warp; ascending index
+// order inside a warp).  Must be called by all 32 lanes.
+__device__ __forceinline__ void
+outlier_append(bool is_out, unsigned long long idx, long long qi,
+               unsigned long long *__restrict__ ocount, uint64_t *__restrict__ oidx,
+               i64 *__restrict__ oval, unsigned long long ocap) {
+  unsigned m = __ballot_sync(0xffffffffu, is_out);
+  if (m == 0)
+    return;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  unsigned long long base = 0;
+  if (lane == leader)
+    base = atomicAdd(ocount, (unsigned long long)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (is_out) {
+    unsigned long long k = base + __popc(m & ((1u << lane) - 1));
+    if (k < ocap) {
+      oidx[k] = idx;
+      oval[k] = qi;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+quantize_linear_kernel(const T *__restrict__ v, i64 N, T q, T vol, int dict,
+                       uint16_t *__restrict__ sym, unsigned *__restrict__ ghist,
+                       unsigned long long *__restrict__ ocount,
+                       uint64_t *__restrict__ oidx, i64 *__restrict__ oval,
+                       unsigned long long ocap) {
+  extern __shared__ unsigned sh[];
+  for (int i = threadIdx.x; i < dict; i += blockDim.x)
+    sh[i] = 0;
+  __syncthreads();
+  i64 stride = (i64)gridDim.x * blockDim.x;
+  i64 nround = (N + stride - 1) / stride * stride;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    bool valid = i < N;
+    unsigned s = 0;
+    long long qi = 0;
+    bool is_out = false;
+    if (valid) {
+      qi = quantize_one<T>(v[i], q, vol, dict);
+      if (qi >= 0 && qi < dict)
+        s = (unsigned)qi;
+      else
+        is_out = true;
+      sym[i] = (uint16_t)s;
+    }
+    outlier_append(is_out, (unsigned long long)i, qi, ocount, oidx, oval, ocap);
+    hist_add(sh, s, valid);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < dict; i += blockDim.x) {
+    unsigned c = sh[i];
+    if (c)
+      atomicAdd(&ghist[i], c);
+  }
+}
+
+// s-norm variant: level = max_d level_marks[d][idx_d]; blocks own rows.
+template <typename T>
+__global__ void __launch_bounds__(256)
+quantize_level_kernel(const QParams p, const Tables<T> tb, const T *__restrict__ v,
+                      uint16_t *__restrict__ sym, unsigned *__restrict__ ghist,
+                      unsigned long long *__restrict__ ocount,
+                      uint64_t *__restrict__ oidx, i64 *__restrict__ oval,
+                      unsigned long long ocap) {
+  extern __shared__ unsigned sh[];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i < p.dict; i += blockDim.x * blockDim.y)
+    sh[i] = 0;
+  __syncthreads();
+  const int D = p.D;
+  const unsigned nf = p.n[D - 1];
+  for (unsigned row0 = blockIdx.x * blockDim.y; row0 < p.rows;
+       row0 += gridDim.x * blockDim.y) {
+    unsigned row = row0 + threadIdx.y;
+    bool rvalid = row < p.rows;
+    int lvl = 0;
+    unsigned rem = rvalid ? row : 0;
+    for (int d = D - 2; d >= 0; d--) {
+      unsigned i = rem % p.n[d];
+      rem /= p.n[d];
+      lvl = max(lvl, p.marks[(size_t)d * p.marks_width + i]);
+    }
+    i64 base = (i64)row * nf;
+    unsigned nfr = (nf + blockDim.x - 1) / blockDim.x * blockDim.x;
+    for (unsigned f = threadIdx.x; f < nfr; f += blockDim.x) {
+      bool valid = rvalid && f < nf;
+      unsigned s = 0;
+      long long qi = 0;
+      bool is_out = false;
+      if (valid) {
+        int l = max(lvl, p.marks[(size_t)(D - 1) * p.marks_width + f]);
+        qi = quantize_one<T>(v[base + f], tb.q[l], tb.vol[l], p.dict);
+        if (qi >= 0 && qi < p.dict)
+          s = (unsigned)qi;
+        else
+          is_out = true;
+        sym[base + f] = (uint16_t)s;
+      }
+      outlier_append(is_out, (unsigned long long)(base + f), qi, ocount, oidx, oval, ocap);
+      hist_add(sh, s, valid);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < p.dict; i += blockDim.x * blockDim.y) {
+    unsigned c = sh[i];
+    if (c)
+      atomicAdd(&ghist[i], c);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+dequantize_linear_kernel(const uint16_t *__restrict__ sym, i64 N, T qv, int dict,
+                         T *__restrict__ v) {
+  i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    long long qi = (long long)sym[i] - dict / 2;
+    v[i] = qv * (T)qi; // (quantizer * volume) * (T)quantized
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+dequantize_level_kernel(const QParams p, const Tables<T> tb,
+                        const uint16_t *__restrict__ sym, T *__restrict__ v) {
+  const int D = p.D;
+  const unsigned nf = p.n[D - 1];
+  for (unsigned row0 = blockIdx.x * blockDim.y; row0 < p.rows;
+       row0 += gridDim.x * blockDim.y) {
+    unsigned row = row0 + threadIdx.y;
+    if (row >= p.rows)
+      continue;
+    int lvl = 0;
+    unsigned rem = row;
+    for (int d = D - 2; d >= 0; d--) {
+      unsigned i = rem % p.n[d];
+      rem /= p.n[d];
+      lvl = max(lvl, p.marks[(size_t)d * p.marks_width + i]);
+    }
+    i64 base = (i64)row * nf;
+    for (unsigned f = threadIdx.x; f < nf; f += blockDim.x) {
+      int l = max(lvl, p.marks[(size_t)(D - 1) * p.marks_width + f]);
+      long long qi = (long long)sym[base + f] - p.dict / 2;
+      v[base + f] = (tb.q[l] * tb.vol[l]) * (T)qi;
+    }
+  }
+}
+
+// outliers: v[idx] = (quantizer * volume) * (T)(outlier - dict/2)
+template <typename T>
+__global__ void outlier_restore_kernel(const QParams p, const Tables<T> tb,
+                                       unsigned long long count,
+                                       const uint64_t *__restrict__ oidx,
+                                       const i64 *__restrict__ oval, T *__restrict__ v) {
+  unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count)
+    return;
+  uint64_t idx = oidx[k];
+  int l = 0;
+  if (p.calc_level) {
+    uint64_t rem = idx;
+    for (int d = p.D - 1; d >= 0; d--) {
+      uint64_t i = rem % p.n[d];
+      rem /= p.n[d];
+      l = max(l, p.marks[(size_t)d * p.marks_width + i]);
+    }
+  }
+  long long qi = oval[k] - p.dict / 2;
+  v[idx] = (tb.q[l] * tb.vol[l]) * (T)qi;
+}
+
+// ------------------------------- norms -------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+norm_partial_kernel(const T *__restrict__ v, i64 N, double *__restrict__ part) {
+  double mx = 0.0, ss = 0.0;
+  i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    double x = (double)v[i];
+    mx = fmax(mx, fabs(x));
+    ss += x * x;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  __shared__ double smx[8], sss[8];
+  int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    smx[w] = mx;
+    sss[w] = ss;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; k++) {
+      mx = fmax(mx, smx[k]);
+      ss += sss[k];
+    }
+    part[2 * blockIdx.x] = mx;
+    part[2 * blockIdx.x + 1] = ss;
+  }
+}
+
+__global__ void norm_final_kernel(const double *__restrict__ part, int nblocks,
+                                  double *__restrict__ out) {
+  // single warp, fixed order => deterministic
+  double mx = 0.0, ss = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 32) {
+    mx = fmax(mx, part[2 * i]);
+    ss += part[2 * i + 1];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if (threadIdx.x == 0) {
+    out[0] = mx;
+    out[1] = ss;
+  }
+}
+
+// LinearQuantizer::CalcQuantizers (LinearQuantization.hpp:495-545), evaluated
+// with the reference's types: tol/s/norm are T, abs_tol is double.
+template <typename T>
+void calc_quantizers(const mgb_plan *p, int ebtype, double tol_, double s_,
+                     double norm_, bool reciprocal, T *out) {
+  T tol = (T)tol_, s = (T)s_, norm = (T)norm_;
+  double abs_tol = tol;
+  if (ebtype == MGB_REL)
+    abs_tol *= norm;
+  abs_tol *= 2;
+  const uint64_t l_target = (uint64_t)p->L;
+  const size_t dof = p->N;
+  if (s == std::numeric_limits<T>::infinity()) {
+    for (int l = 0; l < p->L + 1; l++) {
+      out[l] = (abs_tol) / ((l_target + 1) * (1 + std::pow(3, p->D)));
+      if (reciprocal)
+        out[l] = 1.0f / out[l];
+    }
+  } else {
+    for (int l = 0; l < p->L + 1; l++) {
+      out[l] = (abs_tol) / (std::exp2(s * l) * std::sqrt(dof));
+      if (reciprocal)
+        out[l] = 1.0f / out[l];
+    }
+  }
+}
+
+// level volume factor: Hierarchy::calc_volume (Hierarchy.hpp:165-190) and the
+// product / sqrt of LinearQuantization.hpp:190-198
+template <typename T>
+void calc_volumes(const mgb_plan *p, bool reciprocal, bool calc_vol, T *out) {
+  for (int l = 0; l <= p->L; l++) {
+    T volume = 1;
+    if (calc_vol) {
+      for (int d = p->D - 1; d >= 0; d--) {
+        uint64_t dofd = p->lshape[l][d];
+        T hv = 0.0;
+        if (dofd > 1)
+          hv = 1.0 / (T)(dofd - 1);
+        if (reciprocal)
+          hv = 1.0 / hv;
+        volume *= hv;
+      }
+      if (sizeof(T) == sizeof(double))
+        volume = std::sqrt(volume);
+      else
+        volume = sqrtf((float)volume);
+    }
+    out[l] = volume;
+  }
+}
+
+template <typename T>
+void make_params(const mgb_plan *p, int ebtype, double tol, double s, double norm,
+                 bool dequant, QParams &qp, Tables<T> &tb) {
+  memset(&qp, 0, sizeof(qp));
+  qp.D = p->D;
+  qp.dict = p->cfg.huff_dict_size;
+  qp.L = p->L;
+  bool calc_vol = !(std::isinf(s) && s > 0);
+  qp.calc_level = calc_vol;
+  unsigned rows = 1;
+  for (int d = 0; d < p->D; d++) {
+    qp.n[d] = (unsigned)p->shape[d];
+    if (d < p->D - 1)
+      rows *= (unsigned)p->shape[d];
+  }
+  qp.rows = rows;
+  qp.marks = p->d_marks;
+  qp.marks_width = p->marks_width;
+  calc_quantizers<T>(p, ebtype, tol, s, norm, !dequant, tb.q);
+  calc_volumes<T>(p, dequant, calc_vol, tb.vol);
+}
+
+template <typename T>
+int quantize_t(mgb_plan *p, const T *d_coef, int ebtype, double tol, double s,
+               double norm, uint16_t *d_sym, uint32_t *d_hist,
+               unsigned long long *d_ocount, uint64_t *d_oidx, int64_t *d_oval,
+               uint64_t ocap, cudaStream_t st) {
+  QParams qp;
+  Tables<T> tb;
+  make_params<T>(p, ebtype, tol, s, norm, false, qp, tb);
+  const int dict = qp.dict;
+  MGB_CUDA_CHECK(cudaMemsetAsync(d_hist, 0, dict * sizeof(uint32_t), st));
+  MGB_CUDA_CHECK(cudaMemsetAsync(d_ocount, 0, sizeof(unsigned long long), st));
+  size_t smem = dict * sizeof(unsigned);
+  if (!qp.calc_level) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(quantize_linear_kernel<T>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    unsigned blocks = (unsigned)std::min<i64>((p->N + 255) / 256, 148 * 6);
+    MGB_LAUNCH(MGB_K_QUANTIZE, st,
+               (quantize_linear_kernel<T><<<blocks, 256, smem, st>>>(
+                   d_coef, (i64)p->N, tb.q[0], tb.vol[0], dict, d_sym, d_hist, d_ocount,
+                   d_oidx, (i64 *)d_oval, ocap)));
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(quantize_level_kernel<T>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int bx = 32;
+    while (bx < (int)qp.n[p->D - 1] && bx < 256)
+      bx <<= 1;
+    dim3 block(bx, 256 / bx);
+    unsigned blocks = std::min<unsigned>((qp.rows + block.y - 1) / block.y, 148 * 6);
+    MGB_LAUNCH(MGB_K_QUANTIZE, st,
+               (quantize_level_kernel<T><<<blocks, block, smem, st>>>(
+                   qp, tb, d_coef, d_sym, d_hist, d_ocount, d_oidx, (i64 *)d_oval, ocap)));
+  }
+  MGB_CUDA_CHECK(cudaGetLastError());
+  return MGB_SUCCESS;
+}
+
+template <typename T>
+int dequantize_t(mgb_plan *p, const uint16_t *d_sym, uint64_t ocount,
+                 const uint64_t *d_oidx, const int64_t *d_oval, int ebtype,
+                 double tol, double s, double norm, T *d_coef, cudaStream_t st) {
+  QParams qp;
+  Tables<T> tb;
+  make_params<T>(p, ebtype, tol, s, norm, true, qp, tb);
+  if (!qp.calc_level) {
+    unsigned blocks = (unsigned)std::min<i64>((p->N + 255) / 256, 148 * 16);
+    MGB_LAUNCH(MGB_K_DEQUANTIZE, st,
+               (dequantize_linear_kernel<T><<<blocks, 256, 0, st>>>(
+                   d_sym, (i64)p->N, tb.q[0] * tb.vol[0], qp.dict, d_coef)));
+  } else {
+    int bx = 32;
+    while (bx < (int)qp.n[p->D - 1] && bx < 256)
+      bx <<= 1;
+    dim3 block(bx, 256 / bx);
+    unsigned blocks = std::min<unsigned>((qp.rows + block.y - 1) / block.y, 148 * 16);
+    MGB_LAUNCH(MGB_K_DEQUANTIZE, st,
+               (dequantize_level_kernel<T><<<blocks, block, 0, st>>>(qp, tb, d_sym, d_coef)));
+  }
+  if (ocount) {
+    MGB_LAUNCH(MGB_K_OUTLIER_RESTORE, st,
+               (outlier_restore_kernel<T><<<(unsigned)((ocount + 255) / 256), 256, 0, st>>>(
+                   qp, tb, ocount, d_oidx, (const i64 *)d_oval, d_coef)));
+  }
+  MGB_CUDA_CHECK(cudaGetLastError());
+  return MGB_SUCCESS;
+}
+
+} // namespace
+
+extern "C" int mgb_quantize(mgb_plan *plan, const void *d_coef, int ebtype,
+                            double tol, double s, double norm, uint16_t *d_sym,
+                            uint32_t *d_hist, unsigned long long *d_ocount,
+                            uint64_t *d_oidx, int64_t *d_oval,
+                            uint64_t outlier_cap, void *stream) {
+  if (!plan || !d_coef || !d_sym || !d_hist || !d_ocount)
+    return MGB_BAD_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (plan->dtype == MGB_F32)
+    return quantize_t<float>(plan, (const float *)d_coef, ebtype, tol, s, norm,
+                             d_sym, d_hist, d_ocount, d_oidx, d_oval,
+                             outlier_cap, st);
+  return quantize_t<double>(plan, (const double *)d_coef, ebtype, tol, s, norm,
+                            d_sym, d_hist, d_ocount, d_oidx, d_oval,
+                            outlier_cap, st);
+}
+
+extern "C" int mgb_dequantize(mgb_plan *plan, const uint16_t *d_sym,
+                              uint64_t ocount, const uint64_t *d_oidx,
+                              const int64_t *d_oval, int ebtype, double tol,
+                              double s, double norm, void *d_coef, void *stream) {
+  if (!plan || !d_coef || !d_sym)
+    return MGB_BAD_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (plan->dtype == MGB_F32)
+    return dequantize_t<float>(plan, d_sym, ocount, d_oidx, d_oval, ebtype, tol,
+                               s, norm, (float *)d_coef, st);
+  return dequantize_t<double>(plan, d_sym, ocount, d_oidx, d_oval, ebtype, tol,
+                              s, norm, (double *)d_coef, st);
+}
+
+extern "C" int mgb_norm_partials(mgb_plan *plan, const void *d_in,
+                                 double *absmax, double *sumsq) {
+  if (!plan || !d_in)
+    return MGB_BAD_ARGUMENT;
+  const int nblocks = 148 * 8;
+  if (!plan->d_norm_tmp)
+    MGB_CUDA_CHECK(cudaMalloc(&plan->d_norm_tmp, (2 * nblocks + 2) * sizeof(double)));
+  double *part = (double *)plan->d_norm_tmp;
+  if (plan->dtype == MGB_F32)
+    MGB_LAUNCH(MGB_K_NORM, 0,
+               (norm_partial_kernel<float><<<nblocks, 256>>>((const float *)d_in, (i64)plan->N, part)));
+  else
+    MGB_LAUNCH(MGB_K_NORM, 0,
+               (norm_partial_kernel<double><<<nblocks, 256>>>((const double *)d_in, (i64)plan->N, part)));
+  MGB_LAUNCH(MGB_K_NORM, 0, (norm_final_kernel<<<1, 32>>>(part, nblocks, part + 2 * nblocks)));
+  double h[2];
+  MGB_CUDA_CHECK(cudaMemcpy(h, part + 2 * nblocks, sizeof(h), cudaMemcpyDeviceToHost));
+  if (absmax)
+    *absmax = h[0];
+  if (sumsq)
+    *sumsq = h[1];
+  return MGB_SUCCESS;
+}
+
+extern "C" int mgb_norm(mgb_plan *plan, const void *d_in, double s, double *norm) {
+  if (!norm)
+    return MGB_BAD_ARGUMENT;
+  double mx, ss;
+  int rc = mgb_norm_partials(plan, d_in, &mx, &ss);
+  if (rc)
+    return rc;
+  // NormCalculator.hpp:44-71 (normalize_coordinates = true), result in T
+  double r;
+  if (std::isinf(s) && s > 0) {
+    r = mx;
+  } else {
+    if (plan->dtype == MGB_F32)
+      r = std::sqrt((float)ss / plan->N);
+    else
+      r = std::sqrt(ss / plan->N);
+  }
+  if (plan->dtype == MGB_F32) {
+    float f = (float)r;
+    if (f == 0)
+      f = std::numeric_limits<float>::epsilon();
+    r = f;
+  } else if (r == 0) {
+    r = std::numeric_limits<double>::epsilon();
+  }
+  *norm = r;
+  return MGB_SUCCESS;
+}

@@ -1,0 +1,791 @@
+// Multilevel decomposition / recomposition kernels (sm_100a).
+//
+// What is computed (bit-exact with the reference's non-FMA arithmetic; this
+// file must be compiled with -fmad=false):
+//   coefficients   reference GpkReo3D / GpkReo<D>   (Coefficient/GridProcessingKernel3D.hpp:21-1229,
+//                  lerp: Coefficient/GPKFunctor.h:13-26)
+//   restore        reference GpkRev3D / GpkRev<D>   (GridProcessingKernel3D.hpp:1231-2400)
+//   mass x restr.  reference Lpk{1,2,3}Reo3D        (Correction/LinearProcessingKernel3D.hpp:27-1090,
+//                  mass_trans: Correction/LPKFunctor.h:47-66)
+//   tridiagonal    reference Ipk{1,2,3}Reo3D        (Correction/IterativeProcessingKernel3D.hpp,
+//                  Correction/IPKFunctor.h:14-51)
+//   level loop     reference multi_dimension::decompose / recompose
+//                  (DataRefactoring.hpp:25-177,180-317)
+//
+// How it is laid out here (not the reference's way): the input field is never
+// modified.  Level l reads a DENSE box (the input itself for the finest level,
+// a dense coarse buffer afterwards), writes its coefficients straight to their
+// final position in the output array (coarse-first layout along every
+// dimension) and the coarse nodes to the next dense buffer; no CopyND /
+// in-place permutation passes.  All kernels are dimension-generic (D = 1..5)
+// through a (rows x fastest-dim) mapping: a thread block owns rows, threads
+// sweep the contiguous dimension, so every global access is coalesced.
+#include <cstdint>
+
+#include "plan.h"
+
+namespace {
+
+typedef long long i64;
+
+struct Geom {
+  int D;          // number of dims
+  int n[5];       // fine level shape
+  int nc[5];      // coarse level shape
+  i64 sa[5];      // strides of array A (meaning per kernel)
+  i64 sb[5];      // strides of array B
+  i64 sc[5];      // strides of array C
+  const void *t0[5]; // per-dim table 0 (ratio / coefficient table)
+  int axis, zero_block;
+  unsigned rows;  // product of n[0..D-2] (or kernel specific)
+};
+
+template <typename T> __device__ __forceinline__ T lerp_ref(T v0, T v1, T t) {
+  // GPKFunctor.h:13-26, non-FMA branch
+  T r = v0 + v0 * t * (T)-1;
+  r = r + t * v1;
+  return r;
+}
+
+// ---------------------------------------------------------------------------
+// Coefficient kernel.  A = dense nodal input (level box), B = output array
+// (full-array strides, coarse-first layout), C = dense coarse output.
+// DS = number of slower dims (D-1); MASK bit (DS-1-d) set <=> slower dim d is
+// an odd (new) node, so bit 0 is the fastest of the slower dims.
+// ---------------------------------------------------------------------------
+constexpr int popc(int x) { return x == 0 ? 0 : (x & 1) + popc(x >> 1); }
+
+template <typename T, int DS, int MASK> struct Corner {
+  static constexpr int K = popc(MASK);
+  // interpolate the value at column index `col` of the corner rows
+  // (fastest-dim first reduction order: slower dims from fastest to slowest)
+  template <typename F>
+  static __device__ __forceinline__ T eval(const i64 (&dstride)[5],
+                                           const T (&rat)[5], F rowval) {
+    T vals[1 << K];
+#pragma unroll
+    for (int c = 0; c < (1 << K); c++) {
+      i64 off = 0;
+      int bit = 0;
+#pragma unroll
+      for (int d = DS - 1; d >= 0; d--) {
+        if (MASK & (1 << (DS - 1 - d))) {
+          off += ((c >> bit) & 1) ? dstride[d] : -dstride[d];
+          bit++;
+        }
+      }
+      vals[c] = rowval(off);
+    }
+    int bit = 0;
+#pragma unroll
+    for (int d = DS - 1; d >= 0; d--) {
+      if (MASK & (1 << (DS - 1 - d))) {
+#pragma unroll
+        for (int m = 0; m < (1 << (K - 1 - bit)); m++)
+          vals[m] = lerp_ref(vals[2 * m], vals[2 * m + 1], rat[d]);
+        bit++;
+      }
+    }
+    return vals[0];
+  }
+};
+
+template <typename T, int DS, int MASK>
+__device__ __forceinline__ void
+coef_row(const Geom &g, const T *__restrict__ in_row, T *__restrict__ out_row,
+         T *__restrict__ coarse_row, const i64 (&dstride)[5],
+         const T (&rat)[5]) {
+  const int D = DS + 1;
+  const int nf = g.n[D - 1], ncf = g.nc[D - 1];
+  const bool f_even_n = (nf & 1) == 0;
+  const T *__restrict__ ratio_f = (const T *)g.t0[D - 1];
+  const i64 osf = g.sb[D - 1];
+  const int npairs = (nf + 1) >> 1;
+  for (int j = threadIdx.x; j < npairs; j += blockDim.x) {
+    const int f0 = 2 * j, f1 = 2 * j + 1;
+    // even node f0 -> position j
+    {
+      T v = in_row[f0];
+      if (MASK == 0) {
+        coarse_row[j] = v;
+      } else {
+        T it = Corner<T, DS, MASK>::eval(
+            dstride, rat, [&](i64 off) { return in_row[off + f0]; });
+        out_row[(i64)j * osf] = v - it;
+      }
+    }
+    if (f1 < nf) {
+      T v = in_row[f1];
+      if (f_even_n && f1 == nf - 1) {
+        // ghost node: behaves as the last coarse node along f
+        if (MASK == 0) {
+          coarse_row[ncf - 1] = v;
+        } else {
+          T it = Corner<T, DS, MASK>::eval(
+              dstride, rat, [&](i64 off) { return in_row[off + f1]; });
+          out_row[(i64)(ncf - 1) * osf] = v - it;
+        }
+      } else {
+        const T rf = ratio_f[f0];
+        T it = Corner<T, DS, MASK>::eval(dstride, rat, [&](i64 off) {
+          return lerp_ref(in_row[off + f0], in_row[off + f0 + 2], rf);
+        });
+        out_row[(i64)(ncf + j) * osf] = v - it;
+      }
+    }
+  }
+}
+
+template <typename T, int DS, int MASK> struct CoefDispatch {
+  static __device__ __forceinline__ void
+  run(int mask, const Geom &g, const T *in_row, T *out_row, T *coarse_row,
+      const i64 (&dstride)[5], const T (&rat)[5]) {
+    if (mask == MASK)
+      coef_row<T, DS, MASK>(g, in_row, out_row, coarse_row, dstride, rat);
+    else
+      CoefDispatch<T, DS, MASK - 1>::run(mask, g, in_row, out_row, coarse_row,
+                                         dstride, rat);
+  }
+};
+template <typename T, int DS> struct CoefDispatch<T, DS, -1> {
+  static __device__ __forceinline__ void run(int, const Geom &, const T *, T *,
+                                             T *, const i64 (&)[5],
+                                             const T (&)[5]) {}
+};
+
+template <typename T, int DS>
+__global__ void __launch_bounds__(256) coef_kernel(const Geom g, const T *__restrict__ in,
+                                                   T *__restrict__ out,
+                                                   T *__restrict__ coarse) {
+  unsigned row = blockIdx.x * blockDim.y + threadIdx.y;
+  if (row >= g.rows)
+    return;
+  // decompose the row index into slower-dim nodal indices
+  i64 in_off = 0, out_off = 0, c_off = 0;
+  int mask = 0;
+  i64 dstride[5];
+  T rat[5];
+  unsigned rem = row;
+#pragma unroll
+  for (int d = DS - 1; d >= 0; d--) {
+    unsigned nd = (unsigned)g.n[d];
+    unsigned i = rem % nd;
+    rem /= nd;
+    bool ghost = ((nd & 1) == 0) && (i == nd - 1);
+    bool odd = (i & 1) && !ghost;
+    unsigned p = odd ? g.nc[d] + (i >> 1) : (ghost ? g.nc[d] - 1 : (i >> 1));
+    in_off += (i64)i * g.sa[d];
+    out_off += (i64)p * g.sb[d];
+    c_off += (i64)p * g.sc[d]; // only meaningful when mask == 0
+    dstride[d] = g.sa[d];
+    rat[d] = (T)0;
+    if (odd) {
+      mask |= 1 << (DS - 1 - d);
+      rat[d] = ((const T *)g.t0[d])[i - 1];
+    }
+  }
+  CoefDispatch<T, DS, (1 << DS) - 1>::run(mask, g, in + in_off, out + out_off,
+                                          coarse + c_off, dstride, rat);
+}
+
+// ---------------------------------------------------------------------------
+// Restore kernel (recomposition).  A = dense coarse input, B = coefficient
+// array (full strides, coarse-first layout), C = dense nodal output.
+// ---------------------------------------------------------------------------
+template <typename T, int DS, int MASK>
+__device__ __forceinline__ void
+restore_row(const Geom &g, const T *__restrict__ crow, const T *__restrict__ coef_row_,
+            T *__restrict__ out_row, const i64 (&dstride)[5],
+            const i64 (&dlo)[5], const T (&rat)[5]) {
+  const int D = DS + 1;
+  const int nf = g.n[D - 1], ncf = g.nc[D - 1];
+  const bool f_even_n = (nf & 1) == 0;
+  const T *__restrict__ ratio_f = (const T *)g.t0[D - 1];
+  const i64 bsf = g.sb[D - 1];
+  const int npairs = (nf + 1) >> 1;
+  // corner rows: offsets relative to crow: for odd dims "low" coarse index is
+  // already folded into crow; +stride selects the high neighbour.
+  auto corner = [&](auto rowval) {
+    constexpr int K = popc(MASK);
+    T vals[1 << K];
+#pragma unroll
+    for (int c = 0; c < (1 << K); c++) {
+      i64 off = 0;
+      int bit = 0;
+#pragma unroll
+      for (int d = DS - 1; d >= 0; d--) {
+        if (MASK & (1 << (DS - 1 - d))) {
+          off += ((c >> bit) & 1) ? dstride[d] : 0;
+          bit++;
+        }
+      }
+      vals[c] = rowval(off);
+    }
+    int bit = 0;
+#pragma unroll
+    for (int d = DS - 1; d >= 0; d--) {
+      if (MASK & (1 << (DS - 1 - d))) {
+#pragma unroll
+        for (int m = 0; m < (1 << (K - 1 - bit)); m++)
+          vals[m] = lerp_ref(vals[2 * m], vals[2 * m + 1], rat[d]);
+        bit++;
+      }
+    }
+    return vals[0];
+  };
+  for (int j = threadIdx.x; j < npairs; j += blockDim.x) {
+    const int f0 = 2 * j, f1 = 2 * j + 1;
+    {
+      T r;
+      if (MASK == 0) {
+        r = crow[j];
+      } else {
+        T it = corner([&](i64 off) { return crow[off + j]; });
+        r = coef_row_[(i64)j * bsf] + it;
+      }
+      out_row[f0] = r;
+    }
+    if (f1 < nf) {
+      T r;
+      if (f_even_n && f1 == nf - 1) {
+        if (MASK == 0) {
+          r = crow[ncf - 1];
+        } else {
+          T it = corner([&](i64 off) { return crow[off + ncf - 1]; });
+          r = coef_row_[(i64)(ncf - 1) * bsf] + it;
+        }
+      } else {
+        const T rf = ratio_f[f0];
+        T it = corner([&](i64 off) {
+          return lerp_ref(crow[off + j], crow[off + j + 1], rf);
+        });
+        r = coef_row_[(i64)(ncf + j) * bsf] + it;
+      }
+      out_row[f1] = r;
+    }
+  }
+}
+
+template <typename T, int DS, int MASK> struct RestoreDispatch {
+  static __device__ __forceinline__ void
+  run(int mask, const Geom &g, const T *crow, const T *coef_row_, T *out_row,
+      const i64 (&dstride)[5], const i64 (&dlo)[5], const T (&rat)[5]) {
+    if (mask == MASK)
+      restore_row<T, DS, MASK>(g, crow, coef_row_, out_row, dstride, dlo, rat);
+    else
+      RestoreDispatch<T, DS, MASK - 1>::run(mask, g, crow, coef_row_, out_row,
+                                            dstride, dlo, rat);
+  }
+};
+template <typename T, int DS> struct RestoreDispatch<T, DS, -1> {
+  static __device__ __forceinline__ void run(int, const Geom &, const T *,
+                                             const T *, T *, const i64 (&)[5],
+                                             const i64 (&)[5], const T (&)[5]) {}
+};
+
+template <typename T, int DS>
+__global__ void __launch_bounds__(256) restore_kernel(const Geom g, const T *__restrict__ coarse,
+                                                      const T *__restrict__ coef,
+                                                      T *__restrict__ out) {
+  unsigned row = blockIdx.x * blockDim.y + threadIdx.y;
+  if (row >= g.rows)
+    return;
+  i64 c_off = 0, b_off = 0, o_off = 0;
+  int mask = 0;
+  i64 dstride[5], dlo[5];
+  T rat[5];
+  unsigned rem = row;
+#pragma unroll
+  for (int d = DS - 1; d >= 0; d--) {
+    unsigned nd = (unsigned)g.n[d];
+    unsigned i = rem % nd;
+    rem /= nd;
+    bool ghost = ((nd & 1) == 0) && (i == nd - 1);
+    bool odd = (i & 1) && !ghost;
+    unsigned p = odd ? g.nc[d] + (i >> 1) : (ghost ? g.nc[d] - 1 : (i >> 1));
+    unsigned clo = ghost ? g.nc[d] - 1 : (i >> 1); // low coarse neighbour
+    c_off += (i64)clo * g.sa[d];
+    b_off += (i64)p * g.sb[d];
+    o_off += (i64)i * g.sc[d];
+    dstride[d] = g.sa[d];
+    dlo[d] = 0;
+    rat[d] = (T)0;
+    if (odd) {
+      mask |= 1 << (DS - 1 - d);
+      rat[d] = ((const T *)g.t0[d])[i - 1];
+    }
+  }
+  RestoreDispatch<T, DS, (1 << DS) - 1>::run(mask, g, coarse + c_off,
+                                             coef + b_off, out + o_off,
+                                             dstride, dlo, rat);
+}
+
+// ---------------------------------------------------------------------------
+// Mass matrix x restriction along one axis on the coarse-first layout.
+// A = input (strided, shape n[] with axis already-reduced dims holding nc),
+// B = dense output.  t0[axis] = 9-row coefficient table [9][nc_axis]:
+// h1/6,(h1+h2)/3,h2/6,(h2+h3)/3,h3/6,(h3+h4)/3,h4/6,r1,r4 (LPKFunctor.h:47-66).
+// g.n[]  : input shape;  output shape = n[] with n[axis] -> nc[axis].
+// zero_block: treat input elements with all indices < nc[] as zero
+// (LinearProcessingKernel3D.hpp:99-133).
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) mass_trans_kernel(const Geom g, const T *__restrict__ in,
+                                                         T *__restrict__ out) {
+  const int D = g.D;
+  const int a = g.axis;
+  unsigned row = blockIdx.x * blockDim.y + threadIdx.y;
+  if (row >= g.rows)
+    return;
+  // rows enumerate output indices of dims 0..D-2 (slower dims)
+  i64 in_off = 0, out_off = 0;
+  bool in_block = g.zero_block != 0;
+  int ia = 0; // index along axis if axis is a slower dim
+  unsigned rem = row;
+  for (int d = D - 2; d >= 0; d--) {
+    unsigned nd = (unsigned)(d == a ? g.nc[d] : g.n[d]);
+    unsigned i = rem % nd;
+    rem /= nd;
+    out_off += (i64)i * g.sb[d];
+    if (d == a) {
+      ia = (int)i;
+    } else {
+      in_off += (i64)i * g.sa[d];
+      if ((int)i >= g.nc[d])
+        in_block = false;
+    }
+  }
+  const T *__restrict__ tab = (const T *)g.t0[a];
+  const int na = g.n[a], nca = g.nc[a];
+  const int ncoef = na - nca;
+  const int nf_out = (a == D - 1) ? nca : g.n[D - 1];
+  const i64 sa_a = g.sa[a];
+  const i64 sa_f = g.sa[D - 1];
+  for (int f = threadIdx.x; f < nf_out; f += blockDim.x) {
+    const int i = (a == D - 1) ? f : ia;
+    const T *__restrict__ p = in + in_off + ((a == D - 1) ? 0 : (i64)f * sa_f);
+    bool zb = in_block && (a == D - 1 || f < g.nc[D - 1]);
+    T va = (T)0, vb = (T)0, vc = (T)0, vd = (T)0, ve = (T)0;
+    if (!zb) {
+      vc = p[(i64)i * sa_a];
+      if (i >= 1)
+        va = p[(i64)(i - 1) * sa_a];
+      if (i + 1 < nca)
+        ve = p[(i64)(i + 1) * sa_a];
+    }
+    if (i >= 1 && i - 1 < ncoef)
+      vb = p[(i64)(nca + i - 1) * sa_a];
+    if (i < ncoef)
+      vd = p[(i64)(nca + i) * sa_a];
+    const T c16 = tab[i], c13 = tab[nca + i], c26 = tab[2 * nca + i],
+            c23 = tab[3 * nca + i], c36 = tab[4 * nca + i],
+            c34 = tab[5 * nca + i], c46 = tab[6 * nca + i],
+            r1 = tab[7 * nca + i], r4 = tab[8 * nca + i];
+    T tb = va * c16 + vb * c13 + vc * c26;
+    T tc = vb * c26 + vc * c23 + vd * c36;
+    T td = vc * c36 + vd * c34 + ve * c46;
+    tc += tb * r1 + td * r4;
+    out[out_off + (i64)f * g.sb[D - 1]] = tc;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Thomas solve along a strided axis of a dense array viewed as
+// (outer, n, inner), inner > 1: one thread per line, coalesced across inner.
+// mode: 0 plain, 1 add result to `acc`, 2 subtract result from `acc`
+// (AddND / SubtractND of DataRefactoring.hpp:99,241 fused into the last solve).
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) thomas_strided_kernel(T *__restrict__ x, int n, i64 inner,
+                                                             i64 lines,
+                                                             const T *__restrict__ fw,
+                                                             const T *__restrict__ am,
+                                                             const T *__restrict__ bm) {
+  i64 line = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= lines)
+    return;
+  i64 o = line / inner, in = line - o * inner;
+  T *p = x + o * (i64)n * inner + in;
+  T prev = (T)0;
+  constexpr int U = 8;
+  int i = 0;
+  for (; i + U <= n; i += U) {
+    T v[U];
+#pragma unroll
+    for (int k = 0; k < U; k++)
+      v[k] = p[(i64)(i + k) * inner];
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      prev = v[k] - prev * fw[i + k];
+      p[(i64)(i + k) * inner] = prev;
+    }
+  }
+  for (; i < n; i++) {
+    prev = p[(i64)i * inner] - prev * fw[i];
+    p[(i64)i * inner] = prev;
+  }
+  prev = (T)0;
+  i = n - 1;
+  for (; i - U + 1 >= 0; i -= U) {
+    T v[U];
+#pragma unroll
+    for (int k = 0; k < U; k++)
+      v[k] = p[(i64)(i - k) * inner];
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      prev = (v[k] - am[i - k + 1] * prev) / bm[i - k + 1];
+      p[(i64)(i - k) * inner] = prev;
+    }
+  }
+  for (; i >= 0; i--) {
+    prev = (p[(i64)i * inner] - am[i + 1] * prev) / bm[i + 1];
+    p[(i64)i * inner] = prev;
+  }
+}
+
+// Thomas solve along the contiguous axis: a warp owns 32 lines and streams
+// 32-column tiles through shared memory (transpose so that global accesses
+// stay coalesced while each lane walks its own line).
+template <typename T>
+__global__ void __launch_bounds__(128) thomas_contig_kernel(T *__restrict__ x, int n, i64 lines,
+                                                            const T *__restrict__ fw,
+                                                            const T *__restrict__ am,
+                                                            const T *__restrict__ bm) {
+  __shared__ T tile[4][32][33];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  i64 line0 = ((i64)blockIdx.x * 4 + w) * 32;
+  if (line0 >= lines)
+    return;
+  int nl = (int)min((i64)32, lines - line0);
+  T(*t)[33] = tile[w];
+  T prev = (T)0;
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    int ncol = min(32, n - c0);
+    for (int r = 0; r < nl; r++)
+      if (lane < ncol)
+        t[r][lane] = x[(line0 + r) * n + c0 + lane];
+    __syncwarp();
+    if (lane < nl) {
+      for (int c = 0; c < ncol; c++) {
+        prev = t[lane][c] - prev * fw[c0 + c];
+        t[lane][c] = prev;
+      }
+    }
+    __syncwarp();
+    for (int r = 0; r < nl; r++)
+      if (lane < ncol)
+        x[(line0 + r) * n + c0 + lane] = t[r][lane];
+    __syncwarp();
+  }
+  prev = (T)0;
+  for (int c1 = n; c1 > 0; c1 -= 32) {
+    int c0 = max(0, c1 - 32);
+    int ncol = c1 - c0;
+    for (int r = 0; r < nl; r++)
+      if (lane < ncol)
+        t[r][lane] = x[(line0 + r) * n + c0 + lane];
+    __syncwarp();
+    if (lane < nl) {
+      for (int c = ncol - 1; c >= 0; c--) {
+        prev = (t[lane][c] - am[c0 + c + 1] * prev) / bm[c0 + c + 1];
+        t[lane][c] = prev;
+      }
+    }
+    __syncwarp();
+    for (int r = 0; r < nl; r++)
+      if (lane < ncol)
+        x[(line0 + r) * n + c0 + lane] = t[r][lane];
+    __syncwarp();
+  }
+}
+
+// acc[i] += sign * w[i] on dense arrays (AddND / SubtractND)
+template <typename T>
+__global__ void axpy_kernel(T *__restrict__ acc, const T *__restrict__ w, i64 n, int subtract) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  i64 stride = (i64)gridDim.x * blockDim.x;
+  for (; i < n; i += stride)
+    acc[i] = subtract ? acc[i] - w[i] : acc[i] + w[i];
+}
+
+// copy between a dense box and a strided box (level-0 coarse nodes)
+template <typename T>
+__global__ void box_copy_kernel(const Geom g, const T *__restrict__ src, T *__restrict__ dst,
+                                i64 total) {
+  i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total)
+    return;
+  i64 rem = idx, so = 0, dof = 0;
+  for (int d = g.D - 1; d >= 0; d--) {
+    i64 i = rem % g.n[d];
+    rem /= g.n[d];
+    so += i * g.sa[d];
+    dof += i * g.sb[d];
+  }
+  dst[dof] = src[so];
+}
+
+// ------------------------------ host drivers -------------------------------
+
+void dense_strides(const uint64_t *shape, int D, i64 *s) {
+  i64 acc = 1;
+  for (int d = D - 1; d >= 0; d--) {
+    s[d] = acc;
+    acc *= (i64)shape[d];
+  }
+}
+
+void row_launch_dims(int nf_threads, unsigned rows, dim3 &grid, dim3 &block) {
+  int bx = 32;
+  while (bx < nf_threads && bx < 256)
+    bx <<= 1;
+  int by = 256 / bx;
+  block = dim3(bx, by, 1);
+  grid = dim3((rows + by - 1) / by, 1, 1);
+}
+
+template <typename T>
+void fill_tables(const mgb_plan *p, int l, Geom &g, bool masstrans) {
+  for (int d = 0; d < p->D; d++) {
+    const mgb_dim_tables &m = p->tab[l][d];
+    g.t0[d] = p->dtab(masstrans ? m.mt : m.ratio);
+  }
+}
+
+// correction = Thomas_{f,c,r..}( MassTrans_{f,c,r..}( coefficient function ) )
+// (CalcCorrection3D.hpp:30-196), result dense with the coarse shape of level l-1
+// in *result (either d_wA or d_wB).
+template <typename T>
+int correction(mgb_plan *p, int l, const T *coef, T **result, cudaStream_t st) {
+  const int D = p->D;
+  i64 full[5];
+  dense_strides(p->shape, D, full);
+  const T *src = coef;
+  T *bufs[2] = {(T *)p->d_wA, (T *)p->d_wB};
+  int which = 0;
+  uint64_t cur_shape[5];
+  for (int d = 0; d < D; d++)
+    cur_shape[d] = p->lshape[l][d];
+  i64 src_stride[5];
+  for (int d = 0; d < D; d++)
+    src_stride[d] = full[d];
+  for (int a = D - 1; a >= 0; a--) {
+    Geom g = {};
+    g.D = D;
+    g.axis = a;
+    g.zero_block = (a == D - 1);
+    for (int d = 0; d < D; d++) {
+      g.n[d] = (int)cur_shape[d];
+      g.nc[d] = (int)p->lshape[l - 1][d];
+      g.sa[d] = src_stride[d];
+    }
+    g.n[a] = (int)p->lshape[l][a];
+    uint64_t out_shape[5];
+    for (int d = 0; d < D; d++)
+      out_shape[d] = d == a ? p->lshape[l - 1][d] : cur_shape[d];
+    dense_strides(out_shape, D, g.sb);
+    fill_tables<T>(p, l, g, true);
+    unsigned rows = 1;
+    for (int d = 0; d < D - 1; d++)
+      rows *= (unsigned)out_shape[d];
+    g.rows = rows;
+    dim3 grid, block;
+    row_launch_dims((int)out_shape[D - 1], rows, grid, block);
+    T *dst = bufs[which];
+    MGB_LAUNCH(MGB_K_MASSTRANS, st, (mass_trans_kernel<T><<<grid, block, 0, st>>>(g, src, dst)));
+    src = dst;
+    which ^= 1;
+    for (int d = 0; d < D; d++) {
+      cur_shape[d] = out_shape[d];
+      src_stride[d] = g.sb[d];
+    }
+  }
+  T *w = (T *)src; // dense, coarse shape
+  for (int a = D - 1; a >= 0; a--) {
+    const mgb_dim_tables &m = p->tab[l - 1][a];
+    const T *fw = (const T *)p->dtab(m.fw);
+    const T *am = (const T *)p->dtab(m.am);
+    const T *bm = (const T *)p->dtab(m.bm);
+    int n = (int)p->lshape[l - 1][a];
+    i64 inner = 1, outer = 1;
+    for (int d = a + 1; d < D; d++)
+      inner *= (i64)p->lshape[l - 1][d];
+    for (int d = 0; d < a; d++)
+      outer *= (i64)p->lshape[l - 1][d];
+    if (inner == 1) {
+      i64 lines = outer;
+      unsigned blocks = (unsigned)((lines + 127) / 128);
+      MGB_LAUNCH(MGB_K_THOMAS_CONTIG, st,
+                 (thomas_contig_kernel<T><<<blocks, 128, 0, st>>>(w, n, lines, fw, am, bm)));
+    } else {
+      i64 lines = outer * inner;
+      unsigned blocks = (unsigned)((lines + 127) / 128);
+      MGB_LAUNCH(MGB_K_THOMAS_STRIDED, st,
+                 (thomas_strided_kernel<T><<<blocks, 128, 0, st>>>(w, n, inner, lines, fw, am, bm)));
+    }
+  }
+  *result = w;
+  return MGB_SUCCESS;
+}
+
+template <typename T, int DS>
+void launch_coef(const Geom &g, const T *in, T *out, T *coarse, cudaStream_t st) {
+  dim3 grid, block;
+  row_launch_dims((g.n[DS] + 1) / 2, g.rows, grid, block);
+  MGB_LAUNCH(MGB_K_COEF, st, (coef_kernel<T, DS><<<grid, block, 0, st>>>(g, in, out, coarse)));
+}
+template <typename T, int DS>
+void launch_restore(const Geom &g, const T *coarse, const T *coef, T *out,
+                    cudaStream_t st) {
+  dim3 grid, block;
+  row_launch_dims((g.n[DS] + 1) / 2, g.rows, grid, block);
+  MGB_LAUNCH(MGB_K_RESTORE, st, (restore_kernel<T, DS><<<grid, block, 0, st>>>(g, coarse, coef, out)));
+}
+
+template <typename T>
+void axpy(T *acc, const T *w, i64 n, int subtract, cudaStream_t st) {
+  unsigned blocks = (unsigned)std::min<i64>((n + 255) / 256, 148 * 16);
+  MGB_LAUNCH(MGB_K_AXPY, st, (axpy_kernel<T><<<blocks, 256, 0, st>>>(acc, w, n, subtract)));
+}
+
+template <typename T>
+int decompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
+  int rc = mgb_plan_ensure_workspace(p);
+  if (rc)
+    return rc;
+  const int D = p->D;
+  i64 full[5];
+  dense_strides(p->shape, D, full);
+  const T *cur = d_in;
+  T *cbuf = (T *)p->d_cbuf;
+  for (int l = p->L; l >= 1; l--) {
+    Geom g = {};
+    g.D = D;
+    unsigned rows = 1;
+    for (int d = 0; d < D; d++) {
+      g.n[d] = (int)p->lshape[l][d];
+      g.nc[d] = (int)p->lshape[l - 1][d];
+      g.sb[d] = full[d];
+      if (d < D - 1)
+        rows *= (unsigned)g.n[d];
+    }
+    g.rows = rows;
+    dense_strides(p->lshape[l], D, g.sa);
+    dense_strides(p->lshape[l - 1], D, g.sc);
+    fill_tables<T>(p, l, g, false);
+    T *coarse = cbuf + p->cbuf_off[l - 1];
+    switch (D) {
+    case 1: launch_coef<T, 0>(g, cur, d_out, coarse, st); break;
+    case 2: launch_coef<T, 1>(g, cur, d_out, coarse, st); break;
+    case 3: launch_coef<T, 2>(g, cur, d_out, coarse, st); break;
+    case 4: launch_coef<T, 3>(g, cur, d_out, coarse, st); break;
+    case 5: launch_coef<T, 4>(g, cur, d_out, coarse, st); break;
+    }
+    T *w = nullptr;
+    rc = correction<T>(p, l, d_out, &w, st);
+    if (rc)
+      return rc;
+    axpy<T>(coarse, w, (i64)mgb_level_elems(p, l - 1), 0, st);
+    cur = coarse;
+  }
+  // level-0 nodes into the corner of the output
+  {
+    Geom g = {};
+    g.D = D;
+    for (int d = 0; d < D; d++) {
+      g.n[d] = (int)p->lshape[0][d];
+      g.sb[d] = full[d];
+    }
+    dense_strides(p->lshape[0], D, g.sa);
+    i64 total = (i64)mgb_level_elems(p, 0);
+    MGB_LAUNCH(MGB_K_BOXCOPY, st,
+               (box_copy_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, cur, d_out, total)));
+  }
+  MGB_CUDA_CHECK(cudaGetLastError());
+  return MGB_SUCCESS;
+}
+
+template <typename T>
+int recompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
+  int rc = mgb_plan_ensure_workspace(p);
+  if (rc)
+    return rc;
+  const int D = p->D;
+  i64 full[5];
+  dense_strides(p->shape, D, full);
+  T *cbuf = (T *)p->d_cbuf;
+  if (p->L == 0) {
+    MGB_CUDA_CHECK(cudaMemcpyAsync(d_out, d_in, p->N * sizeof(T),
+                                   cudaMemcpyDeviceToDevice, st));
+    return MGB_SUCCESS;
+  }
+  {
+    Geom g = {};
+    g.D = D;
+    for (int d = 0; d < D; d++) {
+      g.n[d] = (int)p->lshape[0][d];
+      g.sa[d] = full[d];
+    }
+    dense_strides(p->lshape[0], D, g.sb);
+    i64 total = (i64)mgb_level_elems(p, 0);
+    MGB_LAUNCH(MGB_K_BOXCOPY, st,
+               (box_copy_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+                   g, d_in, cbuf + p->cbuf_off[0], total)));
+  }
+  for (int l = 1; l <= p->L; l++) {
+    T *coarse = cbuf + p->cbuf_off[l - 1];
+    T *w = nullptr;
+    rc = correction<T>(p, l, d_in, &w, st);
+    if (rc)
+      return rc;
+    axpy<T>(coarse, w, (i64)mgb_level_elems(p, l - 1), 1, st);
+    Geom g = {};
+    g.D = D;
+    unsigned rows = 1;
+    for (int d = 0; d < D; d++) {
+      g.n[d] = (int)p->lshape[l][d];
+      g.nc[d] = (int)p->lshape[l - 1][d];
+      g.sb[d] = full[d];
+      if (d < D - 1)
+        rows *= (unsigned)g.n[d];
+    }
+    g.rows = rows;
+    dense_strides(p->lshape[l - 1], D, g.sa);
+    dense_strides(p->lshape[l], D, g.sc);
+    fill_tables<T>(p, l, g, false);
+    T *dst = l == p->L ? d_out : cbuf + p->cbuf_off[l];
+    switch (D) {
+    case 1: launch_restore<T, 0>(g, coarse, d_in, dst, st); break;
+    case 2: launch_restore<T, 1>(g, coarse, d_in, dst, st); break;
+    case 3: launch_restore<T, 2>(g, coarse, d_in, dst, st); break;
+    case 4: launch_restore<T, 3>(g, coarse, d_in, dst, st); break;
+    case 5: launch_restore<T, 4>(g, coarse, d_in, dst, st); break;
+    }
+  }
+  MGB_CUDA_CHECK(cudaGetLastError());
+  return MGB_SUCCESS;
+}
+
+} // namespace
+
+int mgb_decompose_impl(mgb_plan *p, const void *d_in, void *d_out, cudaStream_t st) {
+  if (p->dtype == MGB_F32)
+    return decompose_t<float>(p, (const float *)d_in, (float *)d_out, st);
+  return decompose_t<double>(p, (const double *)d_in, (double *)d_out, st);
+}
+int mgb_recompose_impl(mgb_plan *p, const void *d_in, void *d_out, cudaStream_t st) {
+  if (p->dtype == MGB_F32)
+    return recompose_t<float>(p, (const float *)d_in, (float *)d_out, st);
+  return recompose_t<double>(p, (const double *)d_in, (double *)d_out, st);
+}
+
+extern "C" int mgb_decompose(mgb_plan *plan, const void *d_in, void *d_out, void *stream) {
+  if (!plan || !d_in || !d_out)
+    return MGB_BAD_ARGUMENT;
+  return mgb_decompose_impl(plan, d_in, d_out, (cudaStream_t)stream);
+}
+extern "C" int mgb_recompose(mgb_plan *plan, const void *d_in, void *d_out, void *stream) {
+  if (!plan || !d_in || !d_out)
+    return MGB_BAD_ARGUMENT;
+  return mgb_recompose_impl(plan, d_in, d_out, (cudaStream_t)stream);
+}

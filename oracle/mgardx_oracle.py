@@ -855,6 +855,9 @@ def encode_header(shape, dtype, ebtype, tol, s, norm, coords=None,
     if ebtype == REL:
         err += _f_double(4, float(norm))
     err += _f_double(5, float(tol))
+    if not decomposed:
+        # DomainDecomposer.hpp:333-337: dim 0 / size shape[0] when not decomposed
+        dd_dim, dd_size = 0, int(shape[0])
     dd = (_f_varint(1, 1 if decomposed else 0) + _f_varint(2, dd_dim)
           + _f_varint(3, dd_size))
     fd = _f_varint(2, 1)

@@ -72,6 +72,9 @@ int mgb_plan_create(int ndim, const uint64_t *shape, int dtype,
                     mgb_plan **plan);
 void mgb_plan_destroy(mgb_plan *plan);
 int mgb_plan_l_target(const mgb_plan *plan);
+/* Testing aid: route D == 3 through the dimension-generic kernels instead of
+ * the fused 3-D level kernel (both are bit-identical by contract). */
+void mgb_plan_set_generic(mgb_plan *plan, int on);
 uint64_t mgb_plan_num_elems(const mgb_plan *plan);
 /* level_shape(l, d), Hierarchy.hpp:560-577 */
 uint64_t mgb_plan_level_shape(const mgb_plan *plan, int level, int dim);

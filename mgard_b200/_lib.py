@@ -40,6 +40,7 @@ SIGNATURES = {
     "mgb_plan_create": (_i32, [_i32, _pu64, _i32, C.POINTER(_vp), C.POINTER(MgbConfig), C.POINTER(_vp)]),
     "mgb_plan_destroy": (None, [_vp]),
     "mgb_plan_l_target": (_i32, [_vp]),
+    "mgb_plan_set_generic": (None, [_vp, _i32]),
     "mgb_plan_num_elems": (_u64, [_vp]),
     "mgb_plan_level_shape": (_u64, [_vp, _i32, _i32]),
     "mgb_plan_table": (_u64, [_vp, _i32, _i32, _i32, _vp, _u64]),

@@ -297,6 +297,10 @@ class Plan:
         except Exception:
             pass
 
+    def set_generic(self, on=True):
+        """Use the dimension-generic kernels for D == 3 (testing aid)."""
+        _lib.lib().mgb_plan_set_generic(self._h, 1 if on else 0)
+
     def level_shape(self, l):
         L = _lib.lib()
         return tuple(int(L.mgb_plan_level_shape(self._h, l, d)) for d in range(len(self.shape)))

@@ -572,54 +572,236 @@ __global__ void serialize_meta_kernel(unsigned char *__restrict__ out, u64 n, in
 }
 
 // ------------------------------- decode ------------------------------------
-// One thread per chunk (the stream is sequential inside a chunk); canonical
-// decode with first/entry/keys exactly as Decode.hpp:66-116.
-__global__ void __launch_bounds__(128)
-decode_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__restrict__ bits,
-              const u64 *__restrict__ woff, u64 nchunk, int chunk, u64 n,
-              const u64 *__restrict__ decodebook, int dict, uint16_t *__restrict__ out) {
-  extern __shared__ u64 s_db[]; // first[64] entry[64] + keys (u16) packed after
-  u64 *s_first = s_db, *s_entry = s_db + 64;
-  uint16_t *s_keys = (uint16_t *)(s_db + 128);
-  for (int i = threadIdx.x; i < 128; i += blockDim.x)
-    s_db[i] = decodebook[i];
-  for (int i = threadIdx.x; i < dict; i += blockDim.x)
-    s_keys[i] = (uint16_t)decodebook[128 + i];
-  __syncthreads();
-  int lmin = 1;
-  while (lmin < 63 && s_first[lmin] == ~0ull)
-    lmin++;
-  u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nchunk)
-    return;
-  const u64 total_bw = bits[c];
-  const u64 w0 = woff[c];
-  const u64 nw = (total_bw - 1) / 64 + 1;
-  const u64 *src = ddata + w0;
-  uint16_t *dst = out + c * (u64)chunk;
-  u64 nsym_max = min((u64)chunk, n - c * (u64)chunk);
-  u64 wi = 0;
-  u64 cur = src[0];
-  u64 nxt = (1 < nw) ? src[1] : 0ull;
-  unsigned used = 0;
-  u64 consumed = 0, produced = 0;
-  while (consumed < total_bw && produced < nsym_max) {
-    u64 window = used ? ((cur << used) | (nxt >> (64 - used))) : cur;
-    int l = lmin;
-    u64 v = window >> (64 - l);
-    while (v < s_first[l] && l < 63) {
-      l++;
-      v = window >> (64 - l);
-    }
-    u64 ki = s_entry[l] + v - s_first[l];
-    dst[produced++] = ki < (u64)dict ? s_keys[ki] : (uint16_t)0;
-    consumed += l;
+// The reference decodes one chunk per thread, bit by bit (Decode.hpp:66-116).
+// The stream format only guarantees that a CHUNK starts on a codeword (and
+// word) boundary, so here a thread block owns a chunk and finds the interior
+// codeword boundaries itself:
+//   1. the chunk's bit string is cut into 128-bit sub-sequences; every thread
+//      decodes its sub-sequences speculatively from their first bit;
+//   2. each sub-sequence then restarts from where its predecessor really ended
+//      until nothing changes (Huffman codes self-synchronise after a few
+//      codewords, so this takes 2-3 rounds in practice and is exact after at
+//      most #sub-sequences rounds);
+//   3. a block scan of the symbol counts gives every sub-sequence its output
+//      offset; a last decode pass writes the symbols into shared memory and the
+//      chunk is flushed to global memory with coalesced 128-bit stores.
+// Codewords are resolved through a 2^K-entry shared-memory table built from
+// first/entry/keys, falling back to the canonical walk for longer codes.
+constexpr int DEC_K = 12;     // LUT index bits
+constexpr int DEC_SB = 128;   // sub-sequence length in bits
+constexpr int DEC_T = 256;    // threads per block
+
+struct BitReader {
+  const u64 *w;
+  u64 nw, wi, cur, nxt;
+  unsigned used;
+  __device__ __forceinline__ void init(const u64 *words, u64 nwords, u64 bitpos) {
+    w = words;
+    nw = nwords;
+    wi = bitpos >> 6;
+    used = (unsigned)(bitpos & 63);
+    cur = wi < nw ? __ldg(w + wi) : 0ull;
+    nxt = wi + 1 < nw ? __ldg(w + wi + 1) : 0ull;
+  }
+  __device__ __forceinline__ u64 window() const {
+    return used ? ((cur << used) | (nxt >> (64 - used))) : cur;
+  }
+  __device__ __forceinline__ void advance(unsigned l) {
     used += l;
     if (used >= 64) {
       used -= 64;
       wi++;
       cur = nxt;
-      nxt = (wi + 1 < nw) ? src[wi + 1] : 0ull;
+      nxt = wi + 1 < nw ? __ldg(w + wi + 1) : 0ull;
+    }
+  }
+};
+
+struct DecTables {
+  const u64 *first, *entry; // shared
+  const unsigned *lut;      // shared: symbol | len << 16 (len 0: longer than K)
+  const uint16_t *keys;     // shared
+  int dict, lslow;
+};
+
+__device__ __forceinline__ unsigned decode_one(const DecTables &t, u64 window, unsigned &sym) {
+  unsigned e = t.lut[window >> (64 - DEC_K)];
+  unsigned len = e >> 16;
+  if (len) {
+    sym = e & 0xffffu;
+    return len;
+  }
+  int l = t.lslow;
+  u64 v = window >> (64 - l);
+  while (v < t.first[l] && l < 63) {
+    l++;
+    v = window >> (64 - l);
+  }
+  u64 ki = t.entry[l] + v - t.first[l];
+  sym = ki < (u64)t.dict ? t.keys[ki] : 0u;
+  return (unsigned)l;
+}
+
+// decode codewords that START in [start, limit); returns the end position
+// (first boundary >= limit) and the number of codewords.
+template <bool WRITE>
+__device__ __forceinline__ unsigned
+decode_sub(const DecTables &t, const u64 *words, u64 nw, unsigned start, unsigned limit,
+           unsigned &count, uint16_t *dst, unsigned dst_cap) {
+  BitReader br;
+  br.init(words, nw, start);
+  unsigned p = start, c = 0;
+  while (p < limit) {
+    unsigned sym;
+    unsigned l = decode_one(t, br.window(), sym);
+    if (WRITE) {
+      if (c < dst_cap)
+        dst[c] = (uint16_t)sym;
+    }
+    c++;
+    p += l;
+    br.advance(l);
+  }
+  count = c;
+  return p;
+}
+
+template <bool STAGE_OUT>
+__global__ void __launch_bounds__(DEC_T)
+decode_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__restrict__ bits,
+              const u64 *__restrict__ woff, u64 nchunk, int chunk, u64 n,
+              const u64 *__restrict__ decodebook, int dict, unsigned *__restrict__ sub_start,
+              unsigned *__restrict__ sub_end, unsigned *__restrict__ sub_cnt,
+              uint16_t *__restrict__ out) {
+  extern __shared__ u64 s_db[]; // first[64] entry[64] | lut | keys16 | outbuf
+  u64 *s_first = s_db, *s_entry = s_db + 64;
+  unsigned *s_lut = (unsigned *)(s_db + 128);
+  uint16_t *s_keys = (uint16_t *)(s_lut + (1 << DEC_K));
+  uint16_t *s_out = s_keys + ((dict + 7) & ~7);
+  __shared__ unsigned s_scan[DEC_T / 32];
+  __shared__ unsigned s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < 128; i += DEC_T)
+    s_db[i] = decodebook[i];
+  for (int i = tid; i < dict; i += DEC_T)
+    s_keys[i] = (uint16_t)decodebook[128 + i];
+  __syncthreads();
+  int lmin = 1;
+  while (lmin < 63 && s_first[lmin] == ~0ull)
+    lmin++;
+  for (int x = tid; x < (1 << DEC_K); x += DEC_T) {
+    unsigned e = 0;
+    for (int l = lmin; l <= DEC_K; l++) {
+      u64 v = (u64)x >> (DEC_K - l);
+      if (v >= s_first[l]) {
+        u64 ki = s_entry[l] + v - s_first[l];
+        e = (ki < (u64)dict ? (unsigned)s_keys[ki] : 0u) | ((unsigned)l << 16);
+        break;
+      }
+    }
+    s_lut[x] = e;
+  }
+  __syncthreads();
+  DecTables t;
+  t.first = s_first;
+  t.entry = s_entry;
+  t.lut = s_lut;
+  t.keys = s_keys;
+  t.dict = dict;
+  t.lslow = max(lmin, DEC_K + 1);
+
+  for (u64 c = blockIdx.x; c < nchunk; c += gridDim.x) {
+    const u64 B64 = bits[c];
+    const u64 w0 = woff[c];
+    const u64 nw = (B64 - 1) / 64 + 1;
+    const u64 *src = ddata + w0;
+    const unsigned B = (unsigned)B64;
+    const unsigned NS = (B + DEC_SB - 1) / DEC_SB;
+    const u64 sbase = (w0 * 64) / DEC_SB + c;
+    unsigned *st = sub_start + sbase, *en = sub_end + sbase, *cn = sub_cnt + sbase;
+    const unsigned nsym = (unsigned)min((u64)chunk, n - c * (u64)chunk);
+    // 1. speculative decode
+    for (unsigned i = tid; i < NS; i += DEC_T) {
+      unsigned cnt;
+      unsigned s0 = i * DEC_SB;
+      unsigned e = decode_sub<false>(t, src, nw, s0, min(B, s0 + DEC_SB), cnt, nullptr, 0);
+      st[i] = s0;
+      en[i] = e;
+      cn[i] = cnt;
+    }
+    __syncthreads();
+    // 2. synchronise
+    for (unsigned round = 0; round < NS; round++) {
+      int changed = 0;
+      for (unsigned i = tid; i < NS; i += DEC_T) {
+        if (i == 0)
+          continue;
+        unsigned s0 = en[i - 1];
+        if (s0 != st[i]) {
+          unsigned cnt = 0;
+          unsigned lim = min(B, (i + 1) * DEC_SB);
+          unsigned e = s0 >= lim ? s0 : decode_sub<false>(t, src, nw, s0, lim, cnt, nullptr, 0);
+          st[i] = s0;
+          en[i] = e;
+          cn[i] = cnt;
+          changed = 1;
+        }
+      }
+      if (!__syncthreads_or(changed))
+        break;
+    }
+    // 3 + 4. offsets and final decode
+    if (tid == 0)
+      s_carry = 0;
+    __syncthreads();
+    uint16_t *dst_base = STAGE_OUT ? s_out : out + c * (u64)chunk;
+    for (unsigned i0 = 0; i0 < NS; i0 += DEC_T) {
+      unsigned i = i0 + tid;
+      unsigned cnt = i < NS ? cn[i] : 0;
+      unsigned x = cnt;
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o)
+          x += y;
+      }
+      if (lane == 31)
+        s_scan[wid] = x;
+      __syncthreads();
+      unsigned wpre = 0, tot = 0;
+#pragma unroll
+      for (int k = 0; k < DEC_T / 32; k++) {
+        unsigned v = s_scan[k];
+        if (k < wid)
+          wpre += v;
+        tot += v;
+      }
+      unsigned off = s_carry + wpre + x - cnt;
+      if (i < NS && cnt) {
+        unsigned dummy;
+        unsigned s0 = st[i];
+        unsigned cap = off < nsym ? nsym - off : 0;
+        decode_sub<true>(t, src, nw, s0, min(B, (i + 1) * DEC_SB), dummy, dst_base + off, cap);
+      }
+      __syncthreads();
+      if (tid == 0)
+        s_carry += tot;
+      __syncthreads();
+    }
+    if (STAGE_OUT) {
+      uint16_t *g = out + c * (u64)chunk;
+      if ((((uintptr_t)g) & 15) == 0) {
+        const uint4 *s4 = (const uint4 *)s_out;
+        uint4 *g4 = (uint4 *)g;
+        unsigned n16 = nsym / 8;
+        for (unsigned k = tid; k < n16; k += DEC_T)
+          g4[k] = s4[k];
+        for (unsigned k = n16 * 8 + tid; k < nsym; k += DEC_T)
+          g[k] = s_out[k];
+      } else {
+        for (unsigned k = tid; k < nsym; k += DEC_T)
+          g[k] = s_out[k];
+      }
+      __syncthreads();
     }
   }
 }
@@ -834,14 +1016,38 @@ extern "C" int mgb_huffman_decompress(mgb_plan *p, const uint8_t *d_in, uint64_t
     *d_oidx = (const uint64_t *)(d_in + off);
   if (d_oval)
     *d_oval = (const int64_t *)(d_in + off + 8 * oc);
-  size_t smem = 128 * 8 + (size_t)dict * 2;
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  // scratch for the sub-sequence bookkeeping (3 x u32 per 128 stream bits)
+  {
+    u64 need = (total_words * 64) / DEC_SB + nchunk + 8;
+    if (p->dec_sub_cap < need) {
+      cudaFree(p->d_dec_sub);
+      p->d_dec_sub = nullptr;
+      p->dec_sub_cap = 0;
+      MGB_CUDA_CHECK(cudaMalloc(&p->d_dec_sub, need * 3 * sizeof(unsigned)));
+      p->dec_sub_cap = need;
+    }
+  }
+  unsigned *sub = p->d_dec_sub;
+  const u64 subn = p->dec_sub_cap;
+  size_t smem_tab = 128 * 8 + (size_t)(1 << DEC_K) * 4 + (size_t)((dict + 7) & ~7) * 2;
+  size_t smem_out = (size_t)chunk * 2 + 16;
+  unsigned blocks = (unsigned)std::min<u64>(nchunk, 148 * 8);
+  if (smem_tab + smem_out <= 160 * 1024) {
+    size_t smem = smem_tab + smem_out;
+    cudaFuncSetAttribute(decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem);
-  unsigned blocks = (unsigned)((nchunk + 127) / 128);
-  MGB_LAUNCH(MGB_K_DECODE, st,
-             (decode_kernel<<<blocks, 128, smem, st>>>(ddata, total_words, bits, woff, nchunk,
-                                                      chunk, n, decodebook, dict, d_sym)));
+    MGB_LAUNCH(MGB_K_DECODE, st,
+               (decode_kernel<true><<<blocks, DEC_T, smem, st>>>(
+                   ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict, sub,
+                   sub + subn, sub + 2 * subn, d_sym)));
+  } else {
+    cudaFuncSetAttribute(decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem_tab);
+    MGB_LAUNCH(MGB_K_DECODE, st,
+               (decode_kernel<false><<<blocks, DEC_T, smem_tab, st>>>(
+                   ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict, sub,
+                   sub + subn, sub + 2 * subn, d_sym)));
+  }
   MGB_CUDA_CHECK(cudaGetLastError());
   return MGB_SUCCESS;
 }

@@ -387,12 +387,17 @@ extern "C" void mgb_plan_destroy(mgb_plan *p) {
   cudaFree(p->d_oval);
   cudaFree(p->d_norm_tmp);
   cudaFree(p->d_cbwork);
+  cudaFree(p->d_dec_sub);
   if (p->h_pinned)
     cudaFreeHost(p->h_pinned);
   delete p;
 }
 
 extern "C" int mgb_plan_l_target(const mgb_plan *p) { return p ? p->L : -1; }
+extern "C" void mgb_plan_set_generic(mgb_plan *p, int on) {
+  if (p)
+    p->force_generic = on != 0;
+}
 extern "C" uint64_t mgb_plan_num_elems(const mgb_plan *p) {
   return p ? p->N : 0;
 }

@@ -41,6 +41,7 @@ struct mgb_plan {
   uint64_t N = 0;
   bool uniform = true;
   mgb_config cfg;
+  bool force_generic = false; // tests: use the dimension-generic kernels for D == 3
   std::vector<std::vector<double>> coords; // as doubles, for the header
   // hierarchy tables
   mgb_dim_tables tab[MGB_MAX_LEVELS][MGB_MAX_DIMS];
@@ -69,6 +70,8 @@ struct mgb_plan {
   uint64_t outlier_cap = 0;
   unsigned char *d_norm_tmp = nullptr; // reduction partials (doubles)
   unsigned char *d_cbwork = nullptr;   // codebook kernel scratch
+  unsigned *d_dec_sub = nullptr;       // decoder sub-sequence bookkeeping
+  uint64_t dec_sub_cap = 0;
   unsigned long long *h_pinned = nullptr; // pinned host scalars
 
   const unsigned char *dtab(uint64_t off) const { return d_tables + off * tsize; }

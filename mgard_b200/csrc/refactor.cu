@@ -20,8 +20,10 @@
 // in-place permutation passes.  All kernels are dimension-generic (D = 1..5)
 // through a (rows x fastest-dim) mapping: a thread block owns rows, threads
 // sweep the contiguous dimension, so every global access is coalesced.
+#include <algorithm>
 #include <cstdint>
 
+#include "fused3d.cuh"
 #include "plan.h"
 
 namespace {
@@ -552,6 +554,8 @@ void fill_tables(const mgb_plan *p, int l, Geom &g, bool masstrans) {
   }
 }
 
+template <typename T> void thomas_all(mgb_plan *p, int l, T *w, cudaStream_t st);
+
 // correction = Thomas_{f,c,r..}( MassTrans_{f,c,r..}( coefficient function ) )
 // (CalcCorrection3D.hpp:30-196), result dense with the coarse shape of level l-1
 // in *result (either d_wA or d_wB).
@@ -601,6 +605,73 @@ int correction(mgb_plan *p, int l, const T *coef, T **result, cudaStream_t st) {
     }
   }
   T *w = (T *)src; // dense, coarse shape
+  thomas_all<T>(p, l, w, st);
+  *result = w;
+  return MGB_SUCCESS;
+}
+
+template <typename T, int DS>
+void launch_coef(const Geom &g, const T *in, T *out, T *coarse, cudaStream_t st) {
+  dim3 grid, block;
+  row_launch_dims((g.n[DS] + 1) / 2, g.rows, grid, block);
+  MGB_LAUNCH(MGB_K_COEF, st, (coef_kernel<T, DS><<<grid, block, 0, st>>>(g, in, out, coarse)));
+}
+template <typename T, int DS>
+void launch_restore(const Geom &g, const T *coarse, const T *coef, T *out,
+                    cudaStream_t st) {
+  dim3 grid, block;
+  row_launch_dims((g.n[DS] + 1) / 2, g.rows, grid, block);
+  MGB_LAUNCH(MGB_K_RESTORE, st, (restore_kernel<T, DS><<<grid, block, 0, st>>>(g, coarse, coef, out)));
+}
+
+template <typename T>
+void axpy(T *acc, const T *w, i64 n, int subtract, cudaStream_t st) {
+  unsigned blocks = (unsigned)std::min<i64>((n + 255) / 256, 148 * 16);
+  MGB_LAUNCH(MGB_K_AXPY, st, (axpy_kernel<T><<<blocks, 256, 0, st>>>(acc, w, n, subtract)));
+}
+
+// D == 3: one fused launch per level (fused3d.cuh) instead of coef + 3 x mass_trans
+template <typename T, int MODE>
+int launch_fused3d(mgb_plan *p, int l, const T *in, const i64 *in_strides, T *coef_out,
+                   T *coarse_out, T *w_out, cudaStream_t st) {
+  fused3d::Params<T> P;
+  i64 full[5], dc[5];
+  dense_strides(p->shape, 3, full);
+  dense_strides(p->lshape[l - 1], 3, dc);
+  for (int d = 0; d < 3; d++) {
+    P.n[d] = (int)p->lshape[l][d];
+    P.nc[d] = (int)p->lshape[l - 1][d];
+    P.np[d] = 2 * P.nc[d] - 1;
+    P.sin[d] = in_strides[d];
+    P.sout[d] = full[d];
+    P.scoarse[d] = dc[d];
+    P.sw[d] = dc[d];
+    P.ratio[d] = (const T *)p->dtab(p->tab[l][d].ratio);
+    P.mt[d] = (const T *)p->dtab(p->tab[l][d].mt);
+  }
+  P.ctiles = (P.nc[1] + fused3d::TC - 1) / fused3d::TC;
+  P.ftiles = (P.nc[2] + fused3d::TF - 1) / fused3d::TF;
+  int tiles = P.ctiles * P.ftiles;
+  // enough blocks for ~16 per SM so that the last wave is a small fraction;
+  // every r segment re-reads two warm-up plane pairs, so keep them >= 8 planes
+  int rsegs = (148 * 16 + tiles - 1) / tiles;
+  rsegs = std::max(1, std::min(rsegs, std::max(1, P.nc[0] / 8)));
+  P.rsegs = rsegs;
+  size_t smem = fused3d::smem_bytes<T>(MODE);
+  if (smem > 48 * 1024) {
+    cudaFuncSetAttribute(fused3d::level_kernel<T, MODE>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+  unsigned grid = (unsigned)(tiles * rsegs);
+  MGB_LAUNCH(MODE == 0 ? MGB_K_COEF : MGB_K_MASSTRANS, st,
+             (fused3d::level_kernel<T, MODE><<<grid, fused3d::NT, smem, st>>>(
+                 P, in, coef_out, coarse_out, w_out)));
+  return MGB_SUCCESS;
+}
+
+// Thomas solves (all dims) in place on the dense coarse-shaped array w
+template <typename T> void thomas_all(mgb_plan *p, int l, T *w, cudaStream_t st) {
+  const int D = p->D;
   for (int a = D - 1; a >= 0; a--) {
     const mgb_dim_tables &m = p->tab[l - 1][a];
     const T *fw = (const T *)p->dtab(m.fw);
@@ -624,28 +695,6 @@ int correction(mgb_plan *p, int l, const T *coef, T **result, cudaStream_t st) {
                  (thomas_strided_kernel<T><<<blocks, 128, 0, st>>>(w, n, inner, lines, fw, am, bm)));
     }
   }
-  *result = w;
-  return MGB_SUCCESS;
-}
-
-template <typename T, int DS>
-void launch_coef(const Geom &g, const T *in, T *out, T *coarse, cudaStream_t st) {
-  dim3 grid, block;
-  row_launch_dims((g.n[DS] + 1) / 2, g.rows, grid, block);
-  MGB_LAUNCH(MGB_K_COEF, st, (coef_kernel<T, DS><<<grid, block, 0, st>>>(g, in, out, coarse)));
-}
-template <typename T, int DS>
-void launch_restore(const Geom &g, const T *coarse, const T *coef, T *out,
-                    cudaStream_t st) {
-  dim3 grid, block;
-  row_launch_dims((g.n[DS] + 1) / 2, g.rows, grid, block);
-  MGB_LAUNCH(MGB_K_RESTORE, st, (restore_kernel<T, DS><<<grid, block, 0, st>>>(g, coarse, coef, out)));
-}
-
-template <typename T>
-void axpy(T *acc, const T *w, i64 n, int subtract, cudaStream_t st) {
-  unsigned blocks = (unsigned)std::min<i64>((n + 255) / 256, 148 * 16);
-  MGB_LAUNCH(MGB_K_AXPY, st, (axpy_kernel<T><<<blocks, 256, 0, st>>>(acc, w, n, subtract)));
 }
 
 template <typename T>
@@ -674,6 +723,16 @@ int decompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
     dense_strides(p->lshape[l - 1], D, g.sc);
     fill_tables<T>(p, l, g, false);
     T *coarse = cbuf + p->cbuf_off[l - 1];
+    if (D == 3 && !p->force_generic) {
+      T *w = (T *)p->d_wA;
+      rc = launch_fused3d<T, 0>(p, l, cur, g.sa, d_out, coarse, w, st);
+      if (rc)
+        return rc;
+      thomas_all<T>(p, l, w, st);
+      axpy<T>(coarse, w, (i64)mgb_level_elems(p, l - 1), 0, st);
+      cur = coarse;
+      continue;
+    }
     switch (D) {
     case 1: launch_coef<T, 0>(g, cur, d_out, coarse, st); break;
     case 2: launch_coef<T, 1>(g, cur, d_out, coarse, st); break;
@@ -735,7 +794,14 @@ int recompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
   for (int l = 1; l <= p->L; l++) {
     T *coarse = cbuf + p->cbuf_off[l - 1];
     T *w = nullptr;
-    rc = correction<T>(p, l, d_in, &w, st);
+    if (D == 3 && !p->force_generic) {
+      w = (T *)p->d_wA;
+      rc = launch_fused3d<T, 1>(p, l, d_in, full, nullptr, nullptr, w, st);
+      if (!rc)
+        thomas_all<T>(p, l, w, st);
+    } else {
+      rc = correction<T>(p, l, d_in, &w, st);
+    }
     if (rc)
       return rc;
     axpy<T>(coarse, w, (i64)mgb_level_elems(p, l - 1), 1, st);

@@ -309,3 +309,16 @@ def test_full_size_properties_c2(env):
     lhs = p65.decompose(a + 2 * b)
     rhs = p65.decompose(a) + 2 * p65.decompose(b)
     assert float((lhs - rhs).abs().max()) < 1e-4
+
+
+def test_cxx_api_mirror_compiles_and_round_trips(env, tmp_path):
+    """include/mgard_b200/compress_x.hpp (mgard_x::compress / decompress mirror)."""
+    import subprocess
+    root = os.path.dirname(HERE)
+    exe = tmp_path / "api_roundtrip"
+    subprocess.check_call(["g++", "-std=c++17", f"-I{root}/include", f"{HERE}/cxx/api_roundtrip.cpp",
+                           "-o", str(exe), f"-L{root}/mgard_b200", "-lmgard_b200",
+                           f"-Wl,-rpath,{root}/mgard_b200", "-L/usr/local/cuda/lib64", "-lcudart"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "compress status 0" in out.stdout and "decompress status 0" in out.stdout

@@ -44,10 +44,15 @@ __device__ __forceinline__ int modn(int a, int n) {
 }
 
 // Single-block kernel.  d_codebook[dict], d_decodebook = first[64] entry[64] keys[dict].
+// key_smem: the sort buffer lives in dynamic shared memory; ncap: capacity (in
+// entries) of the shared-memory copies of the code-length work arrays, used when
+// the number of non-zero symbols fits (the loop below is a chain of short
+// dependent steps, so its cost is the latency of these arrays).
 __global__ void __launch_bounds__(1024)
 codebook_kernel(const unsigned *__restrict__ hist, int dict, int npow2, CbWork w,
                 u64 *__restrict__ codebook, u64 *__restrict__ decodebook,
-                int *__restrict__ status_out) {
+                int *__restrict__ status_out, int key_smem, int ncap) {
+  extern __shared__ __align__(16) unsigned char cb_smem[];
   const int tid = threadIdx.x, nt = blockDim.x;
   __shared__ int s_front, s_rear, s_lcur, s_isize, s_curleaves, s_mfront, s_mrear,
       s_templen, s_first_nz, s_continue;
@@ -56,8 +61,8 @@ codebook_kernel(const unsigned *__restrict__ hist, int dict, int npow2, CbWork w
   __shared__ u64 s_gbase[66];
   __shared__ int s_ngroups;
 
-  // 1. sort (freq, symbol) ascending: bitonic sort in global scratch
-  u64 *key = w.keys_sorted;
+  // 1. sort (freq, symbol) ascending: bitonic sort (shared memory when it fits)
+  u64 *key = key_smem ? reinterpret_cast<u64 *>(cb_smem) : w.keys_sorted;
   for (int i = tid; i < npow2; i += nt)
     key[i] = i < dict ? (((u64)hist[i] << 32) | (unsigned)i) : ~0ull;
   __syncthreads();
@@ -106,6 +111,17 @@ codebook_kernel(const unsigned *__restrict__ hist, int dict, int npow2, CbWork w
     return;
   }
   // 3. GenerateCL
+  if (n <= ncap) {
+    unsigned *b = reinterpret_cast<unsigned *>(cb_smem + (key_smem ? (size_t)npow2 * 8 : 0));
+    w.lfreq = b;
+    w.CL = b + ncap;
+    w.lleader = reinterpret_cast<int *>(b + 2 * ncap);
+    w.ifreq = b + 3 * ncap;
+    w.ileader = reinterpret_cast<int *>(b + 4 * ncap);
+    w.tfreq = b + 5 * ncap;
+    w.tindex = reinterpret_cast<int *>(b + 6 * ncap);
+    w.tleaf = reinterpret_cast<int *>(b + 7 * ncap);
+  }
   for (int i = tid; i < n; i += nt) {
     w.lfreq[i] = (unsigned)(key[first_nz + i] >> 32);
     w.CL[i] = 0;
@@ -259,26 +275,38 @@ codebook_kernel(const unsigned *__restrict__ hist, int dict, int npow2, CbWork w
   }
   // 4. GenerateCW.  Work in ascending-length order: r = n-1-k (k ascending freq)
   // groups of equal length
-  if (tid == 0) {
-    int ng = 0;
+  // group boundaries found by warp 0 (32 ranks per step), the rest by its lane 0
+  int ng = 0, ok = 0;
+  if (tid < 32) {
     int start = 0;
-    int ok = 0;
+    for (int r0 = 0; r0 < n; r0 += 32) {
+      const int r = r0 + tid;
+      unsigned cl = 0;
+      bool last = false;
+      if (r < n) {
+        cl = w.CL[n - 1 - r];
+        last = (r == n - 1) || (w.CL[n - 1 - (r + 1)] != cl);
+      }
+      unsigned m = __ballot_sync(0xffffffffu, last);
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const unsigned clb = __shfl_sync(0xffffffffu, cl, b);
+        if (tid == 0 && ng < 66) {
+          s_gs[ng] = start;
+          s_ge[ng] = r0 + b;
+          s_gl[ng] = (int)clb;
+        }
+        ng++;
+        start = r0 + b + 1;
+      }
+    }
+    __syncwarp();
+  }
+  if (tid == 0) {
     unsigned maxcl = w.CL[0]; // least frequent symbol has the longest code
     if (maxcl > 56)
       ok = 2; // GetCodebook.hpp:111-121: cannot store the codeword
-    for (int r = 0; r < n; r++) {
-      unsigned cl = w.CL[n - 1 - r];
-      bool last = (r == n - 1) || (w.CL[n - 1 - (r + 1)] != cl);
-      if (last) {
-        if (ng < 66) {
-          s_gs[ng] = start;
-          s_ge[ng] = r;
-          s_gl[ng] = (int)cl;
-        }
-        ng++;
-        start = r + 1;
-      }
-    }
     if (ng > 64)
       ok = 2;
     s_ngroups = ng > 64 ? 0 : ng;
@@ -672,7 +700,12 @@ decode_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__restr
               const u64 *__restrict__ woff, u64 nchunk, int chunk, u64 n,
               const u64 *__restrict__ decodebook, int dict, unsigned *__restrict__ sub_start,
               unsigned *__restrict__ sub_end, unsigned *__restrict__ sub_cnt,
-              uint16_t *__restrict__ out) {
+              uint16_t *__restrict__ out, const unsigned *__restrict__ n_skipped,
+              unsigned fast_bufw) {
+  // fast_bufw != 0: decode_fast_kernel ran first; only the chunks it skipped
+  // (more than fast_bufw words) are left, and usually there are none
+  if (fast_bufw && *n_skipped == 0)
+    return;
   extern __shared__ u64 s_db[]; // first[64] entry[64] | lut | keys16 | outbuf
   u64 *s_first = s_db, *s_entry = s_db + 64;
   unsigned *s_lut = (unsigned *)(s_db + 128);
@@ -714,6 +747,8 @@ decode_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__restr
     const u64 B64 = bits[c];
     const u64 w0 = woff[c];
     const u64 nw = (B64 - 1) / 64 + 1;
+    if (fast_bufw && nw <= fast_bufw && B64 != 0)
+      continue;
     const u64 *src = ddata + w0;
     const unsigned B = (unsigned)B64;
     const unsigned NS = (B + DEC_SB - 1) / DEC_SB;
@@ -806,6 +841,276 @@ decode_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__restr
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fast decoder: same self-synchronising scheme, but the whole chunk (bit
+// stream, sub-sequence bookkeeping, output) lives in shared memory and every
+// thread owns a CONTIGUOUS run of K sub-sequences, so
+//   * only the first sub-sequence of a thread starts speculatively; the rest of
+//     its run continues from the true previous end (one bit reader, no restarts);
+//   * a synchronisation round only re-decodes from the predecessor's end until
+//     the new parse lands on a recorded sub-sequence end (typically 1-2
+//     sub-sequences), and most threads are final after one round;
+//   * the last pass decodes each thread's run once more, writing symbols to a
+//     shared staging buffer that is flushed with 128-bit stores.
+// The bit reader keeps >= 33 valid bits in a 64-bit register refilled 32 bits
+// at a time; codes up to DEC_K bits resolve through the LUT, longer ones start
+// the canonical walk at the shortest length their DEC_K-bit prefix allows.
+// Chunks that do not fit the shared buffers are counted in *n_skipped and left
+// to decode_kernel.
+constexpr int DF_T = 512; // threads per block
+
+struct FastReader {
+  const unsigned *w32; // chunk words as 32-bit halves (shared memory, little-endian u64 words)
+  unsigned n32;
+  u64 buf;
+  int have;
+  unsigned h; // next half (stream order)
+  __device__ __forceinline__ unsigned half(unsigned k) const {
+    return k < n32 ? w32[k ^ 1u] : 0u;
+  }
+  __device__ __forceinline__ void init(unsigned bitpos) {
+    h = bitpos >> 5;
+    const unsigned off = bitpos & 31u;
+    buf = (((u64)half(h) << 32) | half(h + 1)) << off;
+    have = 64 - (int)off;
+    h += 2;
+  }
+  __device__ __forceinline__ void consume(unsigned len) {
+    buf <<= len;
+    have -= (int)len;
+    if (have <= 32) {
+      buf |= (u64)half(h) << (32 - have);
+      have += 32;
+      h++;
+    }
+  }
+  __device__ __forceinline__ u64 full_window(unsigned bitpos) const {
+    const unsigned k = bitpos >> 5, off = bitpos & 31u;
+    u64 w = ((u64)half(k) << 32) | half(k + 1);
+    if (off)
+      w = (w << off) | ((u64)half(k + 2) >> (32 - off));
+    return w;
+  }
+};
+
+struct FastTables {
+  const u64 *first, *entry; // shared
+  const unsigned *lut;      // shared: bit31 clear: symbol | len << 16; set: walk start << 16
+  const u64 *keys;          // global (decodebook + 128)
+  int dict;
+};
+
+template <bool WANT_SYM>
+__device__ __forceinline__ unsigned fast_decode_one(const FastTables &t, const FastReader &r,
+                                                    unsigned p, unsigned &sym) {
+  const unsigned e = t.lut[(unsigned)(r.buf >> (64 - DEC_K))];
+  if (!(e & 0x80000000u)) {
+    sym = e & 0xffffu;
+    return e >> 16;
+  }
+  int l = (int)((e >> 16) & 0xffu);
+  u64 win = l > 32 ? r.full_window(p) : r.buf;
+  u64 v = win >> (64 - l);
+  while (v < t.first[l] && l < 63) {
+    l++;
+    if (l == 33)
+      win = r.full_window(p);
+    v = win >> (64 - l);
+  }
+  if (WANT_SYM) {
+    const u64 ki = t.entry[l] + v - t.first[l];
+    sym = ki < (u64)t.dict ? (unsigned)__ldg(t.keys + ki) : 0u;
+  }
+  return (unsigned)l;
+}
+
+__global__ void __launch_bounds__(DF_T, 2)
+decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
+                   const u64 *__restrict__ woff, u64 nchunk, int chunk, u64 n,
+                   const u64 *__restrict__ decodebook, int dict, unsigned bufw,
+                   unsigned *__restrict__ n_skipped, uint16_t *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char df_smem[];
+  u64 *s_first = reinterpret_cast<u64 *>(df_smem), *s_entry = s_first + 64;
+  unsigned *s_lut = reinterpret_cast<unsigned *>(s_first + 128);
+  u64 *s_words = reinterpret_cast<u64 *>(s_lut + (1 << DEC_K));
+  const unsigned nslot = bufw / 2 + DF_T; // sub-sequence slots
+  unsigned *s_en = reinterpret_cast<unsigned *>(s_words + bufw);
+  unsigned *s_st = s_en + nslot;
+  unsigned char *s_cn = reinterpret_cast<unsigned char *>(s_st + DF_T);
+  uint16_t *s_out = reinterpret_cast<uint16_t *>(s_cn + ((nslot + 15) & ~15u));
+  __shared__ unsigned s_scan[DF_T / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+  for (int i = tid; i < 128; i += DF_T)
+    s_first[i] = decodebook[i];
+  __syncthreads();
+  int lmin = 1;
+  while (lmin < 63 && s_first[lmin] == ~0ull)
+    lmin++;
+  for (int x = tid; x < (1 << DEC_K); x += DF_T) {
+    unsigned e = 0xffffffffu;
+    for (int l = lmin; l <= DEC_K; l++) {
+      const u64 v = (u64)x >> (DEC_K - l);
+      if (v >= s_first[l]) {
+        const u64 ki = s_entry[l] + v - s_first[l];
+        e = (ki < (u64)dict ? (unsigned)(decodebook[128 + ki] & 0xffffu) : 0u) | ((unsigned)l << 16);
+        break;
+      }
+    }
+    if (e == 0xffffffffu) {
+      // longer than DEC_K bits: shortest length this prefix can still carry
+      int l = max(lmin, DEC_K + 1);
+      while (l < 63) {
+        const u64 vmax = (((u64)x + 1) << (l - DEC_K)) - 1;
+        if (s_first[l] != ~0ull && vmax >= s_first[l])
+          break;
+        l++;
+      }
+      e = 0x80000000u | ((unsigned)l << 16);
+    }
+    s_lut[x] = e;
+  }
+  __syncthreads();
+  FastTables t;
+  t.first = s_first;
+  t.entry = s_entry;
+  t.lut = s_lut;
+  t.keys = decodebook + 128;
+  t.dict = dict;
+
+  for (u64 c = blockIdx.x; c < nchunk; c += gridDim.x) {
+    const u64 B64 = bits[c];
+    const u64 nw64 = (B64 - 1) / 64 + 1;
+    if (nw64 > bufw || B64 == 0) {
+      if (tid == 0)
+        atomicAdd(n_skipped, 1u);
+      continue;
+    }
+    const unsigned B = (unsigned)B64, nw = (unsigned)nw64;
+    const u64 *src = ddata + woff[c];
+    const unsigned nsym = (unsigned)min((u64)chunk, n - c * (u64)chunk);
+    // 0. chunk words -> shared memory
+    for (unsigned i = tid; i < nw; i += DF_T) {
+      const unsigned d = (unsigned)__cvta_generic_to_shared(s_words + i);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src + i));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    // run geometry: K sub-sequences of DEC_SB bits per thread
+    const unsigned NS = (B + DEC_SB - 1) / DEC_SB;
+    const unsigned K = (NS + DF_T - 1) / DF_T;
+    const unsigned run0 = tid * K * DEC_SB; // first bit of this thread's run
+    const bool active = run0 < B;
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    FastReader r;
+    r.w32 = reinterpret_cast<const unsigned *>(s_words);
+    r.n32 = 2 * nw;
+    // 1. speculative pass over the run
+    if (active) {
+      unsigned p = run0;
+      r.init(p);
+      for (unsigned j = 0; j < K; j++) {
+        const unsigned i = tid * K + j;
+        const unsigned lim = min(B, (i + 1) * DEC_SB);
+        unsigned cnt = 0;
+        while (p < lim) {
+          unsigned sym;
+          const unsigned l = fast_decode_one<false>(t, r, p, sym);
+          p += l;
+          cnt++;
+          r.consume(l);
+        }
+        s_en[i] = p;
+        s_cn[i] = (unsigned char)cnt;
+      }
+      s_st[tid] = run0;
+    }
+    __syncthreads();
+    // 2. synchronise: restart from the predecessor's end until the parse meets
+    //    a recorded sub-sequence end
+    for (unsigned round = 0; round <= DF_T; round++) {
+      int changed = 0;
+      if (active && tid > 0) {
+        const unsigned s0 = s_en[tid * K - 1];
+        if (s0 != s_st[tid]) {
+          changed = 1;
+          s_st[tid] = s0;
+          unsigned p = s0;
+          r.init(p);
+          for (unsigned j = 0; j < K; j++) {
+            const unsigned i = tid * K + j;
+            const unsigned lim = min(B, (i + 1) * DEC_SB);
+            unsigned cnt = 0;
+            while (p < lim) {
+              unsigned sym;
+              const unsigned l = fast_decode_one<false>(t, r, p, sym);
+              p += l;
+              cnt++;
+              r.consume(l);
+            }
+            const bool met = (p == s_en[i]);
+            s_en[i] = p;
+            s_cn[i] = (unsigned char)cnt;
+            if (met)
+              break;
+          }
+        }
+      }
+      if (!__syncthreads_or(changed))
+        break;
+    }
+    // 3. output offsets (block scan of the per-run symbol counts) + final pass
+    unsigned cnt = 0;
+    if (active)
+      for (unsigned j = 0; j < K; j++)
+        cnt += s_cn[tid * K + j];
+    unsigned x = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o)
+        x += y;
+    }
+    if (lane == 31)
+      s_scan[wid] = x;
+    __syncthreads();
+    unsigned wpre = 0;
+#pragma unroll
+    for (int k = 0; k < DF_T / 32; k++)
+      if (k < wid)
+        wpre += s_scan[k];
+    unsigned off = wpre + x - cnt;
+    if (active && cnt) {
+      unsigned p = tid ? s_en[tid * K - 1] : 0u;
+      const unsigned lim = min(B, (tid + 1) * K * DEC_SB);
+      r.init(p);
+      while (p < lim) {
+        unsigned sym;
+        const unsigned l = fast_decode_one<true>(t, r, p, sym);
+        if (off < nsym)
+          s_out[off] = (uint16_t)sym;
+        off++;
+        p += l;
+        r.consume(l);
+      }
+    }
+    __syncthreads();
+    uint16_t *g = out + c * (u64)chunk;
+    if ((((uintptr_t)g) & 15) == 0) {
+      const uint4 *s4 = reinterpret_cast<const uint4 *>(s_out);
+      uint4 *g4 = reinterpret_cast<uint4 *>(g);
+      const unsigned n16 = nsym / 8;
+      for (unsigned k = tid; k < n16; k += DF_T)
+        __stcs(g4 + k, s4[k]);
+      for (unsigned k = n16 * 8 + tid; k < nsym; k += DF_T)
+        g[k] = s_out[k];
+    } else {
+      for (unsigned k = tid; k < nsym; k += DF_T)
+        g[k] = s_out[k];
+    }
+    __syncthreads();
+  }
+}
+
 // decodebook_size, ddata word count and outlier count of a serialised block
 // (Huffman.hpp:293-312); ~0 marks a truncated stream.
 __global__ void parse_sizes_kernel(const unsigned char *__restrict__ p, u64 off, u64 size,
@@ -872,10 +1177,22 @@ extern "C" int mgb_codebook(mgb_plan *p, const uint32_t *d_hist, uint64_t *d_cod
   w.tfreq = (unsigned *)b; b += (size_t)dict * 4;
   w.tindex = (int *)b; b += (size_t)dict * 4;
   w.tleaf = (int *)b; b += (size_t)dict * 4;
+  // shared memory: sort buffer (8 B x npow2) + 8 work arrays of ncap entries
+  const size_t smem_max = 200 * 1024;
+  const int key_smem = (size_t)npow2 * 8 <= 128 * 1024;
+  size_t left = smem_max - (key_smem ? (size_t)npow2 * 8 : 0);
+  int ncap = (int)std::min<size_t>(left / 32, (size_t)dict);
+  const size_t smem = (key_smem ? (size_t)npow2 * 8 : 0) + (size_t)ncap * 32;
+  static bool configured = false;
+  if (!configured) {
+    MGB_CUDA_CHECK(cudaFuncSetAttribute(codebook_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_max));
+    configured = true;
+  }
   MGB_LAUNCH(MGB_K_CODEBOOK, (cudaStream_t)stream,
-             (codebook_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+             (codebook_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(
                  d_hist, dict, npow2, w, (u64 *)d_codebook, (u64 *)d_decodebook,
-                 (int *)(p->d_scalars + 8))));
+                 (int *)(p->d_scalars + 8), key_smem, ncap)));
   MGB_CUDA_CHECK(cudaGetLastError());
   return MGB_SUCCESS;
 }
@@ -1029,6 +1346,45 @@ extern "C" int mgb_huffman_decompress(mgb_plan *p, const uint8_t *d_in, uint64_t
   }
   unsigned *sub = p->d_dec_sub;
   const u64 subn = p->dec_sub_cap;
+  // fast path: chunks staged in shared memory (2 blocks of 512 threads per SM).
+  // The word buffer is sized from the average chunk (+25 %, at least 2 KB more).
+  unsigned fast_bufw = 0;
+  unsigned *n_skipped = (unsigned *)((u64 *)p->d_scalars + 15);
+  {
+    const size_t budget = 113 * 1024 - 512;
+    const size_t fixed = 128 * 8 + (size_t)(1 << DEC_K) * 4 + (size_t)DF_T * 4 +
+                         (((size_t)chunk * 2 + 15) & ~(size_t)15) + 64;
+    u64 avg = total_words / nchunk + 1;
+    u64 want = avg + avg / 4 + 256;
+    if (fixed < budget) {
+      // per word: 8 B data + 2 B end slot + 0.5 B count
+      size_t maxw = (budget - fixed - (size_t)DF_T * 5) * 2 / 21;
+      if (want > maxw && avg + avg / 16 + 32 <= maxw)
+        want = maxw;
+      if (want <= maxw)
+        fast_bufw = (unsigned)(want & ~(u64)1);
+    }
+  }
+  if (fast_bufw) {
+    const unsigned nslot = fast_bufw / 2 + DF_T;
+    const size_t smem = 128 * 8 + (size_t)(1 << DEC_K) * 4 + (size_t)fast_bufw * 8 +
+                        (size_t)nslot * 4 + (size_t)DF_T * 4 + ((nslot + 15) & ~15u) +
+                        (((size_t)chunk * 2 + 15) & ~(size_t)15);
+    static bool configured = false;
+    if (!configured) {
+      MGB_CUDA_CHECK(cudaFuncSetAttribute(decode_fast_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      cudaFuncSetAttribute(decode_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+      configured = true;
+    }
+    MGB_CUDA_CHECK(cudaMemsetAsync(n_skipped, 0, sizeof(unsigned), st));
+    unsigned fblocks = (unsigned)std::min<u64>(nchunk, 148 * 2);
+    MGB_LAUNCH(MGB_K_DECODE, st,
+               (decode_fast_kernel<<<fblocks, DF_T, smem, st>>>(ddata, bits, woff, nchunk, chunk, n,
+                                                               decodebook, dict, fast_bufw,
+                                                               n_skipped, d_sym)));
+  }
   size_t smem_tab = 128 * 8 + (size_t)(1 << DEC_K) * 4 + (size_t)((dict + 7) & ~7) * 2;
   size_t smem_out = (size_t)chunk * 2 + 16;
   unsigned blocks = (unsigned)std::min<u64>(nchunk, 148 * 8);
@@ -1039,14 +1395,14 @@ extern "C" int mgb_huffman_decompress(mgb_plan *p, const uint8_t *d_in, uint64_t
     MGB_LAUNCH(MGB_K_DECODE, st,
                (decode_kernel<true><<<blocks, DEC_T, smem, st>>>(
                    ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict, sub,
-                   sub + subn, sub + 2 * subn, d_sym)));
+                   sub + subn, sub + 2 * subn, d_sym, n_skipped, fast_bufw)));
   } else {
     cudaFuncSetAttribute(decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem_tab);
     MGB_LAUNCH(MGB_K_DECODE, st,
                (decode_kernel<false><<<blocks, DEC_T, smem_tab, st>>>(
                    ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict, sub,
-                   sub + subn, sub + 2 * subn, d_sym)));
+                   sub + subn, sub + 2 * subn, d_sym, n_skipped, fast_bufw)));
   }
   MGB_CUDA_CHECK(cudaGetLastError());
   return MGB_SUCCESS;

@@ -84,34 +84,113 @@ outlier_append(bool is_out, unsigned long long idx, long long qi,
   }
 }
 
+// vector of 16 bytes of T
+template <typename T> struct Vec16;
+template <> struct Vec16<float> { typedef float4 type; static constexpr int n = 4; };
+template <> struct Vec16<double> { typedef double2 type; static constexpr int n = 2; };
+
+// s = inf: one quantizer for every node (LinearQuantization.hpp:170-176), so the
+// array is a flat stream.  Each thread handles PER consecutive elements per
+// iteration through 128-bit loads (two vectors in flight for fp32, four for
+// fp64) and stores its symbols with one 128-bit store.  Histogram: shared memory,
+// one atomic per run of equal symbols inside a thread, a single atomic per warp
+// when all 32 lanes agree (smooth data); outliers take a ballot-guarded slow path.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 quantize_linear_kernel(const T *__restrict__ v, i64 N, T q, T vol, int dict,
                        uint16_t *__restrict__ sym, unsigned *__restrict__ ghist,
                        unsigned long long *__restrict__ ocount,
                        uint64_t *__restrict__ oidx, i64 *__restrict__ oval,
                        unsigned long long ocap) {
   extern __shared__ unsigned sh[];
+  typedef typename Vec16<T>::type V;
+  constexpr int VN = Vec16<T>::n, PER = 8, NV = PER / VN;
   for (int i = threadIdx.x; i < dict; i += blockDim.x)
     sh[i] = 0;
   __syncthreads();
-  i64 stride = (i64)gridDim.x * blockDim.x;
-  i64 nround = (N + stride - 1) / stride * stride;
-  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-    bool valid = i < N;
-    unsigned s = 0;
-    long long qi = 0;
-    bool is_out = false;
+  // full groups of PER elements (none when an array is not 16-byte aligned)
+  const bool aligned = (((uintptr_t)v | (uintptr_t)sym) & 15) == 0;
+  const i64 ngroups = aligned ? N / PER : 0;
+  const i64 gstride = (i64)gridDim.x * blockDim.x;
+  const i64 ground = (ngroups + gstride - 1) / gstride * gstride;
+  for (i64 gi = (i64)blockIdx.x * blockDim.x + threadIdx.x; gi < ground; gi += gstride) {
+    const bool valid = gi < ngroups;
+    unsigned s[PER];
+    long long qi[PER];
+    bool any_out = false;
     if (valid) {
-      qi = quantize_one<T>(v[i], q, vol, dict);
-      if (qi >= 0 && qi < dict)
-        s = (unsigned)qi;
-      else
-        is_out = true;
-      sym[i] = (uint16_t)s;
+      V raw[NV];
+#pragma unroll
+      for (int k = 0; k < NV; k++)
+        raw[k] = __ldcs(reinterpret_cast<const V *>(v + gi * PER) + k);
+      const T *x = reinterpret_cast<const T *>(raw);
+#pragma unroll
+      for (int k = 0; k < PER; k++) {
+        qi[k] = quantize_one<T>(x[k], q, vol, dict);
+        const bool in = qi[k] >= 0 && qi[k] < dict;
+        s[k] = in ? (unsigned)qi[k] : 0u;
+        any_out |= !in;
+      }
+      uint4 pk;
+      pk.x = s[0] | (s[1] << 16);
+      pk.y = s[2] | (s[3] << 16);
+      pk.z = s[4] | (s[5] << 16);
+      pk.w = s[6] | (s[7] << 16);
+      reinterpret_cast<uint4 *>(sym)[gi] = pk;
     }
-    outlier_append(is_out, (unsigned long long)i, qi, ocount, oidx, oval, ocap);
-    hist_add(sh, s, valid);
+    if (__any_sync(0xffffffffu, any_out)) {
+#pragma unroll
+      for (int k = 0; k < PER; k++) {
+        const bool o = valid && !(qi[k] >= 0 && qi[k] < dict);
+        outlier_append(o, (unsigned long long)(gi * PER + k), valid ? qi[k] : 0, ocount, oidx,
+                       oval, ocap);
+      }
+    }
+    // histogram
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      unsigned run = 1;
+      int allsame = 0;
+#pragma unroll
+      for (int k = 1; k < PER; k++)
+        allsame += s[k] == s[0];
+      int pred = 0;
+      if (act == 0xffffffffu)
+        __match_all_sync(0xffffffffu, allsame == PER - 1 ? s[0] : 0xffffffffu - (threadIdx.x & 31), &pred);
+      if (pred) {
+        if ((threadIdx.x & 31) == 0)
+          atomicAdd(&sh[s[0]], 32u * PER);
+      } else {
+#pragma unroll
+        for (int k = 1; k < PER; k++) {
+          if (s[k] == s[k - 1]) {
+            run++;
+          } else {
+            atomicAdd(&sh[s[k - 1]], run);
+            run = 1;
+          }
+        }
+        atomicAdd(&sh[s[PER - 1]], run);
+      }
+    }
+  }
+  // remainder (and everything, when the arrays are not 16-byte aligned): scalar
+  for (i64 i0 = ngroups * PER + (i64)blockIdx.x * blockDim.x; i0 < N; i0 += gstride) {
+    const i64 i = i0 + threadIdx.x;
+    const bool valid = i < N;
+    long long q1 = 0;
+    unsigned s1 = 0;
+    bool o = false;
+    if (valid) {
+      q1 = quantize_one<T>(v[i], q, vol, dict);
+      if (q1 >= 0 && q1 < dict)
+        s1 = (unsigned)q1;
+      else
+        o = true;
+      sym[i] = (uint16_t)s1;
+      atomicAdd(&sh[s1], 1u);
+    }
+    outlier_append(o, (unsigned long long)i, q1, ocount, oidx, oval, ocap);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < dict; i += blockDim.x) {
@@ -179,10 +258,29 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 dequantize_linear_kernel(const uint16_t *__restrict__ sym, i64 N, T qv, int dict,
                          T *__restrict__ v) {
-  i64 stride = (i64)gridDim.x * blockDim.x;
-  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-    long long qi = (long long)sym[i] - dict / 2;
-    v[i] = qv * (T)qi; // (quantizer * volume) * (T)quantized
+  typedef typename Vec16<T>::type V;
+  constexpr int VN = Vec16<T>::n, PER = 8, NV = PER / VN;
+  const bool aligned = (((uintptr_t)v | (uintptr_t)sym) & 15) == 0;
+  const i64 ngroups = aligned ? N / PER : 0;
+  const i64 gstride = (i64)gridDim.x * blockDim.x;
+  const int half = dict / 2;
+  for (i64 gi = (i64)blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups; gi += gstride) {
+    const uint4 pk = __ldcs(reinterpret_cast<const uint4 *>(sym) + gi);
+    const unsigned w[4] = {pk.x, pk.y, pk.z, pk.w};
+    V outv[NV];
+    T *x = reinterpret_cast<T *>(outv);
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      const long long qi = (long long)((w[k >> 1] >> (16 * (k & 1))) & 0xffffu) - half;
+      x[k] = qv * (T)qi; // (quantizer * volume) * (T)quantized
+    }
+#pragma unroll
+    for (int k = 0; k < NV; k++)
+      reinterpret_cast<V *>(v + gi * PER)[k] = outv[k];
+  }
+  for (i64 i = ngroups * PER + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gstride) {
+    long long qi = (long long)sym[i] - half;
+    v[i] = qv * (T)qi;
   }
 }
 
@@ -240,12 +338,68 @@ __global__ void outlier_restore_kernel(const QParams p, const Tables<T> tb,
 template <typename T>
 __global__ void __launch_bounds__(256)
 norm_partial_kernel(const T *__restrict__ v, i64 N, double *__restrict__ part) {
+  typedef typename Vec16<T>::type V;
+  constexpr int VN = Vec16<T>::n;
   double mx = 0.0, ss = 0.0;
-  i64 stride = (i64)gridDim.x * blockDim.x;
-  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-    double x = (double)v[i];
+  // leading elements up to the first 16-byte boundary (sub-domain pointers are
+  // only element aligned), then whole vectors, then the remainder
+  i64 head = (i64)(((16 - ((uintptr_t)v & 15)) & 15) / sizeof(T));
+  if (((uintptr_t)v % sizeof(T)) != 0 || head > N)
+    head = N;
+  if (blockIdx.x == 0 && threadIdx.x < head && head < 16) {
+    double x = (double)v[threadIdx.x];
     mx = fmax(mx, fabs(x));
     ss += x * x;
+  }
+  if (head >= 16) { // misaligned element type: scalar everything
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (i64)gridDim.x * blockDim.x) {
+      double x = (double)v[k];
+      mx = fmax(mx, fabs(x));
+      ss += x * x;
+    }
+    N = 0;
+    head = 0;
+  }
+  v += head;
+  N -= head;
+  const i64 nvec = N / VN;
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  // two vectors in flight per thread
+  for (; i + stride < nvec; i += 2 * stride) {
+    V a = __ldcs(reinterpret_cast<const V *>(v) + i);
+    V b = __ldcs(reinterpret_cast<const V *>(v) + i + stride);
+    const T *xa = reinterpret_cast<const T *>(&a), *xb = reinterpret_cast<const T *>(&b);
+#pragma unroll
+    for (int k = 0; k < VN; k++) {
+      double x = (double)xa[k];
+      mx = fmax(mx, fabs(x));
+      ss += x * x;
+    }
+#pragma unroll
+    for (int k = 0; k < VN; k++) {
+      double x = (double)xb[k];
+      mx = fmax(mx, fabs(x));
+      ss += x * x;
+    }
+  }
+  for (; i < nvec; i += stride) {
+    V a = reinterpret_cast<const V *>(v)[i];
+    const T *xa = reinterpret_cast<const T *>(&a);
+#pragma unroll
+    for (int k = 0; k < VN; k++) {
+      double x = (double)xa[k];
+      mx = fmax(mx, fabs(x));
+      ss += x * x;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < VN) {
+    const i64 t = nvec * VN + threadIdx.x;
+    if (t < N) {
+      double x = (double)v[t];
+      mx = fmax(mx, fabs(x));
+      ss += x * x;
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -376,7 +530,7 @@ int quantize_t(mgb_plan *p, const T *d_coef, int ebtype, double tol, double s,
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(quantize_linear_kernel<T>,
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    unsigned blocks = (unsigned)std::min<i64>((p->N + 255) / 256, 148 * 6);
+    unsigned blocks = (unsigned)std::min<i64>((p->N + 2047) / 2048, 148 * 4);
     MGB_LAUNCH(MGB_K_QUANTIZE, st,
                (quantize_linear_kernel<T><<<blocks, 256, smem, st>>>(
                    d_coef, (i64)p->N, tb.q[0], tb.vol[0], dict, d_sym, d_hist, d_ocount,
@@ -406,7 +560,7 @@ int dequantize_t(mgb_plan *p, const uint16_t *d_sym, uint64_t ocount,
   Tables<T> tb;
   make_params<T>(p, ebtype, tol, s, norm, true, qp, tb);
   if (!qp.calc_level) {
-    unsigned blocks = (unsigned)std::min<i64>((p->N + 255) / 256, 148 * 16);
+    unsigned blocks = (unsigned)std::min<i64>((p->N + 2047) / 2048, 148 * 8);
     MGB_LAUNCH(MGB_K_DEQUANTIZE, st,
                (dequantize_linear_kernel<T><<<blocks, 256, 0, st>>>(
                    d_sym, (i64)p->N, tb.q[0] * tb.vol[0], qp.dict, d_coef)));

@@ -402,12 +402,14 @@ __global__ void __launch_bounds__(128) thomas_strided_kernel(T *__restrict__ x, 
                                                              i64 lines,
                                                              const T *__restrict__ fw,
                                                              const T *__restrict__ am,
-                                                             const T *__restrict__ bm) {
+                                                             const T *__restrict__ bm,
+                                                             T *__restrict__ acc, int mode) {
   i64 line = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (line >= lines)
     return;
   i64 o = line / inner, in = line - o * inner;
-  T *p = x + o * (i64)n * inner + in;
+  const i64 off0 = o * (i64)n * inner + in;
+  T *p = x + off0;
   T prev = (T)0;
   constexpr int U = 8;
   int i = 0;
@@ -428,20 +430,43 @@ __global__ void __launch_bounds__(128) thomas_strided_kernel(T *__restrict__ x, 
   }
   prev = (T)0;
   i = n - 1;
-  for (; i - U + 1 >= 0; i -= U) {
-    T v[U];
+  if (mode == 0) {
+    for (; i - U + 1 >= 0; i -= U) {
+      T v[U];
 #pragma unroll
-    for (int k = 0; k < U; k++)
-      v[k] = p[(i64)(i - k) * inner];
+      for (int k = 0; k < U; k++)
+        v[k] = p[(i64)(i - k) * inner];
 #pragma unroll
-    for (int k = 0; k < U; k++) {
-      prev = (v[k] - am[i - k + 1] * prev) / bm[i - k + 1];
-      p[(i64)(i - k) * inner] = prev;
+      for (int k = 0; k < U; k++) {
+        prev = (v[k] - am[i - k + 1] * prev) / bm[i - k + 1];
+        p[(i64)(i - k) * inner] = prev;
+      }
     }
-  }
-  for (; i >= 0; i--) {
-    prev = (p[(i64)i * inner] - am[i + 1] * prev) / bm[i + 1];
-    p[(i64)i * inner] = prev;
+    for (; i >= 0; i--) {
+      prev = (p[(i64)i * inner] - am[i + 1] * prev) / bm[i + 1];
+      p[(i64)i * inner] = prev;
+    }
+  } else {
+    // last solve of a correction: the result is added to / subtracted from acc
+    T *q = acc + off0;
+    for (; i - U + 1 >= 0; i -= U) {
+      T v[U], a[U];
+#pragma unroll
+      for (int k = 0; k < U; k++) {
+        v[k] = p[(i64)(i - k) * inner];
+        a[k] = q[(i64)(i - k) * inner];
+      }
+#pragma unroll
+      for (int k = 0; k < U; k++) {
+        prev = (v[k] - am[i - k + 1] * prev) / bm[i - k + 1];
+        q[(i64)(i - k) * inner] = mode == 1 ? a[k] + prev : a[k] - prev;
+      }
+    }
+    for (; i >= 0; i--) {
+      prev = (p[(i64)i * inner] - am[i + 1] * prev) / bm[i + 1];
+      const T a = q[(i64)i * inner];
+      q[(i64)i * inner] = mode == 1 ? a + prev : a - prev;
+    }
   }
 }
 
@@ -501,6 +526,146 @@ __global__ void __launch_bounds__(128) thomas_contig_kernel(T *__restrict__ x, i
   }
 }
 
+// Thomas solve with the whole line set of a thread block staged in shared
+// memory.  A block owns W lines of the (outer, n, inner) view: W consecutive
+// lines along the contiguous axis (inner == 1) or W neighbouring columns of one
+// outer slice (inner > 1).  Every line is brought in with asynchronous copies
+// (all in flight at once, coalesced), the two sequential sweeps then run out
+// of shared memory (the recurrence, not memory latency, bounds them), and the
+// result goes back coalesced.  mode 1 / 2: the result is added to / subtracted
+// from `acc` instead of being stored (AddND / SubtractND of
+// DataRefactoring.hpp:99,241 fused into the last solve).
+template <typename T, int W>
+__global__ void __launch_bounds__(W)
+thomas_smem_kernel(T *__restrict__ x, int n, i64 inner, i64 lines,
+                   const T *__restrict__ fw, const T *__restrict__ am,
+                   const T *__restrict__ bm, T *__restrict__ acc, int mode) {
+  extern __shared__ __align__(16) unsigned char thomas_smem[];
+  T *s = reinterpret_cast<T *>(thomas_smem);
+  constexpr int P = W + 1;
+  const int lane = threadIdx.x;
+  const unsigned sbase = (unsigned)__cvta_generic_to_shared(s);
+  bool mine;      // this thread owns a line
+  i64 gbase;      // strided: element 0 of the thread's line; contiguous: of the block
+  int nl = W;     // contiguous: lines of this block
+  if (inner == 1) {
+    const i64 line0 = (i64)blockIdx.x * W;
+    nl = (int)min((i64)W, lines - line0);
+    mine = lane < nl;
+    gbase = line0 * n;
+    // line t, elements i0 + lane: coalesced segments, transposed into s[i][t]
+    for (int t = 0; t < nl; t++) {
+      const T *g = x + gbase + (i64)t * n;
+      unsigned d = sbase + (unsigned)((lane * P + t) * sizeof(T));
+      for (int i = lane; i < n; i += W) {
+        if (sizeof(T) == 4)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(g + i));
+        else
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(g + i));
+        d += (unsigned)(W * P * sizeof(T));
+      }
+    }
+  } else {
+    const i64 chunks = (inner + W - 1) / W;
+    const i64 o = blockIdx.x / chunks;
+    const i64 in0 = (blockIdx.x - o * chunks) * W;
+    mine = in0 + lane < inner;
+    gbase = o * (i64)n * inner + in0 + lane;
+    if (mine) {
+      const T *g = x + gbase;
+      unsigned d = sbase + (unsigned)(lane * sizeof(T));
+#pragma unroll 4
+      for (int i = 0; i < n; i++) {
+        if (sizeof(T) == 4)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(g));
+        else
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(g));
+        d += (unsigned)(P * sizeof(T));
+        g += inner;
+      }
+    }
+  }
+  fused3d::cp_async_commit();
+  fused3d::cp_async_wait<0>();
+  __syncthreads();
+  if (mine) {
+    T *c = s + lane;
+    T prev = (T)0;
+    int i = 0;
+#pragma unroll 1
+    for (; i + 8 <= n; i += 8) {
+      T v[8], f[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        v[k] = c[(i + k) * P];
+        f[k] = __ldg(fw + i + k);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        prev = v[k] - prev * f[k];
+        c[(i + k) * P] = prev;
+      }
+    }
+    for (; i < n; i++) {
+      prev = c[i * P] - prev * __ldg(fw + i);
+      c[i * P] = prev;
+    }
+    prev = (T)0;
+    i = n - 1;
+#pragma unroll 1
+    for (; i >= 7; i -= 8) {
+      T v[8], a[8], b[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        v[k] = c[(i - k) * P];
+        a[k] = __ldg(am + i - k + 1);
+        b[k] = __ldg(bm + i - k + 1);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        prev = (v[k] - a[k] * prev) / b[k];
+        c[(i - k) * P] = prev;
+      }
+    }
+    for (; i >= 0; i--) {
+      prev = (c[i * P] - __ldg(am + i + 1) * prev) / __ldg(bm + i + 1);
+      c[i * P] = prev;
+    }
+  }
+  __syncthreads();
+  if (inner == 1) {
+    for (int t = 0; t < nl; t++) {
+      const i64 g0 = gbase + (i64)t * n;
+      const T *sp = s + lane * P + t;
+      for (int i = lane; i < n; i += W) {
+        const T r = *sp;
+        sp += W * P;
+        const i64 g = g0 + i;
+        if (mode == 0)
+          x[g] = r;
+        else
+          acc[g] = mode == 1 ? acc[g] + r : acc[g] - r;
+      }
+    }
+  } else if (mine) {
+    const T *sp = s + lane;
+    i64 g = gbase;
+    if (mode == 0) {
+#pragma unroll 4
+      for (int i = 0; i < n; i++, sp += P, g += inner)
+        x[g] = *sp;
+    } else if (mode == 1) {
+#pragma unroll 4
+      for (int i = 0; i < n; i++, sp += P, g += inner)
+        acc[g] = acc[g] + *sp;
+    } else {
+#pragma unroll 4
+      for (int i = 0; i < n; i++, sp += P, g += inner)
+        acc[g] = acc[g] - *sp;
+    }
+  }
+}
+
 // acc[i] += sign * w[i] on dense arrays (AddND / SubtractND)
 template <typename T>
 __global__ void axpy_kernel(T *__restrict__ acc, const T *__restrict__ w, i64 n, int subtract) {
@@ -554,13 +719,17 @@ void fill_tables(const mgb_plan *p, int l, Geom &g, bool masstrans) {
   }
 }
 
-template <typename T> void thomas_all(mgb_plan *p, int l, T *w, cudaStream_t st);
+template <typename T>
+void thomas_all(mgb_plan *p, int l, T *w, T *acc, int mode, cudaStream_t st);
+template <typename T>
+void axpy(T *acc, const T *w, i64 n, int subtract, cudaStream_t st);
 
 // correction = Thomas_{f,c,r..}( MassTrans_{f,c,r..}( coefficient function ) )
 // (CalcCorrection3D.hpp:30-196), result dense with the coarse shape of level l-1
 // in *result (either d_wA or d_wB).
 template <typename T>
-int correction(mgb_plan *p, int l, const T *coef, T **result, cudaStream_t st) {
+int correction(mgb_plan *p, int l, const T *coef, T **result, T *acc, int mode,
+               cudaStream_t st) {
   const int D = p->D;
   i64 full[5];
   dense_strides(p->shape, D, full);
@@ -605,7 +774,7 @@ int correction(mgb_plan *p, int l, const T *coef, T **result, cudaStream_t st) {
     }
   }
   T *w = (T *)src; // dense, coarse shape
-  thomas_all<T>(p, l, w, st);
+  thomas_all<T>(p, l, w, acc, mode, st);
   *result = w;
   return MGB_SUCCESS;
 }
@@ -669,9 +838,34 @@ int launch_fused3d(mgb_plan *p, int l, const T *in, const i64 *in_strides, T *co
   return MGB_SUCCESS;
 }
 
-// Thomas solves (all dims) in place on the dense coarse-shaped array w
-template <typename T> void thomas_all(mgb_plan *p, int l, T *w, cudaStream_t st) {
+template <typename T, int W>
+bool launch_thomas_smem(T *w, int n, i64 inner, i64 outer, const T *fw, const T *am,
+                        const T *bm, T *acc, int mode, cudaStream_t st) {
+  const size_t smem = (size_t)n * (W + 1) * sizeof(T);
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(thomas_smem_kernel<T, W>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return false;
+    cudaFuncSetAttribute(thomas_smem_kernel<T, W>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  i64 blocks = inner == 1 ? (outer + W - 1) / W : outer * ((inner + W - 1) / W);
+  const i64 lines = outer * inner;
+  MGB_LAUNCH(inner == 1 ? MGB_K_THOMAS_CONTIG : MGB_K_THOMAS_STRIDED, st,
+             (thomas_smem_kernel<T, W><<<(unsigned)blocks, W, smem, st>>>(w, n, inner, lines, fw, am,
+                                                                          bm, acc, mode)));
+  return true;
+}
+
+// Thomas solves (all dims) in place on the dense coarse-shaped array w; the
+// last solve adds (mode 1) / subtracts (mode 2) its result to / from `acc`
+// when acc != nullptr, otherwise w holds the correction afterwards.
+template <typename T>
+void thomas_all(mgb_plan *p, int l, T *w, T *acc, int mode, cudaStream_t st) {
   const int D = p->D;
+  const size_t smem_max = 227 * 1024, smem_sm = 228 * 1024 - 1024;
   for (int a = D - 1; a >= 0; a--) {
     const mgb_dim_tables &m = p->tab[l - 1][a];
     const T *fw = (const T *)p->dtab(m.fw);
@@ -683,17 +877,51 @@ template <typename T> void thomas_all(mgb_plan *p, int l, T *w, cudaStream_t st)
       inner *= (i64)p->lshape[l - 1][d];
     for (int d = 0; d < a; d++)
       outer *= (i64)p->lshape[l - 1][d];
-    if (inner == 1) {
+    const bool lastax = (a == 0);
+    T *accp = (lastax && acc) ? acc : nullptr;
+    const int md = accp ? mode : 0;
+    if (inner > 1) {
+      // strided axis: one thread per line, coalesced across the inner dimension
+      // (all lines resident at once hides more latency than staging here)
+      i64 lines = outer * inner;
+      unsigned blocks = (unsigned)((lines + 127) / 128);
+      MGB_LAUNCH(MGB_K_THOMAS_STRIDED, st,
+                 (thomas_strided_kernel<T><<<blocks, 128, 0, st>>>(w, n, inner, lines, fw, am, bm,
+                                                                  accp, md)));
+      continue;
+    }
+    // contiguous axis: whole lines staged in shared memory when they fit
+    int bestW = 0;
+    i64 best = 0;
+    const int Ws[3] = {32, 16, 8};
+    for (int k = 0; k < 3; k++) {
+      size_t sm = (size_t)n * (Ws[k] + 1) * sizeof(T);
+      if (sm > smem_max)
+        continue;
+      i64 nb = std::min<i64>(32, (i64)(smem_sm / (sm + 1024)));
+      i64 eff = std::min<i64>(Ws[k], outer);
+      if (nb * eff > best) {
+        best = nb * eff;
+        bestW = Ws[k];
+      }
+    }
+    bool done = false;
+    if (bestW == 32)
+      done = launch_thomas_smem<T, 32>(w, n, inner, outer, fw, am, bm, accp, md, st);
+    else if (bestW == 16)
+      done = launch_thomas_smem<T, 16>(w, n, inner, outer, fw, am, bm, accp, md, st);
+    else if (bestW == 8)
+      done = launch_thomas_smem<T, 8>(w, n, inner, outer, fw, am, bm, accp, md, st);
+    if (done)
+      continue;
+    {
       i64 lines = outer;
       unsigned blocks = (unsigned)((lines + 127) / 128);
       MGB_LAUNCH(MGB_K_THOMAS_CONTIG, st,
                  (thomas_contig_kernel<T><<<blocks, 128, 0, st>>>(w, n, lines, fw, am, bm)));
-    } else {
-      i64 lines = outer * inner;
-      unsigned blocks = (unsigned)((lines + 127) / 128);
-      MGB_LAUNCH(MGB_K_THOMAS_STRIDED, st,
-                 (thomas_strided_kernel<T><<<blocks, 128, 0, st>>>(w, n, inner, lines, fw, am, bm)));
     }
+    if (accp)
+      axpy<T>(accp, w, (i64)mgb_level_elems(p, l - 1), mode == 2, st);
   }
 }
 
@@ -728,8 +956,7 @@ int decompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
       rc = launch_fused3d<T, 0>(p, l, cur, g.sa, d_out, coarse, w, st);
       if (rc)
         return rc;
-      thomas_all<T>(p, l, w, st);
-      axpy<T>(coarse, w, (i64)mgb_level_elems(p, l - 1), 0, st);
+      thomas_all<T>(p, l, w, coarse, 1, st);
       cur = coarse;
       continue;
     }
@@ -741,10 +968,9 @@ int decompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
     case 5: launch_coef<T, 4>(g, cur, d_out, coarse, st); break;
     }
     T *w = nullptr;
-    rc = correction<T>(p, l, d_out, &w, st);
+    rc = correction<T>(p, l, d_out, &w, coarse, 1, st);
     if (rc)
       return rc;
-    axpy<T>(coarse, w, (i64)mgb_level_elems(p, l - 1), 0, st);
     cur = coarse;
   }
   // level-0 nodes into the corner of the output
@@ -798,13 +1024,12 @@ int recompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
       w = (T *)p->d_wA;
       rc = launch_fused3d<T, 1>(p, l, d_in, full, nullptr, nullptr, w, st);
       if (!rc)
-        thomas_all<T>(p, l, w, st);
+        thomas_all<T>(p, l, w, coarse, 2, st);
     } else {
-      rc = correction<T>(p, l, d_in, &w, st);
+      rc = correction<T>(p, l, d_in, &w, coarse, 2, st);
     }
     if (rc)
       return rc;
-    axpy<T>(coarse, w, (i64)mgb_level_elems(p, l - 1), 1, st);
     Geom g = {};
     g.D = D;
     unsigned rows = 1;

@@ -14,6 +14,7 @@
 // (no fixed-length intermediate, no separate condense pass).
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "plan.h"
@@ -372,21 +373,38 @@ chunk_bits_kernel(const uint16_t *__restrict__ sym, u64 n, int chunk,
                   const u64 *__restrict__ codebook, int dict,
                   u64 *__restrict__ bits) {
   extern __shared__ unsigned char s_len[];
+  __shared__ u64 s_part[8];
   for (int i = threadIdx.x; i < dict; i += blockDim.x)
     s_len[i] = (unsigned char)(codebook[i] >> 56);
   __syncthreads();
   const u64 nchunk = (n - 1) / chunk + 1;
   for (u64 c = blockIdx.x; c < nchunk; c += gridDim.x) {
-    u64 lo = c * (u64)chunk;
-    u64 hi = min(n, lo + (u64)chunk);
-    unsigned total = 0; // <= 65536 * 56 fits; chunk may be larger: use u64 below
+    const u64 lo = c * (u64)chunk;
+    const u64 hi = min(n, lo + (u64)chunk);
+    unsigned total = 0; // one thread sees at most chunk / 256 * 56 bits... kept in 64 bits below
     u64 tot64 = 0;
-    for (u64 i = lo + threadIdx.x; i < hi; i += blockDim.x)
-      total += s_len[sym[i]];
-    tot64 = total;
+    const uint16_t *base = sym + lo;
+    const u64 cnt = hi - lo;
+    u64 done = 0;
+    if ((((uintptr_t)base) & 15) == 0) {
+      const u64 nv = cnt / 8;
+      const uint4 *b4 = reinterpret_cast<const uint4 *>(base);
+      for (u64 i = threadIdx.x; i < nv; i += blockDim.x) {
+        const uint4 v = __ldg(b4 + i);
+        total += s_len[v.x & 0xffffu] + s_len[v.x >> 16] + s_len[v.y & 0xffffu] + s_len[v.y >> 16] +
+                 s_len[v.z & 0xffffu] + s_len[v.z >> 16] + s_len[v.w & 0xffffu] + s_len[v.w >> 16];
+        if (total > 0x7fff0000u) {
+          tot64 += total;
+          total = 0;
+        }
+      }
+      done = nv * 8;
+    }
+    for (u64 i = done + threadIdx.x; i < cnt; i += blockDim.x)
+      total += s_len[base[i]];
+    tot64 += total;
     for (int o = 16; o > 0; o >>= 1)
       tot64 += __shfl_xor_sync(0xffffffffu, tot64, o);
-    __shared__ u64 s_part[8];
     if ((threadIdx.x & 31) == 0)
       s_part[threadIdx.x >> 5] = tot64;
     __syncthreads();
@@ -459,6 +477,12 @@ chunk_scan_kernel(const u64 *__restrict__ bits, u64 nchunk, u64 *__restrict__ wo
   }
 }
 
+// Block per chunk, tiles of 2048 symbols.  A thread takes 8 consecutive
+// symbols (one 128-bit load), concatenates their codewords in a register and
+// places them at its bit offset (block scan of the code lengths) in the tile's
+// shared-memory image: words it fills completely are stored, the (at most two)
+// words it shares with its neighbours are OR-ed in atomically.  Full words of
+// the tile are then flushed, coalesced, to their FINAL place in the stream.
 template <bool CB_SHARED>
 __global__ void __launch_bounds__(256)
 encode_kernel(const uint16_t *__restrict__ sym, u64 n, int chunk,
@@ -471,16 +495,15 @@ encode_kernel(const uint16_t *__restrict__ sym, u64 n, int chunk,
   u64 *s_cb = smem;                         // dict (if CB_SHARED)
   u64 *s_out = smem + (CB_SHARED ? dict : 0); // TILE_WORDS
   __shared__ unsigned s_scan[8];
-  __shared__ unsigned s_tilebits;
   if (scal[2])
     return; // output too small: nothing is written
   if (CB_SHARED) {
     for (int i = threadIdx.x; i < dict; i += NT)
       s_cb[i] = codebook[i];
   }
-  const u64 *cb = CB_SHARED ? s_cb : codebook;
   const u64 nchunk = (n - 1) / chunk + 1;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  auto cbv = [&](unsigned sy) -> u64 { return CB_SHARED ? s_cb[sy] : __ldg(codebook + sy); };
   for (u64 c = blockIdx.x; c < nchunk; c += gridDim.x) {
     const u64 lo = c * (u64)chunk;
     const u64 hi = min(n, lo + (u64)chunk);
@@ -491,16 +514,23 @@ encode_kernel(const uint16_t *__restrict__ sym, u64 n, int chunk,
     unsigned carry_bits = 0; // bits already in s_out[0]
     u64 wdone = 0;
     for (u64 t0 = lo; t0 < hi; t0 += TILE) {
-      // load up to PER symbols
-      u64 s0 = t0 + (u64)tid * PER;
+      const u64 s0 = t0 + (u64)tid * PER;
       u64 cw[PER];
       unsigned mybits = 0;
+      if (s0 + PER <= hi && ((((uintptr_t)(sym + s0)) & 15) == 0)) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(sym + s0));
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int k = 0; k < PER; k++) {
-        u64 idx = s0 + k;
-        cw[k] = idx < hi ? cb[sym[idx]] : 0ull;
-        mybits += (unsigned)(cw[k] >> 56);
+        for (int k = 0; k < PER; k++)
+          cw[k] = cbv((w[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+      } else {
+#pragma unroll
+        for (int k = 0; k < PER; k++)
+          cw[k] = s0 + k < hi ? cbv(sym[s0 + k]) : 0ull;
       }
+#pragma unroll
+      for (int k = 0; k < PER; k++)
+        mybits += (unsigned)(cw[k] >> 56);
       // block exclusive scan of mybits
       unsigned x = mybits;
       for (int o = 1; o < 32; o <<= 1) {
@@ -519,30 +549,44 @@ encode_kernel(const uint16_t *__restrict__ sym, u64 n, int chunk,
           wpre += v;
         tot += v;
       }
-      unsigned pos = carry_bits + wpre + x - mybits;
-      // pack
+      const unsigned pos = carry_bits + wpre + x - mybits;
+      // concatenate in a register, emit word by word
+      if (mybits) {
+        unsigned wi = pos >> 6, fill = pos & 63;
+        bool whole = fill == 0; // the current word started with this thread
+        u64 acc = 0;
 #pragma unroll
-      for (int k = 0; k < PER; k++) {
-        unsigned len = (unsigned)(cw[k] >> 56);
-        if (len) {
-          u64 code = cw[k] & 0x00ffffffffffffffull;
-          unsigned wi = pos >> 6, off = pos & 63;
-          unsigned room = 64 - off;
-          if (len <= room) {
-            atomicOr(&s_out[wi], code << (room - len));
-          } else {
-            atomicOr(&s_out[wi], code >> (len - room));
-            atomicOr(&s_out[wi + 1], code << (64 - (len - room)));
+        for (int k = 0; k < PER; k++) {
+          const unsigned len = (unsigned)(cw[k] >> 56);
+          if (len) {
+            const u64 code = cw[k] & 0x00ffffffffffffffull;
+            const unsigned room = 64 - fill;
+            if (len < room) {
+              acc |= code << (room - len);
+              fill += len;
+            } else {
+              acc |= code >> (len - room);
+              if (whole)
+                s_out[wi] = acc;
+              else
+                atomicOr(&s_out[wi], acc);
+              wi++;
+              whole = true;
+              const unsigned rem = len - room;
+              acc = rem ? code << (64 - rem) : 0ull;
+              fill = rem;
+            }
           }
-          pos += len;
         }
+        if (fill)
+          atomicOr(&s_out[wi], acc);
       }
       __syncthreads();
-      unsigned tile_bits = carry_bits + tot;
-      unsigned nfull = tile_bits >> 6;
+      const unsigned tile_bits = carry_bits + tot;
+      const unsigned nfull = tile_bits >> 6;
       for (unsigned i = tid; i < nfull; i += NT)
-        dst[wdone + i] = s_out[i];
-      u64 partial = s_out[nfull];
+        __stcs(dst + wdone + i, s_out[i]);
+      const u64 partial = s_out[nfull];
       __syncthreads();
       for (unsigned i = tid; i <= nfull + 1 && i < (unsigned)TILE_WORDS; i += NT)
         s_out[i] = 0;
@@ -701,10 +745,11 @@ decode_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__restr
               const u64 *__restrict__ decodebook, int dict, unsigned *__restrict__ sub_start,
               unsigned *__restrict__ sub_end, unsigned *__restrict__ sub_cnt,
               uint16_t *__restrict__ out, const unsigned *__restrict__ n_skipped,
-              unsigned fast_bufw) {
-  // fast_bufw != 0: decode_fast_kernel ran first; only the chunks it skipped
-  // (more than fast_bufw words) are left, and usually there are none
-  if (fast_bufw && *n_skipped == 0)
+              const unsigned *__restrict__ skipped, unsigned fast_bufw) {
+  // fast_bufw != 0: decode_fast_kernel ran first and listed the chunks it left
+  // (more than fast_bufw words); usually there are few or none
+  const u64 nwork = fast_bufw ? (u64)*n_skipped : nchunk;
+  if (blockIdx.x >= nwork)
     return;
   extern __shared__ u64 s_db[]; // first[64] entry[64] | lut | keys16 | outbuf
   u64 *s_first = s_db, *s_entry = s_db + 64;
@@ -743,12 +788,11 @@ decode_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__restr
   t.dict = dict;
   t.lslow = max(lmin, DEC_K + 1);
 
-  for (u64 c = blockIdx.x; c < nchunk; c += gridDim.x) {
+  for (u64 wk = blockIdx.x; wk < nwork; wk += gridDim.x) {
+    const u64 c = fast_bufw ? (u64)skipped[wk] : wk;
     const u64 B64 = bits[c];
     const u64 w0 = woff[c];
     const u64 nw = (B64 - 1) / 64 + 1;
-    if (fast_bufw && nw <= fast_bufw && B64 != 0)
-      continue;
     const u64 *src = ddata + w0;
     const unsigned B = (unsigned)B64;
     const unsigned NS = (B + DEC_SB - 1) / DEC_SB;
@@ -858,63 +902,53 @@ decode_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__restr
 // Chunks that do not fit the shared buffers are counted in *n_skipped and left
 // to decode_kernel.
 constexpr int DF_T = 512; // threads per block
+// sub-sequence length of the fast decoder: 5 words, and every thread owns an ODD
+// number of them, so the threads of a warp read the bit stream at an odd word
+// stride (no shared-memory bank conflicts)
+constexpr int DF_SB = 160;
 
-struct FastReader {
-  const unsigned *w32; // chunk words as 32-bit halves (shared memory, little-endian u64 words)
-  unsigned n32;
-  u64 buf;
-  int have;
-  unsigned h; // next half (stream order)
-  __device__ __forceinline__ unsigned half(unsigned k) const {
-    return k < n32 ? w32[k ^ 1u] : 0u;
-  }
-  __device__ __forceinline__ void init(unsigned bitpos) {
-    h = bitpos >> 5;
-    const unsigned off = bitpos & 31u;
-    buf = (((u64)half(h) << 32) | half(h + 1)) << off;
-    have = 64 - (int)off;
-    h += 2;
-  }
-  __device__ __forceinline__ void consume(unsigned len) {
-    buf <<= len;
-    have -= (int)len;
-    if (have <= 32) {
-      buf |= (u64)half(h) << (32 - have);
-      have += 32;
-      h++;
-    }
-  }
-  __device__ __forceinline__ u64 full_window(unsigned bitpos) const {
-    const unsigned k = bitpos >> 5, off = bitpos & 31u;
-    u64 w = ((u64)half(k) << 32) | half(k + 1);
-    if (off)
-      w = (w << off) | ((u64)half(k + 2) >> (32 - off));
-    return w;
-  }
-};
+__device__ __forceinline__ unsigned lds32(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ unsigned lds32_4(unsigned addr) { // word at addr + 4
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ unsigned lds8(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 
+// Shared-memory tables of the fast decoder, addressed with 32-bit shared
+// addresses (no generic-pointer arithmetic in the decode loop).
 struct FastTables {
-  const u64 *first, *entry; // shared
-  const unsigned *lut;      // shared: bit31 clear: symbol | len << 16; set: walk start << 16
+  unsigned words; // chunk bit stream as 32-bit halves in STREAM order, zero padded
+  unsigned lut;   // 2^DEC_K x u32: bit31 clear: symbol | len << 16; set: walk start << 16
+  unsigned t32;   // [34] first[l] left aligned in 32 bits (0xffffffff: no code of length l)
+  unsigned b32;   // [34] entry[l] - first[l] (mod 2^32): key index = b32[l] + code
+  const u64 *first, *entry; // generic pointers to the 64-entry tables (codes > 32 bits)
   const u64 *keys;          // global (decodebook + 128)
   int dict;
 };
 
+// 32 stream bits starting at bit position p
+__device__ __forceinline__ unsigned fast_window(const FastTables &t, unsigned p) {
+  const unsigned a = t.words + ((p >> 3) & ~3u);
+  return __funnelshift_l(lds32_4(a), lds32(a), p); // shift = p & 31
+}
+
+// codes longer than 32 bits (or a walk of more than two steps): canonical walk
 template <bool WANT_SYM>
-__device__ __forceinline__ unsigned fast_decode_one(const FastTables &t, const FastReader &r,
-                                                    unsigned p, unsigned &sym) {
-  const unsigned e = t.lut[(unsigned)(r.buf >> (64 - DEC_K))];
-  if (!(e & 0x80000000u)) {
-    sym = e & 0xffffu;
-    return e >> 16;
-  }
-  int l = (int)((e >> 16) & 0xffu);
-  u64 win = l > 32 ? r.full_window(p) : r.buf;
+__device__ __noinline__ unsigned fast_decode_slow(const FastTables &t, unsigned p, int l,
+                                                  unsigned &sym) {
+  const u64 win = ((u64)fast_window(t, p) << 32) | fast_window(t, p + 32);
   u64 v = win >> (64 - l);
   while (v < t.first[l] && l < 63) {
     l++;
-    if (l == 33)
-      win = r.full_window(p);
     v = win >> (64 - l);
   }
   if (WANT_SYM) {
@@ -924,26 +958,64 @@ __device__ __forceinline__ unsigned fast_decode_one(const FastTables &t, const F
   return (unsigned)l;
 }
 
+// length of the codeword whose first 32 bits are `hi` (and its symbol)
+template <bool WANT_SYM>
+__device__ __forceinline__ unsigned fast_decode_one(const FastTables &t, unsigned hi, unsigned p,
+                                                    unsigned &sym) {
+  const unsigned e = lds32(t.lut + ((hi >> (32 - DEC_K)) << 2));
+  unsigned l = (e >> 16) & 0xffu;
+  if (e & 0x80000000u) {
+    // longer than DEC_K bits: l is the shortest length this prefix allows; two
+    // predicated steps of the canonical walk cover nearly every code
+    const unsigned ta = t.t32 + (l << 2);
+    const unsigned t0 = lds32(ta), t1 = lds32_4(ta);
+    const bool ok0 = hi >= t0, ok1 = hi >= t1;
+    if (l >= 31 || !(ok0 || ok1))
+      return fast_decode_slow<WANT_SYM>(t, p, (int)l, sym);
+    l += ok0 ? 0u : 1u;
+    if (WANT_SYM) {
+      const unsigned ki = lds32(t.b32 + (l << 2)) + (hi >> (32 - l));
+      sym = ki < (unsigned)t.dict ? (unsigned)__ldg(reinterpret_cast<const unsigned short *>(t.keys + ki)) : 0u;
+    }
+    return l;
+  }
+  sym = e & 0xffffu;
+  return l;
+}
+
 __global__ void __launch_bounds__(DF_T, 2)
 decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
                    const u64 *__restrict__ woff, u64 nchunk, int chunk, u64 n,
                    const u64 *__restrict__ decodebook, int dict, unsigned bufw,
-                   unsigned *__restrict__ n_skipped, uint16_t *__restrict__ out) {
+                   const unsigned *__restrict__ n_work, const unsigned *__restrict__ work,
+                   unsigned *__restrict__ n_skipped, unsigned *__restrict__ skipped,
+                   uint16_t *__restrict__ out) {
+  // work == nullptr: every chunk; otherwise the *n_work chunks listed in work[]
+  // (those an earlier launch with a smaller buffer left over)
+  const u64 nwork = work ? (u64)*n_work : nchunk;
+  if (blockIdx.x >= nwork)
+    return;
   extern __shared__ __align__(16) unsigned char df_smem[];
   u64 *s_first = reinterpret_cast<u64 *>(df_smem), *s_entry = s_first + 64;
   unsigned *s_lut = reinterpret_cast<unsigned *>(s_first + 128);
-  u64 *s_words = reinterpret_cast<u64 *>(s_lut + (1 << DEC_K));
-  const unsigned nslot = bufw / 2 + DF_T; // sub-sequence slots
-  unsigned *s_en = reinterpret_cast<unsigned *>(s_words + bufw);
+  u64 *s_words = reinterpret_cast<u64 *>(s_lut + (1 << DEC_K)); // bufw + 2 (zero padding)
+  const unsigned nslot = (bufw * 64 / DF_SB + 2 * DF_T + 3) & ~3u; // sub-sequence slots (keeps s_out 16-byte aligned)
+  unsigned *s_en = reinterpret_cast<unsigned *>(s_words + bufw + 2);
   unsigned *s_st = s_en + nslot;
   unsigned char *s_cn = reinterpret_cast<unsigned char *>(s_st + DF_T);
   uint16_t *s_out = reinterpret_cast<uint16_t *>(s_cn + ((nslot + 15) & ~15u));
   __shared__ unsigned s_scan[DF_T / 32];
+  __shared__ unsigned s_t32[36], s_b32[36];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
   for (int i = tid; i < 128; i += DF_T)
     s_first[i] = decodebook[i];
   __syncthreads();
+  if (tid < 36) {
+    const bool valid = tid >= 1 && tid <= 32 && s_first[tid] != ~0ull && (s_first[tid] >> tid) == 0;
+    s_t32[tid] = valid ? (unsigned)(s_first[tid] << (32 - tid)) : 0xffffffffu;
+    s_b32[tid] = valid ? (unsigned)(s_entry[tid] - s_first[tid]) : 0u;
+  }
   int lmin = 1;
   while (lmin < 63 && s_first[lmin] == ~0ull)
     lmin++;
@@ -972,53 +1044,60 @@ decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
   }
   __syncthreads();
   FastTables t;
+  t.words = (unsigned)__cvta_generic_to_shared(s_words);
+  t.lut = (unsigned)__cvta_generic_to_shared(s_lut);
+  t.t32 = (unsigned)__cvta_generic_to_shared(s_t32);
+  t.b32 = (unsigned)__cvta_generic_to_shared(s_b32);
   t.first = s_first;
   t.entry = s_entry;
-  t.lut = s_lut;
   t.keys = decodebook + 128;
   t.dict = dict;
+  const unsigned a_en = (unsigned)__cvta_generic_to_shared(s_en);
+  const unsigned a_cn = (unsigned)__cvta_generic_to_shared(s_cn);
 
-  for (u64 c = blockIdx.x; c < nchunk; c += gridDim.x) {
+  for (u64 wk = blockIdx.x; wk < nwork; wk += gridDim.x) {
+    const u64 c = work ? (u64)work[wk] : wk;
     const u64 B64 = bits[c];
     const u64 nw64 = (B64 - 1) / 64 + 1;
     if (nw64 > bufw || B64 == 0) {
       if (tid == 0)
-        atomicAdd(n_skipped, 1u);
+        skipped[atomicAdd(n_skipped, 1u)] = (unsigned)c;
       continue;
     }
     const unsigned B = (unsigned)B64, nw = (unsigned)nw64;
     const u64 *src = ddata + woff[c];
     const unsigned nsym = (unsigned)min((u64)chunk, n - c * (u64)chunk);
-    // 0. chunk words -> shared memory
+    // 0. chunk words -> shared memory (all copies in flight), then every thread
+    //    swaps the halves of its own words into stream order
     for (unsigned i = tid; i < nw; i += DF_T) {
       const unsigned d = (unsigned)__cvta_generic_to_shared(s_words + i);
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src + i));
     }
     asm volatile("cp.async.commit_group;\n" ::);
-    // run geometry: K sub-sequences of DEC_SB bits per thread
-    const unsigned NS = (B + DEC_SB - 1) / DEC_SB;
-    const unsigned K = (NS + DF_T - 1) / DF_T;
-    const unsigned run0 = tid * K * DEC_SB; // first bit of this thread's run
+    if (tid < 2)
+      s_words[nw + tid] = 0; // the reader may look up to two words past the end
+    // run geometry: K (odd) sub-sequences of DF_SB bits per thread
+    const unsigned NS = (B + DF_SB - 1) / DF_SB;
+    const unsigned K = ((NS + DF_T - 1) / DF_T) | 1u;
+    const unsigned run0 = tid * K * DF_SB; // first bit of this thread's run
     const bool active = run0 < B;
     asm volatile("cp.async.wait_group 0;\n" ::);
+    for (unsigned i = tid; i < nw; i += DF_T) {
+      const uint2 w = reinterpret_cast<uint2 *>(s_words)[i];
+      reinterpret_cast<uint2 *>(s_words)[i] = make_uint2(w.y, w.x);
+    }
     __syncthreads();
-    FastReader r;
-    r.w32 = reinterpret_cast<const unsigned *>(s_words);
-    r.n32 = 2 * nw;
     // 1. speculative pass over the run
     if (active) {
       unsigned p = run0;
-      r.init(p);
       for (unsigned j = 0; j < K; j++) {
         const unsigned i = tid * K + j;
-        const unsigned lim = min(B, (i + 1) * DEC_SB);
+        const unsigned lim = min(B, (i + 1) * DF_SB);
         unsigned cnt = 0;
         while (p < lim) {
           unsigned sym;
-          const unsigned l = fast_decode_one<false>(t, r, p, sym);
-          p += l;
+          p += fast_decode_one<false>(t, fast_window(t, p), p, sym);
           cnt++;
-          r.consume(l);
         }
         s_en[i] = p;
         s_cn[i] = (unsigned char)cnt;
@@ -1036,17 +1115,14 @@ decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
           changed = 1;
           s_st[tid] = s0;
           unsigned p = s0;
-          r.init(p);
           for (unsigned j = 0; j < K; j++) {
             const unsigned i = tid * K + j;
-            const unsigned lim = min(B, (i + 1) * DEC_SB);
+            const unsigned lim = min(B, (i + 1) * DF_SB);
             unsigned cnt = 0;
             while (p < lim) {
               unsigned sym;
-              const unsigned l = fast_decode_one<false>(t, r, p, sym);
-              p += l;
+              p += fast_decode_one<false>(t, fast_window(t, p), p, sym);
               cnt++;
-              r.consume(l);
             }
             const bool met = (p == s_en[i]);
             s_en[i] = p;
@@ -1063,7 +1139,7 @@ decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
     unsigned cnt = 0;
     if (active)
       for (unsigned j = 0; j < K; j++)
-        cnt += s_cn[tid * K + j];
+        cnt += lds8(a_cn + tid * K + j);
     unsigned x = cnt;
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
@@ -1080,17 +1156,15 @@ decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
         wpre += s_scan[k];
     unsigned off = wpre + x - cnt;
     if (active && cnt) {
-      unsigned p = tid ? s_en[tid * K - 1] : 0u;
-      const unsigned lim = min(B, (tid + 1) * K * DEC_SB);
-      r.init(p);
+      unsigned p = tid ? lds32(a_en + ((tid * K - 1) << 2)) : 0u;
+      const unsigned lim = min(B, (tid + 1) * K * DF_SB);
+      const unsigned a_out = (unsigned)__cvta_generic_to_shared(s_out);
       while (p < lim) {
         unsigned sym;
-        const unsigned l = fast_decode_one<true>(t, r, p, sym);
+        p += fast_decode_one<true>(t, fast_window(t, p), p, sym);
         if (off < nsym)
-          s_out[off] = (uint16_t)sym;
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(a_out + (off << 1)), "h"((unsigned short)sym));
         off++;
-        p += l;
-        r.consume(l);
       }
     }
     __syncthreads();
@@ -1226,7 +1300,8 @@ int mgb_huffman_compress_async(mgb_plan *p, const uint16_t *d_sym, uint64_t n,
                                                    d_ocount_ptr ? p->outlier_cap : ~0ull)));
   u64 *ddata = (u64 *)(d_out + fixed);
   constexpr int TILE_WORDS = 8 * 256 * 56 / 64 + 4;
-  if (dict <= 16384) {
+  static const bool enc_shared = getenv("MGB_ENC_GLOBAL_CB") == nullptr;
+  if (dict <= 16384 && enc_shared) {
     size_t smem = ((size_t)dict + TILE_WORDS) * 8;
     cudaFuncSetAttribute(encode_kernel<true>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1340,51 +1415,75 @@ extern "C" int mgb_huffman_decompress(mgb_plan *p, const uint8_t *d_in, uint64_t
       cudaFree(p->d_dec_sub);
       p->d_dec_sub = nullptr;
       p->dec_sub_cap = 0;
-      MGB_CUDA_CHECK(cudaMalloc(&p->d_dec_sub, need * 3 * sizeof(unsigned)));
+      MGB_CUDA_CHECK(cudaMalloc(&p->d_dec_sub, (need * 3 + 2 * nchunk) * sizeof(unsigned)));
       p->dec_sub_cap = need;
     }
   }
   unsigned *sub = p->d_dec_sub;
   const u64 subn = p->dec_sub_cap;
-  // fast path: chunks staged in shared memory (2 blocks of 512 threads per SM).
-  // The word buffer is sized from the average chunk (+25 %, at least 2 KB more).
-  unsigned fast_bufw = 0;
-  unsigned *n_skipped = (unsigned *)((u64 *)p->d_scalars + 15);
+  // fast path: chunks staged in shared memory.  First launch: 2 blocks of 512
+  // threads per SM, word buffer sized from the average chunk (+25 %); second
+  // launch (1 block per SM, the largest buffer that fits) for the chunks the
+  // first one left; whatever still does not fit goes to decode_kernel.
+  unsigned fast_bufw = 0, big_bufw = 0;
+  unsigned *cnt1 = (unsigned *)((u64 *)p->d_scalars + 15), *cnt2 = cnt1 + 1;
+  unsigned *list1 = sub + 3 * subn, *list2 = list1 + nchunk;
+  const size_t fixed = 128 * 8 + (size_t)(1 << DEC_K) * 4 + (size_t)DF_T * 4 +
+                       (((size_t)chunk * 2 + 15) & ~(size_t)15) + 64;
+  auto fast_smem = [&](unsigned bw) {
+    const unsigned nslot = (bw * 64 / DF_SB + 2 * DF_T + 3) & ~3u;
+    return 128 * 8 + (size_t)(1 << DEC_K) * 4 + ((size_t)bw + 2) * 8 + (size_t)nslot * 4 +
+           (size_t)DF_T * 4 + ((nslot + 15) & ~15u) + (((size_t)chunk * 2 + 15) & ~(size_t)15);
+  };
   {
-    const size_t budget = 113 * 1024 - 512;
-    const size_t fixed = 128 * 8 + (size_t)(1 << DEC_K) * 4 + (size_t)DF_T * 4 +
-                         (((size_t)chunk * 2 + 15) & ~(size_t)15) + 64;
+    const size_t budget = 113 * 1024 - 512, budget_big = 200 * 1024;
     u64 avg = total_words / nchunk + 1;
     u64 want = avg + avg / 4 + 256;
     if (fixed < budget) {
-      // per word: 8 B data + 2 B end slot + 0.5 B count
-      size_t maxw = (budget - fixed - (size_t)DF_T * 5) * 2 / 21;
+      // per word: 8 B data + 64/DF_SB x (4 B end slot + 1 B count)
+      size_t maxw = (budget - fixed - (size_t)DF_T * 10 - 128) / 10;
       if (want > maxw && avg + avg / 16 + 32 <= maxw)
         want = maxw;
       if (want <= maxw)
         fast_bufw = (unsigned)(want & ~(u64)1);
     }
+    if (fixed + 16384 < budget_big) {
+      size_t maxw = (budget_big - fixed - (size_t)DF_T * 10 - 128) / 10;
+      big_bufw = (unsigned)(std::min<u64>(maxw, (u64)chunk * 56 / 64 + 2) & ~(u64)1);
+      if (big_bufw <= fast_bufw)
+        big_bufw = 0;
+    }
   }
-  if (fast_bufw) {
-    const unsigned nslot = fast_bufw / 2 + DF_T;
-    const size_t smem = 128 * 8 + (size_t)(1 << DEC_K) * 4 + (size_t)fast_bufw * 8 +
-                        (size_t)nslot * 4 + (size_t)DF_T * 4 + ((nslot + 15) & ~15u) +
-                        (((size_t)chunk * 2 + 15) & ~(size_t)15);
+  if (fast_bufw || big_bufw) {
     static bool configured = false;
     if (!configured) {
       MGB_CUDA_CHECK(cudaFuncSetAttribute(decode_fast_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
       cudaFuncSetAttribute(decode_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                            cudaSharedmemCarveoutMaxShared);
       configured = true;
     }
-    MGB_CUDA_CHECK(cudaMemsetAsync(n_skipped, 0, sizeof(unsigned), st));
+    MGB_CUDA_CHECK(cudaMemsetAsync(cnt1, 0, 2 * sizeof(unsigned), st));
+  }
+  if (fast_bufw) {
     unsigned fblocks = (unsigned)std::min<u64>(nchunk, 148 * 2);
     MGB_LAUNCH(MGB_K_DECODE, st,
-               (decode_fast_kernel<<<fblocks, DF_T, smem, st>>>(ddata, bits, woff, nchunk, chunk, n,
-                                                               decodebook, dict, fast_bufw,
-                                                               n_skipped, d_sym)));
+               (decode_fast_kernel<<<fblocks, DF_T, fast_smem(fast_bufw), st>>>(
+                   ddata, bits, woff, nchunk, chunk, n, decodebook, dict, fast_bufw, nullptr, nullptr,
+                   cnt1, list1, d_sym)));
   }
+  if (big_bufw) {
+    unsigned fblocks = (unsigned)std::min<u64>(nchunk, 148);
+    MGB_LAUNCH(MGB_K_DECODE, st,
+               (decode_fast_kernel<<<fblocks, DF_T, fast_smem(big_bufw), st>>>(
+                   ddata, bits, woff, nchunk, chunk, n, decodebook, dict, big_bufw,
+                   fast_bufw ? cnt1 : nullptr, fast_bufw ? list1 : nullptr, cnt2, list2, d_sym)));
+  }
+  // what decode_kernel has to look at: the second list, else the first
+  unsigned *n_skipped = big_bufw ? cnt2 : cnt1;
+  unsigned *skip_list = big_bufw ? list2 : list1;
+  if (big_bufw)
+    fast_bufw = big_bufw;
   size_t smem_tab = 128 * 8 + (size_t)(1 << DEC_K) * 4 + (size_t)((dict + 7) & ~7) * 2;
   size_t smem_out = (size_t)chunk * 2 + 16;
   unsigned blocks = (unsigned)std::min<u64>(nchunk, 148 * 8);
@@ -1395,14 +1494,14 @@ extern "C" int mgb_huffman_decompress(mgb_plan *p, const uint8_t *d_in, uint64_t
     MGB_LAUNCH(MGB_K_DECODE, st,
                (decode_kernel<true><<<blocks, DEC_T, smem, st>>>(
                    ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict, sub,
-                   sub + subn, sub + 2 * subn, d_sym, n_skipped, fast_bufw)));
+                   sub + subn, sub + 2 * subn, d_sym, n_skipped, skip_list, fast_bufw)));
   } else {
     cudaFuncSetAttribute(decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem_tab);
     MGB_LAUNCH(MGB_K_DECODE, st,
                (decode_kernel<false><<<blocks, DEC_T, smem_tab, st>>>(
                    ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict, sub,
-                   sub + subn, sub + 2 * subn, d_sym, n_skipped, fast_bufw)));
+                   sub + subn, sub + 2 * subn, d_sym, n_skipped, skip_list, fast_bufw)));
   }
   MGB_CUDA_CHECK(cudaGetLastError());
   return MGB_SUCCESS;

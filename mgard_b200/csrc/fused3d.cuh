@@ -38,6 +38,7 @@ constexpr int CA = TC + 2, CB = TF + 2; // 2x2 cells per plane
 constexpr int NCELL = (CA * CB + NT - 1) / NT;
 constexpr int LROWS = (PC + NT / 32 - 1) / (NT / 32); // rows per thread in row sweeps
 constexpr int LCOLS = (PF + 31) / 32;
+constexpr int NLOAD = (PC * PF + NT - 1) / NT; // load slots per thread and plane
 
 template <typename T> struct Params {
   int n[3], nc[3];   // fine / coarse level shape (r, c, f)
@@ -130,26 +131,27 @@ level_kernel(const Params<T> P, const T *__restrict__ in, T *__restrict__ coef_o
   const int jstart = 2 * rk0 - 2;
 
   // ---- per-thread constants (hoisted out of the plane loop) ---------------
-  // (1) plane loads: rows ty + 8q, columns tx + 32p; offset = rowoff + coloff
-  int rowoff[LROWS], coloff[LCOLS];
-  unsigned podd_bits = 0; // MODE 1: bit q: row odd, bit 8+p: column odd
+  // (1) plane loads: element e = tid + NT * q of the PC x PF tile (row-major), so
+  // every slot is used and a warp reads runs of consecutive addresses.
+  // ld_off[q]: offset from the plane's base (-1: hole / outside -> zero fill);
+  // MODE 1: ld_even bit q set <=> row and column are both even (the all-coarse
+  // block counts as zero on even planes).
+  int ld_off[NLOAD];
+  unsigned ld_even = 0;
 #pragma unroll
-  for (int q = 0; q < LROWS; q++) {
-    const int lc = ty + q * (NT / 32);
-    const int jc = jc0 + lc;
-    const int scx = lc < PC ? src_index(jc, ncn, npc) : -1;
-    rowoff[q] = scx < 0 ? -1 : (int)((MODE == 0 ? scx : oct_pos(jc, cc)) * P.sin[1]);
-    if (jc & 1)
-      podd_bits |= 1u << q;
-  }
-#pragma unroll
-  for (int pcol = 0; pcol < LCOLS; pcol++) {
-    const int lf = tx + 32 * pcol;
-    const int jf = jf0 + lf;
-    const int sf = lf < PF ? src_index(jf, nf, npf) : -1;
-    coloff[pcol] = sf < 0 ? -1 : (int)((MODE == 0 ? sf : oct_pos(jf, ff)) * P.sin[2]);
-    if (jf & 1)
-      podd_bits |= 1u << (8 + pcol);
+  for (int q = 0; q < NLOAD; q++) {
+    const int e = tid + q * NT;
+    ld_off[q] = -1;
+    if (e < PC * PF) {
+      const int lc = e / PF, lf = e - lc * PF;
+      const int jc = jc0 + lc, jf = jf0 + lf;
+      const int scx = src_index(jc, ncn, npc), sf = src_index(jf, nf, npf);
+      if (scx >= 0 && sf >= 0)
+        ld_off[q] = (int)((MODE == 0 ? scx : oct_pos(jc, cc)) * P.sin[1] +
+                          (MODE == 0 ? sf : oct_pos(jf, ff)) * P.sin[2]);
+      if (!(jc & 1) && !(jf & 1))
+        ld_even |= 1u << q;
+    }
   }
   // (2) 2x2 cells (MODE 0)
   int cell_s[NCELL];       // smem index of the cell's (even c, even f) node; -1: none
@@ -215,27 +217,27 @@ level_kernel(const Params<T> P, const T *__restrict__ in, T *__restrict__ coef_o
 
   // ---- helpers -------------------------------------------------------------
   auto slot = [&](int j) -> T * { return s_raw + ((j - jstart) % NSLOT) * (PC * PF); };
+  const unsigned s_raw_addr = (unsigned)__cvta_generic_to_shared(s_raw);
   // asynchronous copy of nodal plane j (MODE 0) / coefficient plane j (MODE 1)
   auto issue_plane = [&](int j) {
-    T *buf = slot(j);
+    const unsigned buf = s_raw_addr + (unsigned)(((j - jstart) % NSLOT) * (PC * PF) * (int)sizeof(T));
     const int sr = src_index(j, nr, npr);
     const T *base = in + (i64)(sr >= 0 ? (MODE == 0 ? sr : oct_pos(j, rr)) : 0) * P.sin[0];
-    const bool rodd = j & 1;
+    const bool plane_ok = sr >= 0;
+    const bool reven = !(j & 1);
 #pragma unroll
-    for (int q = 0; q < LROWS; q++) {
-      const int lc = ty + q * (NT / 32);
-      if (lc < PC) {
-#pragma unroll
-        for (int pcol = 0; pcol < LCOLS; pcol++) {
-          const int lf = tx + 32 * pcol;
-          if (lf < PF) {
-            bool valid = sr >= 0 && rowoff[q] >= 0 && coloff[pcol] >= 0;
-            if (MODE == 1) // the all-coarse block counts as zero
-              valid = valid && (rodd || (podd_bits & ((1u << q) | (1u << (8 + pcol)))));
-            cp_async(buf + lc * PF + lf, valid ? base + rowoff[q] + coloff[pcol] : in,
-                     (int)sizeof(T), valid);
-          }
-        }
+    for (int q = 0; q < NLOAD; q++) {
+      if (tid + q * NT < PC * PF) {
+        bool valid = plane_ok && ld_off[q] >= 0;
+        if (MODE == 1) // the all-coarse block counts as zero
+          valid = valid && !(reven && (ld_even & (1u << q)));
+        const T *g = valid ? base + ld_off[q] : in;
+        const int sz = valid ? (int)sizeof(T) : 0; // src-size 0: zero fill
+        const unsigned d = buf + (unsigned)((tid + q * NT) * (int)sizeof(T));
+        if (sizeof(T) == 4)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(g), "r"(sz));
+        else
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(g), "r"(sz));
       }
     }
   };

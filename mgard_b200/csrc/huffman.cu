@@ -1300,7 +1300,9 @@ int mgb_huffman_compress_async(mgb_plan *p, const uint16_t *d_sym, uint64_t n,
                                                    d_ocount_ptr ? p->outlier_cap : ~0ull)));
   u64 *ddata = (u64 *)(d_out + fixed);
   constexpr int TILE_WORDS = 8 * 256 * 56 / 64 + 4;
-  static const bool enc_shared = getenv("MGB_ENC_GLOBAL_CB") == nullptr;
+  // the codebook is read through L1 (measured faster than a shared-memory copy,
+  // which limits the kernel to two blocks per SM); MGB_ENC_SHARED_CB=1 for A/B runs
+  static const bool enc_shared = getenv("MGB_ENC_SHARED_CB") != nullptr;
   if (dict <= 16384 && enc_shared) {
     size_t smem = ((size_t)dict + TILE_WORDS) * 8;
     cudaFuncSetAttribute(encode_kernel<true>,

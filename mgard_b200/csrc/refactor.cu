@@ -24,6 +24,7 @@
 #include <cstdint>
 
 #include "fused3d.cuh"
+#include "restore3d.cuh"
 #include "plan.h"
 
 namespace {
@@ -40,6 +41,7 @@ struct Geom {
   const void *t0[5]; // per-dim table 0 (ratio / coefficient table)
   int axis, zero_block;
   unsigned rows;  // product of n[0..D-2] (or kernel specific)
+  int grid_rows;  // slower-dim indices come from blockIdx.{x,y,z} (no division)
 };
 
 template <typename T> __device__ __forceinline__ T lerp_ref(T v0, T v1, T t) {
@@ -155,24 +157,58 @@ template <typename T, int DS> struct CoefDispatch<T, DS, -1> {
                                              const T (&)[5]) {}
 };
 
-template <typename T, int DS>
-__global__ void __launch_bounds__(256) coef_kernel(const Geom g, const T *__restrict__ in,
-                                                   T *__restrict__ out,
-                                                   T *__restrict__ coarse) {
+// Indices of the slower dims of the row a thread works on.  grid_rows: the
+// fastest slower dim comes from blockIdx.x / threadIdx.y, the next from
+// blockIdx.y and the rest from blockIdx.z, so that the common 2-D / 3-D case
+// needs no integer division; otherwise the linear row index is decomposed.
+template <int DS>
+__device__ __forceinline__ bool row_indices(const Geom &g, unsigned (&idx)[5]) {
+  if (DS == 0)
+    return blockIdx.x == 0 && threadIdx.y == 0;
+  if (g.grid_rows) {
+    idx[DS - 1] = blockIdx.x * blockDim.y + threadIdx.y;
+    if (idx[DS - 1] >= (unsigned)g.n[DS - 1])
+      return false;
+    if (DS >= 2)
+      idx[DS - 2] = blockIdx.y;
+    if (DS >= 3) {
+      unsigned rem = blockIdx.z;
+#pragma unroll
+      for (int d = DS - 3; d >= 0; d--) {
+        unsigned nd = (unsigned)g.n[d];
+        idx[d] = rem % nd;
+        rem /= nd;
+      }
+    }
+    return true;
+  }
   unsigned row = blockIdx.x * blockDim.y + threadIdx.y;
   if (row >= g.rows)
+    return false;
+#pragma unroll
+  for (int d = DS - 1; d >= 0; d--) {
+    unsigned nd = (unsigned)g.n[d];
+    idx[d] = row % nd;
+    row /= nd;
+  }
+  return true;
+}
+
+template <typename T, int DS>
+__global__ void __launch_bounds__(512) coef_kernel(const Geom g, const T *__restrict__ in,
+                                                   T *__restrict__ out,
+                                                   T *__restrict__ coarse) {
+  unsigned idx[5];
+  if (!row_indices<DS>(g, idx))
     return;
-  // decompose the row index into slower-dim nodal indices
   i64 in_off = 0, out_off = 0, c_off = 0;
   int mask = 0;
   i64 dstride[5];
   T rat[5];
-  unsigned rem = row;
 #pragma unroll
   for (int d = DS - 1; d >= 0; d--) {
     unsigned nd = (unsigned)g.n[d];
-    unsigned i = rem % nd;
-    rem /= nd;
+    unsigned i = idx[d];
     bool ghost = ((nd & 1) == 0) && (i == nd - 1);
     bool odd = (i & 1) && !ghost;
     unsigned p = odd ? g.nc[d] + (i >> 1) : (ghost ? g.nc[d] - 1 : (i >> 1));
@@ -286,22 +322,20 @@ template <typename T, int DS> struct RestoreDispatch<T, DS, -1> {
 };
 
 template <typename T, int DS>
-__global__ void __launch_bounds__(256) restore_kernel(const Geom g, const T *__restrict__ coarse,
+__global__ void __launch_bounds__(512) restore_kernel(const Geom g, const T *__restrict__ coarse,
                                                       const T *__restrict__ coef,
                                                       T *__restrict__ out) {
-  unsigned row = blockIdx.x * blockDim.y + threadIdx.y;
-  if (row >= g.rows)
+  unsigned idx[5];
+  if (!row_indices<DS>(g, idx))
     return;
   i64 c_off = 0, b_off = 0, o_off = 0;
   int mask = 0;
   i64 dstride[5], dlo[5];
   T rat[5];
-  unsigned rem = row;
 #pragma unroll
   for (int d = DS - 1; d >= 0; d--) {
     unsigned nd = (unsigned)g.n[d];
-    unsigned i = rem % nd;
-    rem /= nd;
+    unsigned i = idx[d];
     bool ghost = ((nd & 1) == 0) && (i == nd - 1);
     bool odd = (i & 1) && !ghost;
     unsigned p = odd ? g.nc[d] + (i >> 1) : (ghost ? g.nc[d] - 1 : (i >> 1));
@@ -332,7 +366,7 @@ __global__ void __launch_bounds__(256) restore_kernel(const Geom g, const T *__r
 // (LinearProcessingKernel3D.hpp:99-133).
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) mass_trans_kernel(const Geom g, const T *__restrict__ in,
+__global__ void __launch_bounds__(512) mass_trans_kernel(const Geom g, const T *__restrict__ in,
                                                          T *__restrict__ out) {
   const int D = g.D;
   const int a = g.axis;
@@ -703,10 +737,23 @@ void dense_strides(const uint64_t *shape, int D, i64 *s) {
 }
 
 void row_launch_dims(int nf_threads, unsigned rows, dim3 &grid, dim3 &block) {
-  int bx = 32;
-  while (bx < nf_threads && bx < 256)
-    bx <<= 1;
-  int by = 256 / bx;
+  // threads along the fastest dimension: a multiple of 32 that wastes the fewest
+  // slots in the last sweep (sizes 2^k + 1 give 2^(k-1) + 1 pairs: a power of two
+  // would leave its second sweep almost empty)
+  int bx = 32, best = 1 << 30;
+  for (int cand = 32; cand <= 512; cand += 32) {
+    int sweeps = (nf_threads + cand - 1) / cand;
+    int waste = sweeps * cand - nf_threads;
+    // prefer few sweeps when the waste ties
+    int cost = waste * 8 + sweeps;
+    if (cost < best) {
+      best = cost;
+      bx = cand;
+    }
+    if (cand >= nf_threads)
+      break;
+  }
+  int by = std::max(1, 256 / bx);
   block = dim3(bx, by, 1);
   grid = dim3((rows + by - 1) / by, 1, 1);
 }
@@ -779,17 +826,34 @@ int correction(mgb_plan *p, int l, const T *coef, T **result, T *acc, int mode,
   return MGB_SUCCESS;
 }
 
+// grid over the slower dims without a linear row index when the sizes fit
+template <int DS> void row_grid(Geom &g, dim3 &grid, const dim3 &block) {
+  g.grid_rows = 0;
+  if (DS == 0)
+    return;
+  unsigned long long gy = DS >= 2 ? (unsigned long long)g.n[DS - 2] : 1, gz = 1;
+  for (int d = 0; d + 3 <= DS; d++)
+    gz *= (unsigned long long)g.n[d];
+  if (gy > 65535 || gz > 65535)
+    return;
+  g.grid_rows = 1;
+  grid = dim3((g.n[DS - 1] + block.y - 1) / block.y, (unsigned)gy, (unsigned)gz);
+}
 template <typename T, int DS>
-void launch_coef(const Geom &g, const T *in, T *out, T *coarse, cudaStream_t st) {
+void launch_coef(const Geom &g0, const T *in, T *out, T *coarse, cudaStream_t st) {
+  Geom g = g0;
   dim3 grid, block;
   row_launch_dims((g.n[DS] + 1) / 2, g.rows, grid, block);
+  row_grid<DS>(g, grid, block);
   MGB_LAUNCH(MGB_K_COEF, st, (coef_kernel<T, DS><<<grid, block, 0, st>>>(g, in, out, coarse)));
 }
 template <typename T, int DS>
-void launch_restore(const Geom &g, const T *coarse, const T *coef, T *out,
+void launch_restore(const Geom &g0, const T *coarse, const T *coef, T *out,
                     cudaStream_t st) {
+  Geom g = g0;
   dim3 grid, block;
   row_launch_dims((g.n[DS] + 1) / 2, g.rows, grid, block);
+  row_grid<DS>(g, grid, block);
   MGB_LAUNCH(MGB_K_RESTORE, st, (restore_kernel<T, DS><<<grid, block, 0, st>>>(g, coarse, coef, out)));
 }
 
@@ -857,6 +921,32 @@ bool launch_thomas_smem(T *w, int n, i64 inner, i64 outer, const T *fw, const T 
              (thomas_smem_kernel<T, W><<<(unsigned)blocks, W, smem, st>>>(w, n, inner, lines, fw, am,
                                                                           bm, acc, mode)));
   return true;
+}
+
+// D == 3: tiled restore (restore3d.cuh) instead of the row-based restore_kernel
+template <typename T>
+void launch_restore3d(mgb_plan *p, int l, const T *coarse, const T *coef, T *out,
+                      cudaStream_t st) {
+  restore3d::Params<T> P;
+  i64 full[5], dc[5], dn[5];
+  dense_strides(p->shape, 3, full);
+  dense_strides(p->lshape[l - 1], 3, dc);
+  dense_strides(p->lshape[l], 3, dn);
+  for (int d = 0; d < 3; d++) {
+    P.n[d] = (int)p->lshape[l][d];
+    P.nc[d] = (int)p->lshape[l - 1][d];
+    P.np[d] = 2 * P.nc[d] - 1;
+    P.sc[d] = dc[d];
+    P.sb[d] = full[d];
+    P.so[d] = dn[d];
+    P.ratio[d] = (const T *)p->dtab(p->tab[l][d].ratio);
+  }
+  const int tiles_r = (P.nc[0] + restore3d::TR - 1) / restore3d::TR;
+  P.tiles_c = (P.nc[1] + restore3d::TC - 1) / restore3d::TC;
+  P.tiles_f = (P.nc[2] + restore3d::TF - 1) / restore3d::TF;
+  unsigned grid = (unsigned)(tiles_r * P.tiles_c * P.tiles_f);
+  MGB_LAUNCH(MGB_K_RESTORE, st,
+             (restore3d::kernel<T><<<grid, restore3d::NT, 0, st>>>(P, coarse, coef, out)));
 }
 
 // Thomas solves (all dims) in place on the dense coarse-shaped array w; the
@@ -1045,6 +1135,10 @@ int recompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
     dense_strides(p->lshape[l], D, g.sc);
     fill_tables<T>(p, l, g, false);
     T *dst = l == p->L ? d_out : cbuf + p->cbuf_off[l];
+    if (D == 3 && !p->force_generic) {
+      launch_restore3d<T>(p, l, coarse, d_in, dst, st);
+      continue;
+    }
     switch (D) {
     case 1: launch_restore<T, 0>(g, coarse, d_in, dst, st); break;
     case 2: launch_restore<T, 1>(g, coarse, d_in, dst, st); break;

@@ -216,11 +216,12 @@ level_kernel(const Params<T> P, const T *__restrict__ in, T *__restrict__ coef_o
   const i64 w_col = (i64)(c0 + ty) * P.sw[1] + (i64)(f0 + tx) * P.sw[2];
 
   // ---- helpers -------------------------------------------------------------
-  auto slot = [&](int j) -> T * { return s_raw + ((j - jstart) % NSLOT) * (PC * PF); };
+  auto slot_idx = [&](int j) -> int { return (j - jstart) % NSLOT; };
+  auto slot = [&](int j) -> T * { return s_raw + slot_idx(j) * (PC * PF); };
   const unsigned s_raw_addr = (unsigned)__cvta_generic_to_shared(s_raw);
   // asynchronous copy of nodal plane j (MODE 0) / coefficient plane j (MODE 1)
   auto issue_plane = [&](int j) {
-    const unsigned buf = s_raw_addr + (unsigned)(((j - jstart) % NSLOT) * (PC * PF) * (int)sizeof(T));
+    const unsigned buf = s_raw_addr + (unsigned)(slot_idx(j) * (PC * PF) * (int)sizeof(T));
     const int sr = src_index(j, nr, npr);
     const T *base = in + (i64)(sr >= 0 ? (MODE == 0 ? sr : oct_pos(j, rr)) : 0) * P.sin[0];
     const bool plane_ok = sr >= 0;

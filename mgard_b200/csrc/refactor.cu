@@ -888,7 +888,12 @@ int launch_fused3d(mgb_plan *p, int l, const T *in, const i64 *in_strides, T *co
   // enough blocks for ~16 per SM so that the last wave is a small fraction;
   // every r segment re-reads two warm-up plane pairs, so keep them >= 8 planes
   int rsegs = (148 * 16 + tiles - 1) / tiles;
-  rsegs = std::max(1, std::min(rsegs, std::max(1, P.nc[0] / 8)));
+  int seg_cap = std::max(1, P.nc[0] / 8);
+  if (tiles * seg_cap < 148 * 3)
+    // small level: the sweep is latency bound, so fill the GPU with short
+    // segments (down to 2 coarse planes) and accept the re-read warm-up planes
+    seg_cap = std::max(1, P.nc[0] / 2);
+  rsegs = std::max(1, std::min(rsegs, seg_cap));
   P.rsegs = rsegs;
   size_t smem = fused3d::smem_bytes<T>(MODE);
   if (smem > 48 * 1024) {

@@ -23,7 +23,9 @@
 #include <algorithm>
 #include <cstdint>
 
+#include "coef3d.cuh"
 #include "fused3d.cuh"
+#include "masstrans3d.cuh"
 #include "restore3d.cuh"
 #include "plan.h"
 
@@ -928,6 +930,57 @@ bool launch_thomas_smem(T *w, int n, i64 inner, i64 outer, const T *fw, const T 
   return true;
 }
 
+// D == 3: coefficients (coef3d.cuh) and load vector (masstrans3d.cuh)
+template <typename T>
+void launch_coef3d(mgb_plan *p, int l, const T *in, T *coef, T *coarse, cudaStream_t st) {
+  coef3d::Params<T> P;
+  i64 full[5], dc[5], dn[5];
+  dense_strides(p->shape, 3, full);
+  dense_strides(p->lshape[l - 1], 3, dc);
+  dense_strides(p->lshape[l], 3, dn);
+  for (int d = 0; d < 3; d++) {
+    P.n[d] = (int)p->lshape[l][d];
+    P.nc[d] = (int)p->lshape[l - 1][d];
+    P.np[d] = 2 * P.nc[d] - 1;
+    P.si[d] = dn[d];
+    P.sb[d] = full[d];
+    P.sc[d] = dc[d];
+    P.ratio[d] = (const T *)p->dtab(p->tab[l][d].ratio);
+  }
+  const int tiles_r = (P.nc[0] + coef3d::TR - 1) / coef3d::TR;
+  P.tiles_c = (P.nc[1] + coef3d::TC - 1) / coef3d::TC;
+  P.tiles_f = (P.nc[2] + coef3d::TF - 1) / coef3d::TF;
+  unsigned grid = (unsigned)(tiles_r * P.tiles_c * P.tiles_f);
+  MGB_LAUNCH(MGB_K_COEF, st, (coef3d::coef3d_kernel<T><<<grid, coef3d::NT, 0, st>>>(P, in, coef, coarse)));
+}
+template <typename T>
+void launch_masstrans3d(mgb_plan *p, int l, const T *coef, T *w_out, cudaStream_t st) {
+  masstrans3d::Params<T> P;
+  i64 full[5], dc[5];
+  dense_strides(p->shape, 3, full);
+  dense_strides(p->lshape[l - 1], 3, dc);
+  for (int d = 0; d < 3; d++) {
+    P.n[d] = (int)p->lshape[l][d];
+    P.nc[d] = (int)p->lshape[l - 1][d];
+    P.sin[d] = full[d];
+    P.sw[d] = dc[d];
+    P.mt[d] = (const T *)p->dtab(p->tab[l][d].mt);
+  }
+  P.ctiles = (P.nc[1] + masstrans3d::TC - 1) / masstrans3d::TC;
+  P.ftiles = (P.nc[2] + masstrans3d::TF - 1) / masstrans3d::TF;
+  const int tiles = P.ctiles * P.ftiles;
+  // ~16 blocks per SM; every r segment re-reads two warm-up plane pairs, so keep
+  // segments >= 8 coarse planes unless the level is too small to fill the GPU
+  int rsegs = (148 * 16 + tiles - 1) / tiles;
+  int seg_cap = std::max(1, P.nc[0] / 8);
+  if (tiles * seg_cap < 148 * 3)
+    seg_cap = std::max(1, P.nc[0] / 2);
+  P.rsegs = std::max(1, std::min(rsegs, seg_cap));
+  unsigned grid = (unsigned)(tiles * P.rsegs);
+  MGB_LAUNCH(MGB_K_MASSTRANS, st,
+             (masstrans3d::masstrans3d_kernel<T><<<grid, masstrans3d::NT, 0, st>>>(P, coef, w_out)));
+}
+
 // D == 3: tiled restore (restore3d.cuh) instead of the row-based restore_kernel
 template <typename T>
 void launch_restore3d(mgb_plan *p, int l, const T *coarse, const T *coef, T *out,
@@ -951,7 +1004,7 @@ void launch_restore3d(mgb_plan *p, int l, const T *coarse, const T *coef, T *out
   P.tiles_f = (P.nc[2] + restore3d::TF - 1) / restore3d::TF;
   unsigned grid = (unsigned)(tiles_r * P.tiles_c * P.tiles_f);
   MGB_LAUNCH(MGB_K_RESTORE, st,
-             (restore3d::kernel<T><<<grid, restore3d::NT, 0, st>>>(P, coarse, coef, out)));
+             (restore3d::restore3d_kernel<T><<<grid, restore3d::NT, 0, st>>>(P, coarse, coef, out)));
 }
 
 // Thomas solves (all dims) in place on the dense coarse-shaped array w; the
@@ -1048,9 +1101,8 @@ int decompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
     T *coarse = cbuf + p->cbuf_off[l - 1];
     if (D == 3 && !p->force_generic) {
       T *w = (T *)p->d_wA;
-      rc = launch_fused3d<T, 0>(p, l, cur, g.sa, d_out, coarse, w, st);
-      if (rc)
-        return rc;
+      launch_coef3d<T>(p, l, cur, d_out, coarse, st);
+      launch_masstrans3d<T>(p, l, d_out, w, st);
       thomas_all<T>(p, l, w, coarse, 1, st);
       cur = coarse;
       continue;
@@ -1117,9 +1169,8 @@ int recompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
     T *w = nullptr;
     if (D == 3 && !p->force_generic) {
       w = (T *)p->d_wA;
-      rc = launch_fused3d<T, 1>(p, l, d_in, full, nullptr, nullptr, w, st);
-      if (!rc)
-        thomas_all<T>(p, l, w, coarse, 2, st);
+      launch_masstrans3d<T>(p, l, d_in, w, st);
+      thomas_all<T>(p, l, w, coarse, 2, st);
     } else {
       rc = correction<T>(p, l, d_in, &w, coarse, 2, st);
     }

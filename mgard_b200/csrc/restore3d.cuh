@@ -53,7 +53,7 @@ __device__ __forceinline__ int src_index(int j, int n, int np) {
 
 template <typename T>
 __global__ void __launch_bounds__(NT)
-kernel(const Params<T> P, const T *__restrict__ coarse, const T *__restrict__ coef,
+restore3d_kernel(const Params<T> P, const T *__restrict__ coarse, const T *__restrict__ coef,
        T *__restrict__ out) {
   __shared__ T s[CR * CC * CF];
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;

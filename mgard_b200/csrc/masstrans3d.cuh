@@ -11,7 +11,8 @@
 // line are two contiguous vectors, and the five inputs of mass_trans at coarse
 // index i are E[i-1], O[i-1], E[i], O[i], E[i+1].  So
 //   f pass: a warp takes one row; every lane loads E[kf] and O[kf] (two
-//           coalesced loads) and gets its neighbours' values with shuffles;
+//           coalesced loads) and gets its neighbours' values with shuffles (the
+//           warp spans 32 columns and owns the inner 30);
 //   c pass: from the f-pass rows of the tile in shared memory;
 //   r pass: from a five-deep register ring while the block sweeps r.
 // A thread block owns a TC x TF tile of coarse (c, f) columns and a segment of
@@ -23,9 +24,13 @@ namespace masstrans3d {
 
 typedef long long i64;
 
-constexpr int TC = 8, TF = 32, NT = 256, NW = NT / 32;
+// A warp covers 32 consecutive coarse f columns kf0-1 .. kf0+30 and OWNS the
+// middle TF = 30: the two outer lanes only supply their neighbours' inputs, so
+// no separate halo loads are needed.
+constexpr int TC = 8, TF = 30, NT = 256, NW = NT / 32;
 constexpr int NROW = 2 * TC + 3;                  // E rows kc0-1..kc0+TC, O rows kc0-1..kc0+TC-1
 constexpr int RPW = (NROW + NW - 1) / NW;         // rows per warp and plane
+constexpr int NST = 4;                            // raw planes in flight (power of two)
 
 template <typename T> struct Params {
   int n[3], nc[3];  // fine / coarse level shape (r, c, f)
@@ -56,7 +61,8 @@ __device__ __forceinline__ int pos(int m, bool odd, int n, int nc) {
 template <typename T>
 __global__ void __launch_bounds__(NT, 3)
 masstrans3d_kernel(const Params<T> P, const T *__restrict__ in, T *__restrict__ w_out) {
-  __shared__ T s_a1[2][NROW][TF]; // f-pass rows of the current plane (double buffered)
+  __shared__ T s_a1[2][NROW][32];
+  __shared__ T s_raw[NST][NROW][2][32]; // [stage][row][E / O][lane] // f-pass rows of the current plane (double buffered)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   int bid = blockIdx.x;
   const int ft = bid % P.ftiles;
@@ -72,97 +78,101 @@ masstrans3d_kernel(const Params<T> P, const T *__restrict__ in, T *__restrict__ 
     return;
 
   // ---- per-thread constants -------------------------------------------------
-  // f: offsets of this lane's E and O element and of the halo element it fetches
-  // (lane 0: E[kf0-1], lane 1: O[kf0-1], lane 2: E[kf0+TF])
-  const int kf = kf0 + lane;
+  // f: this lane's column, offsets of its E and O element (-1: none -> zero)
+  const int kf = kf0 - 1 + lane;
+  const bool own_f = lane >= 1 && lane <= TF && kf < ff;
   const int pe = pos(kf, false, nf, ff), po = pos(kf, true, nf, ff);
-  int px = -1;
-  bool x_odd = false;
-  if (lane == 0)
-    px = pos(kf0 - 1, false, nf, ff);
-  else if (lane == 1) {
-    px = pos(kf0 - 1, true, nf, ff);
-    x_odd = true;
-  } else if (lane == 2)
-    px = pos(kf0 + TF, false, nf, ff);
-  const i64 off_e = (i64)pe * P.sin[2], off_o = (i64)po * P.sin[2], off_x = (i64)px * P.sin[2];
-  // rows of this warp: row index q -> (c position, is odd-c row)
-  i64 row_off[RPW];
-  bool row_ok[RPW], row_odd[RPW];
+  // rows of this warp: per row the offsets of the lane's E and O element from the
+  // plane base (32-bit; -1: nothing to load)
+  int roff_e[RPW], roff_o[RPW];
+  bool row_odd[RPW];
 #pragma unroll
   for (int q = 0; q < RPW; q++) {
     const int row = wid + q * NW;
-    row_ok[q] = false;
+    roff_e[q] = roff_o[q] = -1;
     row_odd[q] = false;
-    row_off[q] = 0;
     if (row < NROW) {
       const bool odd = row >= TC + 2;
       const int m = kc0 - 1 + (odd ? row - (TC + 2) : row);
       const int pc = pos(m, odd, ncn, cc);
       row_odd[q] = odd;
       if (pc >= 0) {
-        row_ok[q] = true;
-        row_off[q] = (i64)pc * P.sin[1];
+        if (pe >= 0)
+          roff_e[q] = (int)((i64)pc * P.sin[1] + (i64)pe * P.sin[2]);
+        if (po >= 0)
+          roff_o[q] = (int)((i64)pc * P.sin[1] + (i64)po * P.sin[2]);
       }
     }
   }
   T kfc[9], kcc[9];
 #pragma unroll
   for (int m = 0; m < 9; m++) {
-    kfc[m] = kf < ff ? P.mt[2][m * ff + kf] : (T)0;
+    kfc[m] = (kf >= 0 && kf < ff) ? P.mt[2][m * ff + kf] : (T)0;
     kcc[m] = (kc0 + wid < cc) ? P.mt[1][m * cc + kc0 + wid] : (T)0;
   }
-  const bool col_ok = (kc0 + wid < cc) && (kf < ff);
+  const bool col_ok = (kc0 + wid < cc) && own_f;
   const i64 w_col = (i64)(kc0 + wid) * P.sw[1] + (i64)kf * P.sw[2];
 
   // ---- plane sequence: (E,O) of k = rk0-1 .. rk1-1, then E of rk1 ------------
   // plane index t: k = rk0 - 1 + t / 2, odd-r plane iff t & 1
   const int nplanes = 2 * (rk1 - rk0 + 1) + 1;
-  T ve[RPW], vo[RPW], vx[RPW]; // prefetched raw values of the next plane
-  auto fetch = [&](int t) {
+  // raw planes: ring of NST stages in shared memory filled with asynchronous
+  // copies NST-1 planes ahead (a warp only ever reads the rows it requested
+  // itself, so completion needs no block-wide barrier)
+  const unsigned raw_addr = (unsigned)__cvta_generic_to_shared(&s_raw[0][0][0][0]);
+  auto issue = [&](int t) {
     const int k = rk0 - 1 + (t >> 1);
     const bool rodd = t & 1;
     const int pr = pos(k, rodd, nr, rr);
     const T *base = in + (i64)(pr >= 0 ? pr : 0) * P.sin[0];
+    const unsigned stage = raw_addr + (unsigned)((t & (NST - 1)) * (NROW * 64) * (int)sizeof(T));
 #pragma unroll
     for (int q = 0; q < RPW; q++) {
-      ve[q] = vo[q] = vx[q] = (T)0;
-      if (pr >= 0 && row_ok[q]) {
-        const T *rp = base + row_off[q];
+      const int row = wid + q * NW;
+      if (row < NROW) { // warp uniform
         // the all-coarse block (even r, even c, even f) counts as zero
-        const bool ezero = !rodd && !row_odd[q];
-        if (pe >= 0 && !ezero)
-          ve[q] = rp[off_e];
-        if (po >= 0)
-          vo[q] = rp[off_o];
-        if (px >= 0 && !(ezero && !x_odd))
-          vx[q] = rp[off_x];
+        const bool ve_ok = pr >= 0 && roff_e[q] >= 0 && (rodd || row_odd[q]);
+        const bool vo_ok = pr >= 0 && roff_o[q] >= 0;
+        const unsigned d = stage + (unsigned)((row * 64 + lane) * (int)sizeof(T));
+        const T *ge = ve_ok ? base + roff_e[q] : in;
+        const T *go = vo_ok ? base + roff_o[q] : in;
+        const int se = ve_ok ? (int)sizeof(T) : 0, so = vo_ok ? (int)sizeof(T) : 0; // 0: zero fill
+        if (sizeof(T) == 4) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(ge), "r"(se));
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d + 32 * 4), "l"(go), "r"(so));
+        } else {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(ge), "r"(se));
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d + 32 * 8), "l"(go), "r"(so));
+        }
       }
     }
   };
   T ring[5] = {(T)0, (T)0, (T)0, (T)0, (T)0};
-  fetch(0);
+#pragma unroll
+  for (int t = 0; t < NST - 1; t++) {
+    if (t < nplanes)
+      issue(t);
+    asm volatile("cp.async.commit_group;\n" ::);
+  }
+  const int lm = lane > 0 ? lane - 1 : 0, lp = lane < 31 ? lane + 1 : 31;
   for (int t = 0; t < nplanes; t++) {
-    // f pass of plane t from the prefetched registers
+    if (t + NST - 1 < nplanes)
+      issue(t + NST - 1);
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(NST - 1));
+    __syncwarp();
+    // f pass of plane t
     T a1[RPW];
+    const T(*raw)[2][32] = s_raw[t & (NST - 1)];
 #pragma unroll
     for (int q = 0; q < RPW; q++) {
-      const T e = ve[q], o = vo[q], x = vx[q];
-      T em1 = __shfl_up_sync(0xffffffffu, e, 1), om1 = __shfl_up_sync(0xffffffffu, o, 1);
-      T ep1 = __shfl_down_sync(0xffffffffu, e, 1);
-      const T x0 = __shfl_sync(0xffffffffu, x, 0), x1 = __shfl_sync(0xffffffffu, x, 1),
-              x2 = __shfl_sync(0xffffffffu, x, 2);
-      if (lane == 0) {
-        em1 = x0;
-        om1 = x1;
-      }
-      if (lane == 31)
-        ep1 = x2;
-      a1[q] = mass_trans_k<T>(em1, om1, e, o, ep1, kfc);
+      const int row = wid + q * NW;
+      a1[q] = (T)0;
+      if (row < NROW) // warp uniform; lanes 0 and 31 produce values nobody uses
+        a1[q] = mass_trans_k<T>(raw[row][0][lm], raw[row][1][lm], raw[row][0][lane],
+                                raw[row][1][lane], raw[row][0][lp], kfc);
     }
-    if (t + 1 < nplanes)
-      fetch(t + 1);
-    T(*sa)[TF] = s_a1[t & 1];
+    T(*sa)[32] = s_a1[t & 1];
 #pragma unroll
     for (int q = 0; q < RPW; q++) {
       const int row = wid + q * NW;

@@ -367,7 +367,7 @@ def main():
         alg = {
             "coef": 2 * nl * 4,                    # read the level box, write coefficients + coarse
             "restore": 2 * nl * 4,
-            "mass_trans": (nl + nl // 2) * 4,      # finest pass: read n, write n/2
+            "mass_trans": (nl + cs) * 4,           # fused f/c/r pass: read n, write n/8
             "quantize_hist": nl * 4 + nl * 2,      # read T, write u16 symbols
             "dequantize": nl * 2 + nl * 4,
             "encode": nl * 2 + total_stream / world,

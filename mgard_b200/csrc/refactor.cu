@@ -17,14 +17,14 @@
 // a dense coarse buffer afterwards), writes its coefficients straight to their
 // final position in the output array (coarse-first layout along every
 // dimension) and the coarse nodes to the next dense buffer; no CopyND /
-// in-place permutation passes.  All kernels are dimension-generic (D = 1..5)
-// through a (rows x fastest-dim) mapping: a thread block owns rows, threads
-// sweep the contiguous dimension, so every global access is coalesced.
+// in-place permutation passes.  The kernels in this file are dimension-generic
+// (D = 1..5) through a (rows x fastest-dim) mapping: a thread block owns rows,
+// threads sweep the contiguous dimension, so every global access is coalesced.
+// D == 3 takes the tiled kernels of coef3d.cuh / masstrans3d.cuh / restore3d.cuh.
 #include <algorithm>
 #include <cstdint>
 
 #include "coef3d.cuh"
-#include "fused3d.cuh"
 #include "masstrans3d.cuh"
 #include "restore3d.cuh"
 #include "plan.h"
@@ -621,8 +621,8 @@ thomas_smem_kernel(T *__restrict__ x, int n, i64 inner, i64 lines,
       }
     }
   }
-  fused3d::cp_async_commit();
-  fused3d::cp_async_wait<0>();
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
   __syncthreads();
   if (mine) {
     T *c = s + lane;
@@ -863,50 +863,6 @@ template <typename T>
 void axpy(T *acc, const T *w, i64 n, int subtract, cudaStream_t st) {
   unsigned blocks = (unsigned)std::min<i64>((n + 255) / 256, 148 * 16);
   MGB_LAUNCH(MGB_K_AXPY, st, (axpy_kernel<T><<<blocks, 256, 0, st>>>(acc, w, n, subtract)));
-}
-
-// D == 3: one fused launch per level (fused3d.cuh) instead of coef + 3 x mass_trans
-template <typename T, int MODE>
-int launch_fused3d(mgb_plan *p, int l, const T *in, const i64 *in_strides, T *coef_out,
-                   T *coarse_out, T *w_out, cudaStream_t st) {
-  fused3d::Params<T> P;
-  i64 full[5], dc[5];
-  dense_strides(p->shape, 3, full);
-  dense_strides(p->lshape[l - 1], 3, dc);
-  for (int d = 0; d < 3; d++) {
-    P.n[d] = (int)p->lshape[l][d];
-    P.nc[d] = (int)p->lshape[l - 1][d];
-    P.np[d] = 2 * P.nc[d] - 1;
-    P.sin[d] = in_strides[d];
-    P.sout[d] = full[d];
-    P.scoarse[d] = dc[d];
-    P.sw[d] = dc[d];
-    P.ratio[d] = (const T *)p->dtab(p->tab[l][d].ratio);
-    P.mt[d] = (const T *)p->dtab(p->tab[l][d].mt);
-  }
-  P.ctiles = (P.nc[1] + fused3d::TC - 1) / fused3d::TC;
-  P.ftiles = (P.nc[2] + fused3d::TF - 1) / fused3d::TF;
-  int tiles = P.ctiles * P.ftiles;
-  // enough blocks for ~16 per SM so that the last wave is a small fraction;
-  // every r segment re-reads two warm-up plane pairs, so keep them >= 8 planes
-  int rsegs = (148 * 16 + tiles - 1) / tiles;
-  int seg_cap = std::max(1, P.nc[0] / 8);
-  if (tiles * seg_cap < 148 * 3)
-    // small level: the sweep is latency bound, so fill the GPU with short
-    // segments (down to 2 coarse planes) and accept the re-read warm-up planes
-    seg_cap = std::max(1, P.nc[0] / 2);
-  rsegs = std::max(1, std::min(rsegs, seg_cap));
-  P.rsegs = rsegs;
-  size_t smem = fused3d::smem_bytes<T>(MODE);
-  if (smem > 48 * 1024) {
-    cudaFuncSetAttribute(fused3d::level_kernel<T, MODE>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  }
-  unsigned grid = (unsigned)(tiles * rsegs);
-  MGB_LAUNCH(MODE == 0 ? MGB_K_COEF : MGB_K_MASSTRANS, st,
-             (fused3d::level_kernel<T, MODE><<<grid, fused3d::NT, smem, st>>>(
-                 P, in, coef_out, coarse_out, w_out)));
-  return MGB_SUCCESS;
 }
 
 template <typename T, int W>

@@ -901,7 +901,8 @@ decode_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__restr
 // the canonical walk at the shortest length their DEC_K-bit prefix allows.
 // Chunks that do not fit the shared buffers are counted in *n_skipped and left
 // to decode_kernel.
-constexpr int DF_T = 512; // threads per block
+constexpr int DF_T = 512;   // threads per block, first launch (two blocks per SM)
+constexpr int DF_TBIG = 1024; // second launch (one block per SM, large buffers)
 // sub-sequence length of the fast decoder: 5 words, and every thread owns an ODD
 // number of them, so the threads of a warp read the bit stream at an odd word
 // stride (no shared-memory bank conflicts)
@@ -983,7 +984,8 @@ __device__ __forceinline__ unsigned fast_decode_one(const FastTables &t, unsigne
   return l;
 }
 
-__global__ void __launch_bounds__(DF_T, 2)
+template <int NT>
+__global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1)
 decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
                    const u64 *__restrict__ woff, u64 nchunk, int chunk, u64 n,
                    const u64 *__restrict__ decodebook, int dict, unsigned bufw,
@@ -999,16 +1001,16 @@ decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
   u64 *s_first = reinterpret_cast<u64 *>(df_smem), *s_entry = s_first + 64;
   unsigned *s_lut = reinterpret_cast<unsigned *>(s_first + 128);
   u64 *s_words = reinterpret_cast<u64 *>(s_lut + (1 << DEC_K)); // bufw + 2 (zero padding)
-  const unsigned nslot = (bufw * 64 / DF_SB + 2 * DF_T + 3) & ~3u; // sub-sequence slots (keeps s_out 16-byte aligned)
+  const unsigned nslot = (bufw * 64 / DF_SB + 2 * NT + 3) & ~3u; // sub-sequence slots (keeps s_out 16-byte aligned)
   unsigned *s_en = reinterpret_cast<unsigned *>(s_words + bufw + 2);
   unsigned *s_st = s_en + nslot;
-  unsigned char *s_cn = reinterpret_cast<unsigned char *>(s_st + DF_T);
+  unsigned char *s_cn = reinterpret_cast<unsigned char *>(s_st + NT);
   uint16_t *s_out = reinterpret_cast<uint16_t *>(s_cn + ((nslot + 15) & ~15u));
-  __shared__ unsigned s_scan[DF_T / 32];
+  __shared__ unsigned s_scan[NT / 32];
   __shared__ unsigned s_t32[36], s_b32[36];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
-  for (int i = tid; i < 128; i += DF_T)
+  for (int i = tid; i < 128; i += NT)
     s_first[i] = decodebook[i];
   __syncthreads();
   if (tid < 36) {
@@ -1019,7 +1021,7 @@ decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
   int lmin = 1;
   while (lmin < 63 && s_first[lmin] == ~0ull)
     lmin++;
-  for (int x = tid; x < (1 << DEC_K); x += DF_T) {
+  for (int x = tid; x < (1 << DEC_K); x += NT) {
     unsigned e = 0xffffffffu;
     for (int l = lmin; l <= DEC_K; l++) {
       const u64 v = (u64)x >> (DEC_K - l);
@@ -1069,7 +1071,7 @@ decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
     const unsigned nsym = (unsigned)min((u64)chunk, n - c * (u64)chunk);
     // 0. chunk words -> shared memory (all copies in flight), then every thread
     //    swaps the halves of its own words into stream order
-    for (unsigned i = tid; i < nw; i += DF_T) {
+    for (unsigned i = tid; i < nw; i += NT) {
       const unsigned d = (unsigned)__cvta_generic_to_shared(s_words + i);
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src + i));
     }
@@ -1078,11 +1080,11 @@ decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
       s_words[nw + tid] = 0; // the reader may look up to two words past the end
     // run geometry: K (odd) sub-sequences of DF_SB bits per thread
     const unsigned NS = (B + DF_SB - 1) / DF_SB;
-    const unsigned K = ((NS + DF_T - 1) / DF_T) | 1u;
+    const unsigned K = ((NS + NT - 1) / NT) | 1u;
     const unsigned run0 = tid * K * DF_SB; // first bit of this thread's run
     const bool active = run0 < B;
     asm volatile("cp.async.wait_group 0;\n" ::);
-    for (unsigned i = tid; i < nw; i += DF_T) {
+    for (unsigned i = tid; i < nw; i += NT) {
       const uint2 w = reinterpret_cast<uint2 *>(s_words)[i];
       reinterpret_cast<uint2 *>(s_words)[i] = make_uint2(w.y, w.x);
     }
@@ -1107,7 +1109,7 @@ decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
     __syncthreads();
     // 2. synchronise: restart from the predecessor's end until the parse meets
     //    a recorded sub-sequence end
-    for (unsigned round = 0; round <= DF_T; round++) {
+    for (unsigned round = 0; round <= NT; round++) {
       int changed = 0;
       if (active && tid > 0) {
         const unsigned s0 = s_en[tid * K - 1];
@@ -1151,7 +1153,7 @@ decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
     __syncthreads();
     unsigned wpre = 0;
 #pragma unroll
-    for (int k = 0; k < DF_T / 32; k++)
+    for (int k = 0; k < NT / 32; k++)
       if (k < wid)
         wpre += s_scan[k];
     unsigned off = wpre + x - cnt;
@@ -1173,12 +1175,12 @@ decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
       const uint4 *s4 = reinterpret_cast<const uint4 *>(s_out);
       uint4 *g4 = reinterpret_cast<uint4 *>(g);
       const unsigned n16 = nsym / 8;
-      for (unsigned k = tid; k < n16; k += DF_T)
+      for (unsigned k = tid; k < n16; k += NT)
         __stcs(g4 + k, s4[k]);
-      for (unsigned k = n16 * 8 + tid; k < nsym; k += DF_T)
+      for (unsigned k = n16 * 8 + tid; k < nsym; k += NT)
         g[k] = s_out[k];
     } else {
-      for (unsigned k = tid; k < nsym; k += DF_T)
+      for (unsigned k = tid; k < nsym; k += NT)
         g[k] = s_out[k];
     }
     __syncthreads();
@@ -1430,28 +1432,28 @@ extern "C" int mgb_huffman_decompress(mgb_plan *p, const uint8_t *d_in, uint64_t
   unsigned fast_bufw = 0, big_bufw = 0;
   unsigned *cnt1 = (unsigned *)((u64 *)p->d_scalars + 15), *cnt2 = cnt1 + 1;
   unsigned *list1 = sub + 3 * subn, *list2 = list1 + nchunk;
-  const size_t fixed = 128 * 8 + (size_t)(1 << DEC_K) * 4 + (size_t)DF_T * 4 +
-                       (((size_t)chunk * 2 + 15) & ~(size_t)15) + 64;
-  auto fast_smem = [&](unsigned bw) {
-    const unsigned nslot = (bw * 64 / DF_SB + 2 * DF_T + 3) & ~3u;
+  auto fast_smem = [&](unsigned bw, int nt) {
+    const unsigned nslot = (bw * 64 / DF_SB + 2 * nt + 3) & ~3u;
     return 128 * 8 + (size_t)(1 << DEC_K) * 4 + ((size_t)bw + 2) * 8 + (size_t)nslot * 4 +
-           (size_t)DF_T * 4 + ((nslot + 15) & ~15u) + (((size_t)chunk * 2 + 15) & ~(size_t)15);
+           (size_t)nt * 4 + ((nslot + 15) & ~15u) + (((size_t)chunk * 2 + 15) & ~(size_t)15);
+  };
+  // largest word buffer whose launch fits `budget` bytes of shared memory
+  // (per word: 8 B data + 64/DF_SB x (4 B end slot + 1 B count))
+  auto max_words = [&](size_t budget, int nt) -> u64 {
+    const size_t fixed = fast_smem(0, nt) + 64;
+    return fixed >= budget ? 0 : (budget - fixed) / 10;
   };
   {
-    const size_t budget = 113 * 1024 - 512, budget_big = 200 * 1024;
-    u64 avg = total_words / nchunk + 1;
+    const u64 avg = total_words / nchunk + 1;
+    const u64 small_max = max_words(113 * 1024 - 512, DF_T);
+    const u64 big_max = max_words(200 * 1024, DF_TBIG);
     u64 want = avg + avg / 4 + 256;
-    if (fixed < budget) {
-      // per word: 8 B data + 64/DF_SB x (4 B end slot + 1 B count)
-      size_t maxw = (budget - fixed - (size_t)DF_T * 10 - 128) / 10;
-      if (want > maxw && avg + avg / 16 + 32 <= maxw)
-        want = maxw;
-      if (want <= maxw)
-        fast_bufw = (unsigned)(want & ~(u64)1);
-    }
-    if (fixed + 16384 < budget_big) {
-      size_t maxw = (budget_big - fixed - (size_t)DF_T * 10 - 128) / 10;
-      big_bufw = (unsigned)(std::min<u64>(maxw, (u64)chunk * 56 / 64 + 2) & ~(u64)1);
+    if (want > small_max && avg + avg / 16 + 32 <= small_max)
+      want = small_max;
+    if (want <= small_max)
+      fast_bufw = (unsigned)(want & ~(u64)1);
+    if (big_max > 64) {
+      big_bufw = (unsigned)(std::min<u64>(big_max, (u64)chunk * 56 / 64 + 2) & ~(u64)1);
       if (big_bufw <= fast_bufw)
         big_bufw = 0;
     }
@@ -1459,9 +1461,13 @@ extern "C" int mgb_huffman_decompress(mgb_plan *p, const uint8_t *d_in, uint64_t
   if (fast_bufw || big_bufw) {
     static bool configured = false;
     if (!configured) {
-      MGB_CUDA_CHECK(cudaFuncSetAttribute(decode_fast_kernel,
+      MGB_CUDA_CHECK(cudaFuncSetAttribute(decode_fast_kernel<DF_T>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 114 * 1024));
+      cudaFuncSetAttribute(decode_fast_kernel<DF_T>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+      MGB_CUDA_CHECK(cudaFuncSetAttribute(decode_fast_kernel<DF_TBIG>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      cudaFuncSetAttribute(decode_fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+      cudaFuncSetAttribute(decode_fast_kernel<DF_TBIG>, cudaFuncAttributePreferredSharedMemoryCarveout,
                            cudaSharedmemCarveoutMaxShared);
       configured = true;
     }
@@ -1470,14 +1476,14 @@ extern "C" int mgb_huffman_decompress(mgb_plan *p, const uint8_t *d_in, uint64_t
   if (fast_bufw) {
     unsigned fblocks = (unsigned)std::min<u64>(nchunk, 148 * 2);
     MGB_LAUNCH(MGB_K_DECODE, st,
-               (decode_fast_kernel<<<fblocks, DF_T, fast_smem(fast_bufw), st>>>(
+               (decode_fast_kernel<DF_T><<<fblocks, DF_T, fast_smem(fast_bufw, DF_T), st>>>(
                    ddata, bits, woff, nchunk, chunk, n, decodebook, dict, fast_bufw, nullptr, nullptr,
                    cnt1, list1, d_sym)));
   }
   if (big_bufw) {
     unsigned fblocks = (unsigned)std::min<u64>(nchunk, 148);
     MGB_LAUNCH(MGB_K_DECODE, st,
-               (decode_fast_kernel<<<fblocks, DF_T, fast_smem(big_bufw), st>>>(
+               (decode_fast_kernel<DF_TBIG><<<fblocks, DF_TBIG, fast_smem(big_bufw, DF_TBIG), st>>>(
                    ddata, bits, woff, nchunk, chunk, n, decodebook, dict, big_bufw,
                    fast_bufw ? cnt1 : nullptr, fast_bufw ? list1 : nullptr, cnt2, list2, d_sym)));
   }

@@ -30,6 +30,16 @@ int mgb_huffman_compress_async(mgb_plan *p, const uint16_t *d_sym, uint64_t n,
                                const int64_t *d_oval, uint8_t *d_out, uint64_t cap,
                                cudaStream_t st);
 int mgb_huffman_finish(mgb_plan *p, uint64_t *size, cudaStream_t st);
+int mgb_huffman_decompress_impl(mgb_plan *p, const uint8_t *d_in, uint64_t size, uint16_t *d_sym,
+                                uint64_t n, uint64_t *ocount, const uint64_t **d_oidx,
+                                const int64_t **d_oval, void *stream, void *d_deq,
+                                double deq_scale, int *fused);
+// quantize.cu internals
+int mgb_linear_dequant_scale(mgb_plan *plan, int ebtype, double tol, double s, double norm,
+                             double *scale);
+int mgb_outlier_restore(mgb_plan *plan, uint64_t ocount, const uint64_t *d_oidx,
+                        const int64_t *d_oval, int ebtype, double tol, double s, double norm,
+                        void *d_coef, cudaStream_t st);
 
 namespace {
 
@@ -124,10 +134,19 @@ extern "C" int mgb_decompress_lowlevel(mgb_plan *p, const uint8_t *d_in, uint64_
   uint64_t oc = 0;
   const uint64_t *oidx = nullptr;
   const int64_t *oval = nullptr;
-  rc = mgb_huffman_decompress(p, d_in, size, p->d_sym, p->N, &oc, &oidx, &oval, st);
+  // s = inf: one dequantization factor for every node, applied by the decoder
+  // while it flushes its chunks (no symbol array, no dequantize pass)
+  double scale = 0;
+  const int linear = mgb_linear_dequant_scale(p, ebtype, tol, s, norm, &scale);
+  int fused = 0;
+  rc = mgb_huffman_decompress_impl(p, d_in, size, p->d_sym, p->N, &oc, &oidx, &oval, st,
+                                   linear ? p->d_coef : nullptr, scale, &fused);
   if (rc)
     return rc;
-  rc = mgb_dequantize(p, p->d_sym, oc, oidx, oval, ebtype, tol, s, norm, p->d_coef, st);
+  if (fused)
+    rc = mgb_outlier_restore(p, oc, oidx, oval, ebtype, tol, s, norm, p->d_coef, st);
+  else
+    rc = mgb_dequantize(p, p->d_sym, oc, oidx, oval, ebtype, tol, s, norm, p->d_coef, st);
   if (rc)
     return rc;
   rc = mgb_recompose_impl(p, p->d_coef, d_out, st);

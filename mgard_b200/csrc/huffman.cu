@@ -738,13 +738,53 @@ decode_sub(const DecTables &t, const u64 *words, u64 nw, unsigned start, unsigne
   return p;
 }
 
-template <bool STAGE_OUT>
+// Flush of a decoded chunk staged in shared memory: symbols as they are, or
+// (DEQ) dequantized on the way out: v = scale * (T)(symbol - dict / 2), the
+// arithmetic of dequantize_linear_kernel (LinearQuantization.hpp:251-264).
+template <typename OUT, int NT>
+__device__ __forceinline__ void flush_chunk(const uint16_t *s_out, OUT *g, unsigned nsym, OUT scale,
+                                            int half, int tid) {
+  if (sizeof(OUT) == 2) {
+    uint16_t *gs = reinterpret_cast<uint16_t *>(g);
+    if ((((uintptr_t)gs) & 15) == 0) {
+      const uint4 *s4 = reinterpret_cast<const uint4 *>(s_out);
+      uint4 *g4 = reinterpret_cast<uint4 *>(gs);
+      const unsigned n16 = nsym / 8;
+      for (unsigned k = tid; k < n16; k += NT)
+        __stcs(g4 + k, s4[k]);
+      for (unsigned k = n16 * 8 + tid; k < nsym; k += NT)
+        gs[k] = s_out[k];
+    } else {
+      for (unsigned k = tid; k < nsym; k += NT)
+        gs[k] = s_out[k];
+    }
+  } else {
+    constexpr int V = 16 / sizeof(OUT); // values per 128-bit store
+    if ((((uintptr_t)g) & 15) == 0) {
+      const unsigned nv = nsym / V;
+      for (unsigned k = tid; k < nv; k += NT) {
+        __align__(16) OUT v[V];
+#pragma unroll
+        for (int j = 0; j < V; j++)
+          v[j] = scale * (OUT)((long long)s_out[k * V + j] - half);
+        __stcs(reinterpret_cast<uint4 *>(g) + k, *reinterpret_cast<const uint4 *>(v));
+      }
+      for (unsigned k = nv * V + tid; k < nsym; k += NT)
+        g[k] = scale * (OUT)((long long)s_out[k] - half);
+    } else {
+      for (unsigned k = tid; k < nsym; k += NT)
+        g[k] = scale * (OUT)((long long)s_out[k] - half);
+    }
+  }
+}
+
+template <bool STAGE_OUT, typename OUT>
 __global__ void __launch_bounds__(DEC_T)
 decode_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__restrict__ bits,
               const u64 *__restrict__ woff, u64 nchunk, int chunk, u64 n,
               const u64 *__restrict__ decodebook, int dict, unsigned *__restrict__ sub_start,
               unsigned *__restrict__ sub_end, unsigned *__restrict__ sub_cnt,
-              uint16_t *__restrict__ out, const unsigned *__restrict__ n_skipped,
+              OUT *__restrict__ out, OUT scale, const unsigned *__restrict__ n_skipped,
               const unsigned *__restrict__ skipped, unsigned fast_bufw) {
   // fast_bufw != 0: decode_fast_kernel ran first and listed the chunks it left
   // (more than fast_bufw words); usually there are few or none
@@ -833,7 +873,8 @@ decode_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__restr
     if (tid == 0)
       s_carry = 0;
     __syncthreads();
-    uint16_t *dst_base = STAGE_OUT ? s_out : out + c * (u64)chunk;
+    // unstaged output is only instantiated for OUT = symbols
+    uint16_t *dst_base = STAGE_OUT ? s_out : reinterpret_cast<uint16_t *>(out) + c * (u64)chunk;
     for (unsigned i0 = 0; i0 < NS; i0 += DEC_T) {
       unsigned i = i0 + tid;
       unsigned cnt = i < NS ? cn[i] : 0;
@@ -867,19 +908,7 @@ decode_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__restr
       __syncthreads();
     }
     if (STAGE_OUT) {
-      uint16_t *g = out + c * (u64)chunk;
-      if ((((uintptr_t)g) & 15) == 0) {
-        const uint4 *s4 = (const uint4 *)s_out;
-        uint4 *g4 = (uint4 *)g;
-        unsigned n16 = nsym / 8;
-        for (unsigned k = tid; k < n16; k += DEC_T)
-          g4[k] = s4[k];
-        for (unsigned k = n16 * 8 + tid; k < nsym; k += DEC_T)
-          g[k] = s_out[k];
-      } else {
-        for (unsigned k = tid; k < nsym; k += DEC_T)
-          g[k] = s_out[k];
-      }
+      flush_chunk<OUT, DEC_T>(s_out, out + c * (u64)chunk, nsym, scale, dict / 2, tid);
       __syncthreads();
     }
   }
@@ -984,14 +1013,14 @@ __device__ __forceinline__ unsigned fast_decode_one(const FastTables &t, unsigne
   return l;
 }
 
-template <int NT>
+template <int NT, typename OUT>
 __global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1)
 decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
                    const u64 *__restrict__ woff, u64 nchunk, int chunk, u64 n,
                    const u64 *__restrict__ decodebook, int dict, unsigned bufw,
                    const unsigned *__restrict__ n_work, const unsigned *__restrict__ work,
                    unsigned *__restrict__ n_skipped, unsigned *__restrict__ skipped,
-                   uint16_t *__restrict__ out) {
+                   OUT *__restrict__ out, OUT scale) {
   // work == nullptr: every chunk; otherwise the *n_work chunks listed in work[]
   // (those an earlier launch with a smaller buffer left over)
   const u64 nwork = work ? (u64)*n_work : nchunk;
@@ -1170,19 +1199,7 @@ decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
       }
     }
     __syncthreads();
-    uint16_t *g = out + c * (u64)chunk;
-    if ((((uintptr_t)g) & 15) == 0) {
-      const uint4 *s4 = reinterpret_cast<const uint4 *>(s_out);
-      uint4 *g4 = reinterpret_cast<uint4 *>(g);
-      const unsigned n16 = nsym / 8;
-      for (unsigned k = tid; k < n16; k += NT)
-        __stcs(g4 + k, s4[k]);
-      for (unsigned k = n16 * 8 + tid; k < nsym; k += NT)
-        g[k] = s_out[k];
-    } else {
-      for (unsigned k = tid; k < nsym; k += NT)
-        g[k] = s_out[k];
-    }
+    flush_chunk<OUT, NT>(s_out, out + c * (u64)chunk, nsym, scale, dict / 2, tid);
     __syncthreads();
   }
 }
@@ -1204,6 +1221,107 @@ __global__ void parse_sizes_kernel(const unsigned char *__restrict__ p, u64 off,
     return;
   dst[1] = tw;
   dst[2] = *(const u64 *)(p + o2 + 8 + 8 * tw);
+}
+
+// Launches the decoders for one serialised block.  OUT = uint16_t: symbols;
+// OUT = float / double: values dequantized with `scale` while a chunk is flushed.
+template <typename OUT>
+int launch_decoders(mgb_plan *p, const u64 *ddata, u64 total_words, const u64 *bits,
+                    const u64 *woff, u64 nchunk, int chunk, u64 n, const u64 *decodebook, int dict,
+                    OUT *out, OUT scale, cudaStream_t st) {
+  unsigned *sub = p->d_dec_sub;
+  const u64 subn = p->dec_sub_cap;
+  // fast path: chunks staged in shared memory.  First launch: 2 blocks of 512
+  // threads per SM, word buffer sized from the average chunk (+25 %); second
+  // launch (1 block per SM, the largest buffer that fits) for the chunks the
+  // first one left; whatever still does not fit goes to decode_kernel.
+  unsigned fast_bufw = 0, big_bufw = 0;
+  unsigned *cnt1 = (unsigned *)((u64 *)p->d_scalars + 15), *cnt2 = cnt1 + 1;
+  unsigned *list1 = sub + 3 * subn, *list2 = list1 + nchunk;
+  auto fast_smem = [&](unsigned bw, int nt) {
+    const unsigned nslot = (bw * 64 / DF_SB + 2 * nt + 3) & ~3u;
+    return 128 * 8 + (size_t)(1 << DEC_K) * 4 + ((size_t)bw + 2) * 8 + (size_t)nslot * 4 +
+           (size_t)nt * 4 + ((nslot + 15) & ~15u) + (((size_t)chunk * 2 + 15) & ~(size_t)15);
+  };
+  // largest word buffer whose launch fits `budget` bytes of shared memory
+  // (per word: 8 B data + 64/DF_SB x (4 B end slot + 1 B count))
+  auto max_words = [&](size_t budget, int nt) -> u64 {
+    const size_t fixed = fast_smem(0, nt) + 64;
+    return fixed >= budget ? 0 : (budget - fixed) / 10;
+  };
+  {
+    const u64 avg = total_words / nchunk + 1;
+    const u64 small_max = max_words(113 * 1024 - 512, DF_T);
+    const u64 big_max = max_words(200 * 1024, DF_TBIG);
+    u64 want = avg + avg / 4 + 256;
+    if (want > small_max && avg + avg / 16 + 32 <= small_max)
+      want = small_max;
+    if (want <= small_max)
+      fast_bufw = (unsigned)(want & ~(u64)1);
+    if (big_max > 64) {
+      big_bufw = (unsigned)(std::min<u64>(big_max, (u64)chunk * 56 / 64 + 2) & ~(u64)1);
+      if (big_bufw <= fast_bufw)
+        big_bufw = 0;
+    }
+  }
+  if (fast_bufw || big_bufw) {
+    static bool configured = false;
+    if (!configured) {
+      MGB_CUDA_CHECK(cudaFuncSetAttribute(decode_fast_kernel<DF_T, OUT>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 114 * 1024));
+      cudaFuncSetAttribute(decode_fast_kernel<DF_T, OUT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+      MGB_CUDA_CHECK(cudaFuncSetAttribute(decode_fast_kernel<DF_TBIG, OUT>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      cudaFuncSetAttribute(decode_fast_kernel<DF_TBIG, OUT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+      configured = true;
+    }
+    MGB_CUDA_CHECK(cudaMemsetAsync(cnt1, 0, 2 * sizeof(unsigned), st));
+  }
+  if (fast_bufw) {
+    unsigned fblocks = (unsigned)std::min<u64>(nchunk, 148 * 2);
+    MGB_LAUNCH(MGB_K_DECODE, st,
+               (decode_fast_kernel<DF_T, OUT><<<fblocks, DF_T, fast_smem(fast_bufw, DF_T), st>>>(
+                   ddata, bits, woff, nchunk, chunk, n, decodebook, dict, fast_bufw, nullptr, nullptr,
+                   cnt1, list1, out, scale)));
+  }
+  if (big_bufw) {
+    unsigned fblocks = (unsigned)std::min<u64>(nchunk, 148);
+    MGB_LAUNCH(MGB_K_DECODE, st,
+               (decode_fast_kernel<DF_TBIG, OUT><<<fblocks, DF_TBIG, fast_smem(big_bufw, DF_TBIG), st>>>(
+                   ddata, bits, woff, nchunk, chunk, n, decodebook, dict, big_bufw,
+                   fast_bufw ? cnt1 : nullptr, fast_bufw ? list1 : nullptr, cnt2, list2, out, scale)));
+  }
+  // what decode_kernel has to look at: the second list, else the first
+  unsigned *n_skipped = big_bufw ? cnt2 : cnt1;
+  unsigned *skip_list = big_bufw ? list2 : list1;
+  if (big_bufw)
+    fast_bufw = big_bufw;
+  size_t smem_tab = 128 * 8 + (size_t)(1 << DEC_K) * 4 + (size_t)((dict + 7) & ~7) * 2;
+  size_t smem_out = (size_t)chunk * 2 + 16;
+  unsigned blocks = (unsigned)std::min<u64>(nchunk, 148 * 8);
+  if (smem_tab + smem_out <= 160 * 1024) {
+    size_t smem = smem_tab + smem_out;
+    cudaFuncSetAttribute(decode_kernel<true, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    MGB_LAUNCH(MGB_K_DECODE, st,
+               (decode_kernel<true, OUT><<<blocks, DEC_T, smem, st>>>(
+                   ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict, sub,
+                   sub + subn, sub + 2 * subn, out, scale, n_skipped, skip_list, fast_bufw)));
+  } else {
+    if (sizeof(OUT) != 2)
+      return MGB_FAILURE; // the caller only fuses the dequantizer when chunks can be staged
+    cudaFuncSetAttribute(decode_kernel<false, uint16_t>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tab);
+    MGB_LAUNCH(MGB_K_DECODE, st,
+               (decode_kernel<false, uint16_t><<<blocks, DEC_T, smem_tab, st>>>(
+                   ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict, sub,
+                   sub + subn, sub + 2 * subn, reinterpret_cast<uint16_t *>(out), (uint16_t)0,
+                   n_skipped, skip_list, fast_bufw)));
+  }
+  MGB_CUDA_CHECK(cudaGetLastError());
+  return MGB_SUCCESS;
 }
 
 int ensure_huff_workspace(mgb_plan *p) {
@@ -1265,8 +1383,9 @@ extern "C" int mgb_codebook(mgb_plan *p, const uint32_t *d_hist, uint64_t *d_cod
                                         (int)smem_max));
     configured = true;
   }
+  static const int cb_threads = getenv("MGB_CB_THREADS") ? atoi(getenv("MGB_CB_THREADS")) : 1024;
   MGB_LAUNCH(MGB_K_CODEBOOK, (cudaStream_t)stream,
-             (codebook_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(
+             (codebook_kernel<<<1, cb_threads, smem, (cudaStream_t)stream>>>(
                  d_hist, dict, npow2, w, (u64 *)d_codebook, (u64 *)d_decodebook,
                  (int *)(p->d_scalars + 8), key_smem, ncap)));
   MGB_CUDA_CHECK(cudaGetLastError());
@@ -1358,10 +1477,14 @@ extern "C" int mgb_huffman_compress(mgb_plan *p, const uint16_t *d_sym, uint64_t
   return mgb_huffman_finish(p, size, st);
 }
 
-extern "C" int mgb_huffman_decompress(mgb_plan *p, const uint8_t *d_in, uint64_t size,
-                                      uint16_t *d_sym, uint64_t n, uint64_t *ocount,
-                                      const uint64_t **d_oidx, const int64_t **d_oval,
-                                      void *stream) {
+// d_deq != nullptr: write values dequantized with deq_scale to d_deq instead of
+// symbols to d_sym when possible (*fused = 1 then).
+int mgb_huffman_decompress_impl(mgb_plan *p, const uint8_t *d_in, uint64_t size,
+                                uint16_t *d_sym, uint64_t n, uint64_t *ocount,
+                                const uint64_t **d_oidx, const int64_t **d_oval, void *stream,
+                                void *d_deq, double deq_scale, int *fused) {
+  if (fused)
+    *fused = 0;
   if (!p || !d_in || !d_sym || size < 32)
     return MGB_BAD_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1423,94 +1546,26 @@ extern "C" int mgb_huffman_decompress(mgb_plan *p, const uint8_t *d_in, uint64_t
       p->dec_sub_cap = need;
     }
   }
-  unsigned *sub = p->d_dec_sub;
-  const u64 subn = p->dec_sub_cap;
-  // fast path: chunks staged in shared memory.  First launch: 2 blocks of 512
-  // threads per SM, word buffer sized from the average chunk (+25 %); second
-  // launch (1 block per SM, the largest buffer that fits) for the chunks the
-  // first one left; whatever still does not fit goes to decode_kernel.
-  unsigned fast_bufw = 0, big_bufw = 0;
-  unsigned *cnt1 = (unsigned *)((u64 *)p->d_scalars + 15), *cnt2 = cnt1 + 1;
-  unsigned *list1 = sub + 3 * subn, *list2 = list1 + nchunk;
-  auto fast_smem = [&](unsigned bw, int nt) {
-    const unsigned nslot = (bw * 64 / DF_SB + 2 * nt + 3) & ~3u;
-    return 128 * 8 + (size_t)(1 << DEC_K) * 4 + ((size_t)bw + 2) * 8 + (size_t)nslot * 4 +
-           (size_t)nt * 4 + ((nslot + 15) & ~15u) + (((size_t)chunk * 2 + 15) & ~(size_t)15);
-  };
-  // largest word buffer whose launch fits `budget` bytes of shared memory
-  // (per word: 8 B data + 64/DF_SB x (4 B end slot + 1 B count))
-  auto max_words = [&](size_t budget, int nt) -> u64 {
-    const size_t fixed = fast_smem(0, nt) + 64;
-    return fixed >= budget ? 0 : (budget - fixed) / 10;
-  };
-  {
-    const u64 avg = total_words / nchunk + 1;
-    const u64 small_max = max_words(113 * 1024 - 512, DF_T);
-    const u64 big_max = max_words(200 * 1024, DF_TBIG);
-    u64 want = avg + avg / 4 + 256;
-    if (want > small_max && avg + avg / 16 + 32 <= small_max)
-      want = small_max;
-    if (want <= small_max)
-      fast_bufw = (unsigned)(want & ~(u64)1);
-    if (big_max > 64) {
-      big_bufw = (unsigned)(std::min<u64>(big_max, (u64)chunk * 56 / 64 + 2) & ~(u64)1);
-      if (big_bufw <= fast_bufw)
-        big_bufw = 0;
-    }
+  // dequantize while flushing (s = inf) when the chunks can be staged in shared memory
+  const bool can_stage = 128 * 8 + (size_t)(1 << DEC_K) * 4 + (size_t)((dict + 7) & ~7) * 2 +
+                             (size_t)chunk * 2 + 16 <= 160 * 1024;
+  if (d_deq && can_stage) {
+    if (fused)
+      *fused = 1;
+    if (p->dtype == MGB_F32)
+      return launch_decoders<float>(p, ddata, total_words, bits, woff, nchunk, chunk, n, decodebook,
+                                    dict, (float *)d_deq, (float)deq_scale, st);
+    return launch_decoders<double>(p, ddata, total_words, bits, woff, nchunk, chunk, n, decodebook,
+                                   dict, (double *)d_deq, deq_scale, st);
   }
-  if (fast_bufw || big_bufw) {
-    static bool configured = false;
-    if (!configured) {
-      MGB_CUDA_CHECK(cudaFuncSetAttribute(decode_fast_kernel<DF_T>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 114 * 1024));
-      cudaFuncSetAttribute(decode_fast_kernel<DF_T>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                           cudaSharedmemCarveoutMaxShared);
-      MGB_CUDA_CHECK(cudaFuncSetAttribute(decode_fast_kernel<DF_TBIG>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      cudaFuncSetAttribute(decode_fast_kernel<DF_TBIG>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                           cudaSharedmemCarveoutMaxShared);
-      configured = true;
-    }
-    MGB_CUDA_CHECK(cudaMemsetAsync(cnt1, 0, 2 * sizeof(unsigned), st));
-  }
-  if (fast_bufw) {
-    unsigned fblocks = (unsigned)std::min<u64>(nchunk, 148 * 2);
-    MGB_LAUNCH(MGB_K_DECODE, st,
-               (decode_fast_kernel<DF_T><<<fblocks, DF_T, fast_smem(fast_bufw, DF_T), st>>>(
-                   ddata, bits, woff, nchunk, chunk, n, decodebook, dict, fast_bufw, nullptr, nullptr,
-                   cnt1, list1, d_sym)));
-  }
-  if (big_bufw) {
-    unsigned fblocks = (unsigned)std::min<u64>(nchunk, 148);
-    MGB_LAUNCH(MGB_K_DECODE, st,
-               (decode_fast_kernel<DF_TBIG><<<fblocks, DF_TBIG, fast_smem(big_bufw, DF_TBIG), st>>>(
-                   ddata, bits, woff, nchunk, chunk, n, decodebook, dict, big_bufw,
-                   fast_bufw ? cnt1 : nullptr, fast_bufw ? list1 : nullptr, cnt2, list2, d_sym)));
-  }
-  // what decode_kernel has to look at: the second list, else the first
-  unsigned *n_skipped = big_bufw ? cnt2 : cnt1;
-  unsigned *skip_list = big_bufw ? list2 : list1;
-  if (big_bufw)
-    fast_bufw = big_bufw;
-  size_t smem_tab = 128 * 8 + (size_t)(1 << DEC_K) * 4 + (size_t)((dict + 7) & ~7) * 2;
-  size_t smem_out = (size_t)chunk * 2 + 16;
-  unsigned blocks = (unsigned)std::min<u64>(nchunk, 148 * 8);
-  if (smem_tab + smem_out <= 160 * 1024) {
-    size_t smem = smem_tab + smem_out;
-    cudaFuncSetAttribute(decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem);
-    MGB_LAUNCH(MGB_K_DECODE, st,
-               (decode_kernel<true><<<blocks, DEC_T, smem, st>>>(
-                   ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict, sub,
-                   sub + subn, sub + 2 * subn, d_sym, n_skipped, skip_list, fast_bufw)));
-  } else {
-    cudaFuncSetAttribute(decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem_tab);
-    MGB_LAUNCH(MGB_K_DECODE, st,
-               (decode_kernel<false><<<blocks, DEC_T, smem_tab, st>>>(
-                   ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict, sub,
-                   sub + subn, sub + 2 * subn, d_sym, n_skipped, skip_list, fast_bufw)));
-  }
-  MGB_CUDA_CHECK(cudaGetLastError());
-  return MGB_SUCCESS;
+  return launch_decoders<uint16_t>(p, ddata, total_words, bits, woff, nchunk, chunk, n, decodebook,
+                                   dict, d_sym, (uint16_t)0, st);
+}
+
+extern "C" int mgb_huffman_decompress(mgb_plan *p, const uint8_t *d_in, uint64_t size,
+                                      uint16_t *d_sym, uint64_t n, uint64_t *ocount,
+                                      const uint64_t **d_oidx, const int64_t **d_oval,
+                                      void *stream) {
+  return mgb_huffman_decompress_impl(p, d_in, size, d_sym, n, ocount, d_oidx, d_oval, stream,
+                                     nullptr, 0.0, nullptr);
 }

@@ -555,11 +555,14 @@ int quantize_t(mgb_plan *p, const T *d_coef, int ebtype, double tol, double s,
 template <typename T>
 int dequantize_t(mgb_plan *p, const uint16_t *d_sym, uint64_t ocount,
                  const uint64_t *d_oidx, const int64_t *d_oval, int ebtype,
-                 double tol, double s, double norm, T *d_coef, cudaStream_t st) {
+                 double tol, double s, double norm, T *d_coef, cudaStream_t st,
+                 bool outliers_only = false) {
   QParams qp;
   Tables<T> tb;
   make_params<T>(p, ebtype, tol, s, norm, true, qp, tb);
-  if (!qp.calc_level) {
+  if (outliers_only) {
+    // the decoder already wrote (quantizer * volume) * (T)quantized
+  } else if (!qp.calc_level) {
     unsigned blocks = (unsigned)std::min<i64>((p->N + 2047) / 2048, 148 * 8);
     MGB_LAUNCH(MGB_K_DEQUANTIZE, st,
                (dequantize_linear_kernel<T><<<blocks, 256, 0, st>>>(
@@ -666,4 +669,37 @@ extern "C" int mgb_norm(mgb_plan *plan, const void *d_in, double s, double *norm
   }
   *norm = r;
   return MGB_SUCCESS;
+}
+
+// s = inf: the dequantizer is one scalar for every node, so the Huffman decoder
+// can apply it while it flushes a chunk (no symbol array, no dequantize pass).
+// Returns 1 and the factor (quantizer * volume, evaluated in T) if so.
+int mgb_linear_dequant_scale(mgb_plan *plan, int ebtype, double tol, double s, double norm,
+                             double *scale) {
+  if (!(std::isinf(s) && s > 0))
+    return 0;
+  if (plan->dtype == MGB_F32) {
+    QParams qp;
+    Tables<float> tb;
+    make_params<float>(plan, ebtype, tol, s, norm, true, qp, tb);
+    *scale = (double)(tb.q[0] * tb.vol[0]);
+  } else {
+    QParams qp;
+    Tables<double> tb;
+    make_params<double>(plan, ebtype, tol, s, norm, true, qp, tb);
+    *scale = tb.q[0] * tb.vol[0];
+  }
+  return 1;
+}
+
+int mgb_outlier_restore(mgb_plan *plan, uint64_t ocount, const uint64_t *d_oidx,
+                        const int64_t *d_oval, int ebtype, double tol, double s, double norm,
+                        void *d_coef, cudaStream_t st) {
+  if (!ocount)
+    return MGB_SUCCESS;
+  if (plan->dtype == MGB_F32)
+    return dequantize_t<float>(plan, nullptr, ocount, d_oidx, d_oval, ebtype, tol, s, norm,
+                               (float *)d_coef, st, true);
+  return dequantize_t<double>(plan, nullptr, ocount, d_oidx, d_oval, ebtype, tol, s, norm,
+                              (double *)d_coef, st, true);
 }

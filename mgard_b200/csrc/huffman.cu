@@ -483,13 +483,14 @@ chunk_scan_kernel(const u64 *__restrict__ bits, u64 nchunk, u64 *__restrict__ wo
 // shared-memory image: words it fills completely are stored, the (at most two)
 // words it shares with its neighbours are OR-ed in atomically.  Full words of
 // the tile are then flushed, coalesced, to their FINAL place in the stream.
+constexpr int ENC_PER = 16; // symbols per thread and tile (two 128-bit loads)
 template <bool CB_SHARED>
 __global__ void __launch_bounds__(256)
 encode_kernel(const uint16_t *__restrict__ sym, u64 n, int chunk,
               const u64 *__restrict__ codebook, int dict,
               const u64 *__restrict__ woff, const u64 *__restrict__ scal,
               u64 *__restrict__ ddata) {
-  constexpr int PER = 8, NT = 256, TILE = PER * NT;
+  constexpr int PER = ENC_PER, NT = 256, TILE = PER * NT;
   constexpr int TILE_WORDS = TILE * 56 / 64 + 4;
   extern __shared__ u64 smem[];
   u64 *s_cb = smem;                         // dict (if CB_SHARED)
@@ -518,8 +519,11 @@ encode_kernel(const uint16_t *__restrict__ sym, u64 n, int chunk,
       u64 cw[PER];
       unsigned mybits = 0;
       if (s0 + PER <= hi && ((((uintptr_t)(sym + s0)) & 15) == 0)) {
-        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(sym + s0));
-        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+        uint4 v[PER / 8];
+#pragma unroll
+        for (int q = 0; q < PER / 8; q++)
+          v[q] = __ldcs(reinterpret_cast<const uint4 *>(sym + s0) + q);
+        const unsigned *w = reinterpret_cast<const unsigned *>(v);
 #pragma unroll
         for (int k = 0; k < PER; k++)
           cw[k] = cbv((w[k >> 1] >> (16 * (k & 1))) & 0xffffu);
@@ -1420,7 +1424,7 @@ int mgb_huffman_compress_async(mgb_plan *p, const uint16_t *d_sym, uint64_t n,
                                                    (const u64 *)d_ocount_ptr, ocount_fixed,
                                                    d_ocount_ptr ? p->outlier_cap : ~0ull)));
   u64 *ddata = (u64 *)(d_out + fixed);
-  constexpr int TILE_WORDS = 8 * 256 * 56 / 64 + 4;
+  constexpr int TILE_WORDS = ENC_PER * 256 * 56 / 64 + 4;
   // the codebook is read through L1 (measured faster than a shared-memory copy,
   // which limits the kernel to two blocks per SM); MGB_ENC_SHARED_CB=1 for A/B runs
   static const bool enc_shared = getenv("MGB_ENC_SHARED_CB") != nullptr;

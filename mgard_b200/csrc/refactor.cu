@@ -702,6 +702,56 @@ thomas_smem_kernel(T *__restrict__ x, int n, i64 inner, i64 lines,
   }
 }
 
+// All solves of a small correction in ONE launch: when the whole coarse array
+// fits in shared memory a single thread block loads it, runs the Thomas solves
+// along every dimension (fastest first, one thread per line, a barrier between
+// dimensions) and adds / subtracts the result to / from the coarse nodes.  The
+// levels this applies to are latency bound, so one launch instead of D (+ the
+// traffic between them) is what counts.
+struct SmallSolve {
+  int D;
+  int n[5];            // coarse shape
+  const void *fw[5], *am[5], *bm[5];
+};
+template <typename T>
+__global__ void __launch_bounds__(1024)
+thomas_small_kernel(const SmallSolve g, const T *__restrict__ w, T *__restrict__ acc, int mode,
+                    int total) {
+  extern __shared__ __align__(16) unsigned char small_smem[];
+  T *s = reinterpret_cast<T *>(small_smem);
+  for (int i = threadIdx.x; i < total; i += blockDim.x)
+    s[i] = w[i];
+  __syncthreads();
+  int inner = 1;
+  for (int a = g.D - 1; a >= 0; a--) {
+    const int n = g.n[a];
+    const int lines = total / n;
+    const T *__restrict__ fw = (const T *)g.fw[a];
+    const T *__restrict__ am = (const T *)g.am[a];
+    const T *__restrict__ bm = (const T *)g.bm[a];
+    for (int line = threadIdx.x; line < lines; line += blockDim.x) {
+      const int o = line / inner, in = line - o * inner;
+      T *p = s + (size_t)o * n * inner + in;
+      T prev = (T)0;
+      for (int i = 0; i < n; i++) {
+        prev = p[i * inner] - prev * __ldg(fw + i);
+        p[i * inner] = prev;
+      }
+      prev = (T)0;
+      for (int i = n - 1; i >= 0; i--) {
+        prev = (p[i * inner] - __ldg(am + i + 1) * prev) / __ldg(bm + i + 1);
+        p[i * inner] = prev;
+      }
+    }
+    inner *= n;
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const T r = s[i];
+    acc[i] = mode == 1 ? acc[i] + r : acc[i] - r;
+  }
+}
+
 // acc[i] += sign * w[i] on dense arrays (AddND / SubtractND)
 template <typename T>
 __global__ void axpy_kernel(T *__restrict__ acc, const T *__restrict__ w, i64 n, int subtract) {
@@ -969,6 +1019,32 @@ void launch_restore3d(mgb_plan *p, int l, const T *coarse, const T *coef, T *out
 template <typename T>
 void thomas_all(mgb_plan *p, int l, T *w, T *acc, int mode, cudaStream_t st) {
   const int D = p->D;
+  // small correction: every solve and the final add / subtract in one launch
+  {
+    const uint64_t total = mgb_level_elems(p, l - 1);
+    const size_t smem = total * sizeof(T);
+    if (acc && smem <= 200 * 1024) {
+      SmallSolve g;
+      g.D = D;
+      for (int d = 0; d < D; d++) {
+        const mgb_dim_tables &m = p->tab[l - 1][d];
+        g.n[d] = (int)p->lshape[l - 1][d];
+        g.fw[d] = p->dtab(m.fw);
+        g.am[d] = p->dtab(m.am);
+        g.bm[d] = p->dtab(m.bm);
+      }
+      static bool configured = false;
+      if (!configured) {
+        cudaFuncSetAttribute(thomas_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             200 * 1024);
+        configured = true;
+      }
+      int threads = 1024;
+      MGB_LAUNCH(MGB_K_THOMAS_CONTIG, st,
+                 (thomas_small_kernel<T><<<1, threads, smem, st>>>(g, w, acc, mode, (int)total)));
+      return;
+    }
+  }
   const size_t smem_max = 227 * 1024, smem_sm = 228 * 1024 - 1024;
   for (int a = D - 1; a >= 0; a--) {
     const mgb_dim_tables &m = p->tab[l - 1][a];

@@ -364,21 +364,42 @@ def main():
             k += 1
         fam.sort(key=lambda f: -f["ms_per_step"])
         line["kernel_breakdown"] = fam
-        # algorithmic bytes of the largest launch of each family (finest level), fp32:
+        # algorithmic bytes of the largest launch of each family (finest level), fp32
+        # (DESIGN.md section 4):
         nl = N
         cs = (SHAPE[0] // 2 + 1) * (SHAPE[1] // 2 + 1) * (SHAPE[2] // 2 + 1)
         alg = {
             "coef": 2 * nl * 4,                    # read the level box, write coefficients + coarse
-            "restore": 2 * nl * 4,
+            "restore": 2 * nl * 4 + cs * 4,        # read coefficients + coarse, write the level box
             "mass_trans": (nl + cs) * 4,           # fused f/c/r pass: read n, write n/8
             "quantize_hist": nl * 4 + nl * 2,      # read T, write u16 symbols
-            "dequantize": nl * 2 + nl * 4,
             "encode": nl * 2 + total_stream / world,
             "chunk_bits": nl * 2,
-            "decode": total_stream / world + nl * 2,
+            "decode": total_stream / world + nl * 4,   # s=inf: dequantized while flushing
             "thomas_contig": 2 * cs * 4, "thomas_strided": 2 * cs * 4,
-            "axpy": 3 * cs * 4, "norm": nl * 4,
+            "norm": nl * 4,
         }
+        # DRAM bytes per launch measured by ncu --set full on the same workload
+        # (profiles/r1_ncu_traffic.json, produced by scripts/make_profiles.py)
+        ncu = {}
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+        except Exception:
+            pass
+
+        def traffic_of(k):
+            t = ncu.get(k)
+            return (t["dram_read_bytes"] + t["dram_write_bytes"]) if t else None
+
+        per_kernel = []
+        for f in fam:
+            a = alg.get(f["kernel"])
+            if a:
+                ach = a / (f["max_launch_ms"] * 1e-3) / 1e9
+                per_kernel.append({"kernel": f["kernel"], "achieved": ach, "frac": ach / peak,
+                                   "algorithmic_bytes": a, "traffic": traffic_of(f["kernel"]),
+                                   "launch_ms": f["max_launch_ms"]})
+        line["roofline_kernels"] = per_kernel
         if fam:
             top = fam[0]
             a = alg.get(top["kernel"])
@@ -386,8 +407,16 @@ def main():
                 achieved = a / (top["max_launch_ms"] * 1e-3) / 1e9
                 line["roofline"] = {"bound": "hbm", "kernel": top["kernel"], "achieved": achieved,
                                     "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                                    "traffic": None, "peak_source": peak_src,
-                                    "note": "largest (finest-level) launch of the family: algorithmic bytes / CUDA-event duration"}
+                                    "traffic": traffic_of(top["kernel"]), "peak_source": peak_src,
+                                    "note": "largest (finest-level) launch of the dominant family: algorithmic bytes / "
+                                            "CUDA-event duration; traffic = dram read+write bytes of that launch from "
+                                            "ncu --set full (profiles/r1_ncu_traffic.json)"}
+        # time-weighted DRAM efficiency over the finest-level launches:
+        # sum of ncu DRAM bytes / sum of live launch durations / peak
+        tb = sum(k["traffic"] for k in per_kernel if k["traffic"])
+        tt = sum(k["launch_ms"] for k in per_kernel if k["traffic"]) * 1e-3
+        if tt > 0:
+            line["roofline"]["dram_efficiency"] = tb / tt / 1e9 / peak
         # whole-codec view on the B_alg basis of SURVEY §8d
         line["roofline_codec"] = {
             "compress_frac": (nbytes + total_stream / world) / (tc * 1e-3) / 1e9 / peak,

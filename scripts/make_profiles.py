@@ -1,0 +1,56 @@
+"""Builds profiles/r1_ncu_kernels.md and profiles/r1_ncu_traffic.json from the
+`ncu --set full` captures of the finest-level launches (gpurun_out/r1_final_*.ncu-rep)."""
+import csv, io, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPS = ["r1_final_levels", "r1_final_huff", "r1_final_restore"]
+FAM = [("norm_partial", "norm"), ("coef3d", "coef"), ("masstrans3d", "mass_trans"), ("thomas_smem", "thomas_contig"),
+       ("thomas_strided", "thomas_strided"), ("restore3d", "restore"), ("quantize_linear", "quantize_hist"),
+       ("codebook", "codebook"), ("chunk_bits", "chunk_bits"), ("encode_kernel", "encode"), ("decode_fast", "decode")]
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "smsp__inst_executed.sum",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+def to_bytes(v, unit):
+    f = float(v.replace(",", ""))
+    return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+def to_us(v, unit):
+    f = float(v.replace(",", ""))
+    return f * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}[unit]
+traffic, md = {}, ["# r1: `ncu --set full --clock-control none` of the finest-level launch of every kernel family",
+                   "", "513^3 fp32 bench field (scripts/prof_one.py); one launch per family; durations under ncu are cold-cache.", ""]
+for rep in REPS:
+    path = os.path.join(ROOT, "gpurun_out", rep + ".ncu-rep")
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    h, units = rows[0], rows[1]
+    seen = set()
+    for r in rows[2:]:
+        d = dict(zip(h, r)); u = dict(zip(h, units))
+        fam = next((f for k, f in FAM if k in d["Kernel Name"]), None)
+        if fam is None or fam in seen:
+            continue
+        seen.add(fam)
+        rd = to_bytes(d["dram__bytes_read.sum"], u["dram__bytes_read.sum"])
+        wr = to_bytes(d["dram__bytes_write.sum"], u["dram__bytes_write.sum"])
+        us = to_us(d["gpu__time_duration.sum"], u["gpu__time_duration.sum"])
+        traffic[fam] = {"kernel": d["Kernel Name"][:80], "grid": d.get("Grid Size"), "block": d.get("Block Size"),
+                        "dram_read_bytes": rd, "dram_write_bytes": wr, "ncu_duration_us": us,
+                        "dram_gbs_under_ncu": (rd + wr) / us / 1e3,
+                        "issue_active_pct": float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
+                        "registers": int(d["launch__registers_per_thread"]), "source": rep + ".ncu-rep"}
+        md.append(f"## {fam}: `{d['Kernel Name'][:100]}`  grid {d.get('Grid Size')} block {d.get('Block Size')}\n")
+        md.append("| metric | value | unit |\n|---|---:|---|")
+        for k in KEYS:
+            if k in d and d[k] != "":
+                md.append(f"| {k} | {d[k]} | {u[k]} |")
+        md.append("")
+json.dump(traffic, open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json"), "w"), indent=1)
+open(os.path.join(ROOT, "profiles", "r1_ncu_kernels.md"), "w").write("\n".join(md) + "\n")
+for f, t in traffic.items():
+    print(f"{f:16s} {t['ncu_duration_us']:9.1f} us  dram {(t['dram_read_bytes']+t['dram_write_bytes'])/1e6:8.1f} MB  {t['dram_gbs_under_ncu']:7.0f} GB/s  issue {t['issue_active_pct']:5.1f}%  regs {t['registers']}")

@@ -322,3 +322,67 @@ def test_cxx_api_mirror_compiles_and_round_trips(env, tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "compress status 0" in out.stdout and "decompress status 0" in out.stdout
+
+
+def _huff_roundtrip(torch, mg, d, sym, dict_size, block, oracle=True):
+    """encode + decode of a symbol stream through the stage API; optionally the
+    payload against the oracle's."""
+    cfg = mg.Config()
+    cfg.huff_dict_size, cfg.huff_block_size = dict_size, block
+    p = mg.Plan((sym.size,), np.float32, config=cfg)
+    ds = torch.from_numpy(sym.astype(np.uint16).view(np.int16)).to(d)
+    hist = torch.from_numpy(np.bincount(sym, minlength=dict_size).astype(np.uint32).view(np.int32)).to(d)
+    e = torch.empty(0, dtype=torch.int64, device=d)
+    pay = p.huffman_compress(ds, hist, e, e)
+    if oracle:
+        ref = mo.huffman_compress(sym.astype(np.int64), dict_size, block, (), ())
+        assert pay.cpu().numpy().tobytes() == ref
+    back, _, _ = p.huffman_decompress(pay, sym.size)
+    assert np.array_equal(back.cpu().numpy().view(np.uint16), sym.astype(np.uint16))
+    return pay.numel()
+
+
+def test_decoder_paths(env):
+    """The three decoders: chunks staged by the 512-thread launch, chunks that only
+    fit the 1024-thread big-buffer launch (mixed entropy: long chunks are far above
+    the average the first launch is sized for), and the global-memory decoder
+    (block size too large to stage a chunk in shared memory)."""
+    torch, mg, d = env
+    rng = np.random.default_rng(5)
+    # (a) mixed entropy: 40 chunks of one repeated symbol, 8 chunks of ~13 bits/symbol
+    block = 20480
+    quiet = np.full(40 * block, 4096, dtype=np.int64)
+    loud = rng.integers(0, 8192, 8 * block)
+    sym = np.concatenate([quiet[: 20 * block], loud[: 3 * block], quiet[20 * block:], loud[3 * block:]])
+    _huff_roundtrip(torch, mg, d, sym, 8192, block, oracle=False)
+    # (b) small case of the same kind, bytes against the oracle
+    sym = np.concatenate([np.full(3000, 7), rng.integers(0, 64, 2000), np.full(3000, 9), rng.integers(0, 64, 500)])
+    _huff_roundtrip(torch, mg, d, sym, 64, 1000)
+    # (c) one chunk larger than any shared-memory staging -> decode_kernel, unstaged output
+    sym = np.clip(np.rint(rng.standard_normal(300000) * 40 + 2048), 0, 4095).astype(np.int64)
+    _huff_roundtrip(torch, mg, d, sym, 4096, 250000, oracle=False)
+    # (d) skewed code with long codewords (Fibonacci-like counts -> lengths up to ~30 bits)
+    counts = [1, 1]
+    while len(counts) < 30:
+        counts.append(counts[-1] + counts[-2])
+    sym = rng.permutation(np.repeat(np.arange(30), np.minimum(counts, 200000)))
+    _huff_roundtrip(torch, mg, d, sym, 32, 4096)
+
+
+def test_fused_dequantization_matches_separate_stages(env):
+    """Compressor::Decompress with s = inf dequantizes inside the decoder's flush;
+    the result must equal decode -> dequantize -> recompose run as separate stages."""
+    torch, mg, d = env
+    u = field((40, 37, 50), np.float32, 3)
+    u[3, 4, 5] = 80.0  # a few outliers
+    u[30, 1, 7] = -95.0
+    p = mg.Plan(u.shape, np.float32)
+    du = dev(torch, u, d)
+    payload, norm = p.compress(du, mo.REL, 1e-4, np.inf)
+    fused = p.decompress(payload, mo.REL, 1e-4, np.inf, norm).cpu().numpy()
+    sym, oidx, oval = p.huffman_decompress(payload, u.size)
+    assert oidx.numel() > 0
+    coef = p.dequantize(sym, oidx, oval, mo.REL, 1e-4, np.inf, norm)
+    staged = p.recompose(coef.reshape(u.shape)).cpu().numpy()
+    assert np.array_equal(fused, staged)
+    assert np.abs(fused - u).max() <= 1e-4 * np.abs(u).max()

@@ -376,6 +376,12 @@ extern "C" void mgb_plan_destroy(mgb_plan *p) {
   cudaFree(p->d_cbuf);
   cudaFree(p->d_wA);
   cudaFree(p->d_wB);
+  if (p->side)
+    cudaStreamDestroy(p->side);
+  if (p->ev_fork)
+    cudaEventDestroy(p->ev_fork);
+  if (p->ev_join)
+    cudaEventDestroy(p->ev_join);
   cudaFree(p->d_sym);
   cudaFree(p->d_hist);
   cudaFree(p->d_codebook);

@@ -73,6 +73,10 @@ struct mgb_plan {
   unsigned *d_dec_sub = nullptr;       // decoder sub-sequence bookkeeping
   uint64_t dec_sub_cap = 0;
   unsigned long long *h_pinned = nullptr; // pinned host scalars
+  // side stream + events: work that does not depend on the level recursion runs
+  // next to the latency-bound small levels (refactor.cu: recompose_t)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   const unsigned char *dtab(uint64_t off) const { return d_tables + off * tsize; }
 };

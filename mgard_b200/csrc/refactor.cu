@@ -1198,13 +1198,39 @@ int recompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
                (box_copy_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
                    g, d_in, cbuf + p->cbuf_off[0], total)));
   }
+  // The load vector of a level depends only on the coefficients, not on the level
+  // recursion: the finest level's (throughput bound, most of the work) runs on
+  // the caller's stream while the latency-bound chain of the coarse levels runs
+  // next to it on a high-priority side stream.
+  const bool fork = D == 3 && !p->force_generic && p->L >= 2;
+  cudaStream_t sc = st; // stream of the coarse-level chain
+  if (fork) {
+    if (!p->side) {
+      int least = 0, greatest = 0;
+      cudaDeviceGetStreamPriorityRange(&least, &greatest);
+      MGB_CUDA_CHECK(cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, greatest));
+      MGB_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+      MGB_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    }
+    sc = p->side;
+    MGB_CUDA_CHECK(cudaEventRecord(p->ev_fork, st));
+    MGB_CUDA_CHECK(cudaStreamWaitEvent(sc, p->ev_fork, 0));
+    launch_masstrans3d<T>(p, p->L, d_in, (T *)p->d_wA, st);
+  }
   for (int l = 1; l <= p->L; l++) {
     T *coarse = cbuf + p->cbuf_off[l - 1];
     T *w = nullptr;
+    cudaStream_t sl = (fork && l < p->L) ? sc : st;
     if (D == 3 && !p->force_generic) {
-      w = (T *)p->d_wA;
-      launch_masstrans3d<T>(p, l, d_in, w, st);
-      thomas_all<T>(p, l, w, coarse, 2, st);
+      if (fork && l == p->L) {
+        w = (T *)p->d_wA;
+        MGB_CUDA_CHECK(cudaEventRecord(p->ev_join, sc));
+        MGB_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_join, 0));
+      } else {
+        w = (T *)(fork ? p->d_wB : p->d_wA);
+        launch_masstrans3d<T>(p, l, d_in, w, sl);
+      }
+      thomas_all<T>(p, l, w, coarse, 2, sl);
     } else {
       rc = correction<T>(p, l, d_in, &w, coarse, 2, st);
     }
@@ -1226,7 +1252,7 @@ int recompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
     fill_tables<T>(p, l, g, false);
     T *dst = l == p->L ? d_out : cbuf + p->cbuf_off[l];
     if (D == 3 && !p->force_generic) {
-      launch_restore3d<T>(p, l, coarse, d_in, dst, st);
+      launch_restore3d<T>(p, l, coarse, d_in, dst, sl);
       continue;
     }
     switch (D) {

@@ -39,8 +39,9 @@ struct CbWork {
   u64 *cw; // codewords in ascending-length order
 };
 
+// a mod n for -n < a < 2n (every use below: sums / differences of ring indices)
 __device__ __forceinline__ int modn(int a, int n) {
-  int r = a % n;
+  int r = a >= n ? a - n : a;
   return r < 0 ? r + n : r;
 }
 

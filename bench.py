@@ -34,6 +34,7 @@ METRIC = "compress/decompress GB/s at 1/2/4/8 B200 vs HBM roofline; ratio at bou
 SHAPE = (513, 513, 513)
 TOL, S = 1e-3, float("inf")
 SEED = 2049
+_REAL_STDOUT = None  # saved stdout fd when N > 1 (see main)
 
 
 def measured_peaks():
@@ -242,9 +243,13 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL's debug output (the version banner
-        # at NCCL_DEBUG >= VERSION) goes to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # keep stdout to the one JSON line: whatever NCCL / torch print while the
+        # communicator comes up (e.g. the version banner at NCCL_DEBUG >= VERSION) is
+        # sent to stderr; the JSON line is written to the saved stdout at the end
+        sys.stdout.flush()
+        global _REAL_STDOUT
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
     K = args.steps
@@ -497,7 +502,11 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_size)
     if rank == 0:
-        print(json.dumps(line))
+        if _REAL_STDOUT is not None:
+            sys.stdout.flush()
+            os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0

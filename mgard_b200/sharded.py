@@ -120,6 +120,9 @@ def compress_sharded(local, global_shape, tol, s, mode, decomposition_size, conf
                 first=first, count=count)
 
 
+_PARTIAL_PLANS = {}
+
+
 def _cuda_backend(config):
     """Local work through the C ABI (mgb_norm_partials / mgb_compress_subdomains /
     mgb_write_header)."""
@@ -136,8 +139,13 @@ def _cuda_backend(config):
         return c
 
     def partials(local):
-        p = Plan(tuple(local.shape), np.float32 if local.dtype == torch.float32 else np.float64,
-                 config=cfg_py)
+        # the plan only carries the reduction scratch here; keep it across calls
+        key = (tuple(local.shape), str(local.dtype), local.device.index)
+        p = _PARTIAL_PLANS.get(key)
+        if p is None:
+            p = Plan(tuple(local.shape), np.float32 if local.dtype == torch.float32 else np.float64,
+                     config=cfg_py)
+            _PARTIAL_PLANS[key] = p
         mx, ss = C.c_double(0), C.c_double(0)
         torch.cuda.current_stream().synchronize()
         _lib.check(L.mgb_norm_partials(p._h, local.data_ptr(), C.byref(mx), C.byref(ss)),

@@ -432,15 +432,24 @@ int compress_records(int ndim, int dtype, const uint64_t *shape, const Partition
     }
     uint64_t pcap = raw_bytes + 2 * (1024 + 8ull * cfg->huff_dict_size) +
                     32 * ((nsub - 1) / cfg->huff_block_size + 1) + 4096;
-    rc = ensure_bytes(&g_cache.d_payload, &g_cache.payload_bytes, pcap);
-    if (rc)
-      return rc;
+    // device output whose payload position is 8-byte aligned: compress straight
+    // into the record (no staging copy); otherwise through an aligned buffer
+    unsigned char *direct = nullptr;
+    if (out_on_device && *offset + 8 <= cap && (((uintptr_t)(out + *offset + 8)) & 7) == 0)
+      direct = out + *offset + 8;
+    if (!direct) {
+      rc = ensure_bytes(&g_cache.d_payload, &g_cache.payload_bytes, pcap);
+      if (rc)
+        return rc;
+    }
     uint64_t psize = 0;
     rc = mgb_compress_lowlevel(plan, d_in, local_eb, local_tol, s, norm,
-                               g_cache.d_payload, pcap, &psize, st);
+                               direct ? direct : g_cache.d_payload,
+                               direct ? std::min<uint64_t>(pcap, cap - *offset - 8) : pcap, &psize,
+                               st);
     if (owned)
       mgb_plan_destroy(plan);
-    const void *payload = g_cache.d_payload;
+    const void *payload = direct ? direct : g_cache.d_payload;
     if (rc == MGB_OUTPUT_TOO_LARGE || (rc == MGB_SUCCESS && psize >= raw_bytes)) {
       // GPUPipelines.hpp:139-155: store the sub-domain uncompressed
       payload = d_in;
@@ -459,8 +468,10 @@ int compress_records(int ndim, int dtype, const uint64_t *shape, const Partition
     } else {
       memcpy(out + *offset, &sz, 8);
     }
-    MGB_CUDA_CHECK(cudaMemcpyAsync(out + *offset + 8, payload, psize, cudaMemcpyDefault, st));
-    MGB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (payload != (const void *)(out + *offset + 8)) {
+      MGB_CUDA_CHECK(cudaMemcpyAsync(out + *offset + 8, payload, psize, cudaMemcpyDefault, st));
+      MGB_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
     *offset += 8 + psize;
   }
   return MGB_SUCCESS;

@@ -79,9 +79,14 @@ def exchange_sizes(local_size, dist=None, group=None, device=None):
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     mine = torch.tensor([int(local_size)], dtype=torch.int64, device=device)
-    allsz = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(allsz, mine, group=group)
-    sizes = [int(x.item()) for x in allsz]
+    allsz = torch.zeros(world, dtype=torch.int64, device=device)
+    if hasattr(dist, "all_gather_into_tensor") and device is not None:
+        dist.all_gather_into_tensor(allsz, mine, group=group)
+        sizes = [int(x) for x in allsz.tolist()]  # one device-to-host read
+    else:  # gloo (CPU tests)
+        parts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        sizes = [int(x.item()) for x in parts]
     return sizes, sum(sizes[:rank])
 
 

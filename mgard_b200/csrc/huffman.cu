@@ -1270,8 +1270,8 @@ int launch_decoders(mgb_plan *p, const u64 *ddata, u64 total_words, const u64 *b
     }
   }
   if (fast_bufw || big_bufw) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (mgb_first_use_on_device(configured)) {
       MGB_CUDA_CHECK(cudaFuncSetAttribute(decode_fast_kernel<DF_T, OUT>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 114 * 1024));
       cudaFuncSetAttribute(decode_fast_kernel<DF_T, OUT>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -1280,7 +1280,6 @@ int launch_decoders(mgb_plan *p, const u64 *ddata, u64 total_words, const u64 *b
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
       cudaFuncSetAttribute(decode_fast_kernel<DF_TBIG, OUT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                            cudaSharedmemCarveoutMaxShared);
-      configured = true;
     }
     MGB_CUDA_CHECK(cudaMemsetAsync(cnt1, 0, 2 * sizeof(unsigned), st));
   }
@@ -1382,11 +1381,10 @@ extern "C" int mgb_codebook(mgb_plan *p, const uint32_t *d_hist, uint64_t *d_cod
   size_t left = smem_max - (key_smem ? (size_t)npow2 * 8 : 0);
   int ncap = (int)std::min<size_t>(left / 32, (size_t)dict);
   const size_t smem = (key_smem ? (size_t)npow2 * 8 : 0) + (size_t)ncap * 32;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  if (mgb_first_use_on_device(configured)) {
     MGB_CUDA_CHECK(cudaFuncSetAttribute(codebook_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem_max));
-    configured = true;
   }
   static const int cb_threads = getenv("MGB_CB_THREADS") ? atoi(getenv("MGB_CB_THREADS")) : 1024;
   MGB_LAUNCH(MGB_K_CODEBOOK, (cudaStream_t)stream,

@@ -81,6 +81,18 @@ struct mgb_plan {
   const unsigned char *dtab(uint64_t off) const { return d_tables + off * tsize; }
 };
 
+// Function attributes (dynamic shared memory limits) are per device: true the
+// first time the calling site runs on the current device.
+inline bool mgb_first_use_on_device(bool (&seen)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (seen[dev])
+    return false;
+  seen[dev] = true;
+  return true;
+}
+
 // plan.cu
 int mgb_plan_ensure_workspace(mgb_plan *p);
 uint64_t mgb_level_elems(const mgb_plan *p, int l);

@@ -919,14 +919,13 @@ template <typename T, int W>
 bool launch_thomas_smem(T *w, int n, i64 inner, i64 outer, const T *fw, const T *am,
                         const T *bm, T *acc, int mode, cudaStream_t st) {
   const size_t smem = (size_t)n * (W + 1) * sizeof(T);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  if (mgb_first_use_on_device(configured)) {
     if (cudaFuncSetAttribute(thomas_smem_kernel<T, W>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return false;
     cudaFuncSetAttribute(thomas_smem_kernel<T, W>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
-    configured = true;
   }
   i64 blocks = inner == 1 ? (outer + W - 1) / W : outer * ((inner + W - 1) / W);
   const i64 lines = outer * inner;
@@ -1035,11 +1034,10 @@ void thomas_all(mgb_plan *p, int l, T *w, T *acc, int mode, cudaStream_t st) {
         g.am[d] = p->dtab(m.am);
         g.bm[d] = p->dtab(m.bm);
       }
-      static bool configured = false;
-      if (!configured) {
+      static bool configured[64] = {};
+      if (mgb_first_use_on_device(configured)) {
         cudaFuncSetAttribute(thomas_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              200 * 1024);
-        configured = true;
       }
       int threads = 1024;
       MGB_LAUNCH(MGB_K_THOMAS_CONTIG, st,

@@ -35,6 +35,8 @@ int mgb_huffman_decompress_impl(mgb_plan *p, const uint8_t *d_in, uint64_t size,
                                 const int64_t **d_oval, void *stream, void *d_deq,
                                 double deq_scale, int *fused);
 // quantize.cu internals
+int mgb_sort_outliers(const unsigned long long *d_ocount, uint64_t *d_oidx, int64_t *d_oval,
+                      uint64_t cap, cudaStream_t st);
 int mgb_linear_dequant_scale(mgb_plan *plan, int ebtype, double tol, double s, double norm,
                              double *scale);
 int mgb_outlier_restore(mgb_plan *plan, uint64_t ocount, const uint64_t *d_oidx,
@@ -57,7 +59,10 @@ int ensure_lowlevel_workspace(mgb_plan *p) {
   if (!p->d_hist)
     MGB_CUDA_CHECK(cudaMalloc(&p->d_hist, p->cfg.huff_dict_size * sizeof(uint32_t)));
   if (!p->d_oidx) {
-    p->outlier_cap = std::max<uint64_t>(p->N / 32, 4096);
+    // a power of two, so that the list can always be padded for the index sort
+    p->outlier_cap = 4096;
+    while (p->outlier_cap < p->N / 32)
+      p->outlier_cap <<= 1;
     MGB_CUDA_CHECK(cudaMalloc(&p->d_oidx, p->outlier_cap * 8));
     MGB_CUDA_CHECK(cudaMalloc(&p->d_oval, p->outlier_cap * 8));
   }
@@ -93,6 +98,10 @@ extern "C" int mgb_compress_lowlevel(mgb_plan *p, const void *d_in, int ebtype,
                       p->d_scalars, p->d_oidx, p->d_oval, p->outlier_cap, st);
     if (rc)
       return rc;
+    // index order, like the reference's SERIAL adapter (deterministic stream)
+    rc = mgb_sort_outliers(p->d_scalars, p->d_oidx, p->d_oval, p->outlier_cap, st);
+    if (rc)
+      return rc;
     if (attempt == 0) {
       // speculative: encode assuming the outlier buffer was large enough
       rc = mgb_huffman_compress_async(p, p->d_sym, p->N, p->d_hist, p->d_scalars, 0,
@@ -108,7 +117,8 @@ extern "C" int mgb_compress_lowlevel(mgb_plan *p, const void *d_in, int ebtype,
       cudaFree(p->d_oval);
       p->d_oidx = nullptr;
       p->d_oval = nullptr;
-      p->outlier_cap = oc;
+      while (p->outlier_cap < oc)
+        p->outlier_cap <<= 1;
       MGB_CUDA_CHECK(cudaMalloc(&p->d_oidx, p->outlier_cap * 8));
       MGB_CUDA_CHECK(cudaMalloc(&p->d_oval, p->outlier_cap * 8));
     } else {

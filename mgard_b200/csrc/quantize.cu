@@ -703,3 +703,54 @@ int mgb_outlier_restore(mgb_plan *plan, uint64_t ocount, const uint64_t *d_oidx,
   return dequantize_t<double>(plan, nullptr, ocount, d_oidx, d_oval, ebtype, tol, s, norm,
                               (double *)d_coef, st, true);
 }
+
+// Outliers are appended with atomics, so their order depends on scheduling.
+// Sorting them by index (what the reference's SERIAL adapter produces) makes the
+// stream deterministic and byte-identical to the reference's.  One block,
+// bitonic sort in place; lists longer than 65536 entries (or that do not fit
+// their power-of-two padding) are left as they are.
+namespace {
+__global__ void __launch_bounds__(1024)
+sort_outliers_kernel(const unsigned long long *__restrict__ ocount, uint64_t *__restrict__ oidx,
+                     long long *__restrict__ oval, unsigned long long cap) {
+  const unsigned long long n64 = *ocount;
+  if (n64 < 2 || n64 > 65536 || n64 > cap)
+    return;
+  const unsigned n = (unsigned)n64;
+  unsigned np = 1;
+  while (np < n)
+    np <<= 1;
+  if (np > cap)
+    return;
+  for (unsigned i = n + threadIdx.x; i < np; i += blockDim.x)
+    oidx[i] = ~0ull; // padding sorts to the end
+  __syncthreads();
+  for (unsigned k = 2; k <= np; k <<= 1) {
+    for (unsigned j = k >> 1; j > 0; j >>= 1) {
+      for (unsigned i = threadIdx.x; i < np; i += blockDim.x) {
+        const unsigned ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t a = oidx[i], b = oidx[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            oidx[i] = b;
+            oidx[ixj] = a;
+            const long long va = oval[i];
+            oval[i] = oval[ixj];
+            oval[ixj] = va;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+} // namespace
+
+int mgb_sort_outliers(const unsigned long long *d_ocount, uint64_t *d_oidx, int64_t *d_oval,
+                      uint64_t cap, cudaStream_t st) {
+  MGB_LAUNCH(MGB_K_OUTLIER_RESTORE, st,
+             (sort_outliers_kernel<<<1, 1024, 0, st>>>(d_ocount, d_oidx, (long long *)d_oval, cap)));
+  MGB_CUDA_CHECK(cudaGetLastError());
+  return MGB_SUCCESS;
+}

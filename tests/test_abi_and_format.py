@@ -123,3 +123,27 @@ def test_parser_rejects_corruption():
         with pytest.raises(mg.MgardError) as e:
             mg.peek_header(np.frombuffer(b, dtype=np.uint8))
         assert e.value.status in (_lib.BAD_STREAM, _lib.BAD_ARGUMENT)
+
+
+def test_cli_builds_and_reports_missing_backend(tmp_path):
+    """mgard-x-b200 (the reference CLI's options on this engine): usage text without
+    arguments; without a CUDA device a compression request fails loudly with
+    BackendNotAvailableFailure (5), never a CPU fallback."""
+    import subprocess
+    exe = os.path.join(ROOT, "mgard_b200", "mgard-x-b200")
+    if not os.path.exists(exe):
+        pytest.skip("CLI not built")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "--compress" in r.stdout and "--decompress" in r.stdout
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    src = tmp_path / "u.bin"
+    np.sin(np.arange(9 * 9 * 9) * 0.1).astype(np.float32).tofile(src)
+    r = subprocess.run([exe, "-z", "-i", str(src), "-o", str(tmp_path / "u.mgard"), "-dt", "s", "-dim", "3",
+                        "9", "9", "9", "-em", "rel", "-e", "1e-3", "-s", "inf"], capture_output=True, text=True)
+    assert r.returncode == 1 and "status 5" in r.stderr

@@ -55,7 +55,9 @@ def sorted_pairs(oi, ov):
     return oi[o], np.asarray(ov)[o]
 
 
-def check_payload(gpu_payload, oracle_payload):
+def check_payload(gpu_payload, oracle_payload, compressor=True):
+    """compressor: the payload comes from Compressor::Compress (outliers sorted by index,
+    byte-identical block); False: from the Huffman stage API fed with an unsorted list."""
     a = mo.huffman_parse(gpu_payload)
     b = mo.huffman_parse(oracle_payload)
     for k in ("n", "dict_size", "chunk_size"):
@@ -64,6 +66,11 @@ def check_payload(gpu_payload, oracle_payload):
         assert np.array_equal(a[k], b[k]), k
     x, y = sorted_pairs(a["oidx"], a["oval"]), sorted_pairs(b["oidx"], b["oval"])
     assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1])
+    if compressor and len(b["oidx"]) <= 65536:
+        # the compressor sorts the outlier list by index (the order of the reference's
+        # SERIAL adapter), so the whole block is byte-identical
+        assert np.array_equal(np.asarray(a["oidx"]).astype(np.uint64), np.asarray(b["oidx"]).astype(np.uint64))
+        assert gpu_payload == oracle_payload
     assert a["size"] == b["size"] == len(gpu_payload)
 
 
@@ -115,7 +122,7 @@ def test_stages_bit_exact_vs_oracle(env, shape, dtype):
         assert np.array_equal(gdb[128:], cb["keys"])
         pay = p.huffman_compress(sym, hist, goi, gov).cpu().numpy().tobytes()
         opay = mo.huffman_compress(q, 8192, 20480, oi, ov)
-        check_payload(pay, opay)
+        check_payload(pay, opay, compressor=False)
         sym2, oi2, ov2 = p.huffman_decompress(dev(torch, np.frombuffer(opay, dtype=np.uint8), d), u.size)
         assert np.array_equal(sym_np(sym2), q.ravel())
         dq = p.dequantize(sym, goi, gov, eb, tol, s, float(norm)).cpu().numpy()
@@ -386,3 +393,40 @@ def test_fused_dequantization_matches_separate_stages(env):
     staged = p.recompose(coef.reshape(u.shape)).cpu().numpy()
     assert np.array_equal(fused, staged)
     assert np.abs(fused - u).max() <= 1e-4 * np.abs(u).max()
+
+
+def test_cli_round_trip_and_stream_identity(env, tmp_path):
+    """mgard-x-b200 -z / -x (options of the reference's mgard-x executable): the file it
+    writes is byte-identical to mgard_b200.compress's stream on the same input (outliers
+    are sorted by index, so streams are deterministic), and -x reproduces the library's
+    reconstruction."""
+    import subprocess
+    torch, mg, d = env
+    exe = os.path.join(os.path.dirname(HERE), "mgard_b200", "mgard-x-b200")
+    assert os.path.exists(exe), "build the CLI with __graft_entry__.build()"
+    u = field((40, 33, 50), np.float32, 11)
+    src, comp, back = tmp_path / "u.bin", tmp_path / "u.mgard", tmp_path / "u.out"
+    u.tofile(src)
+    r = subprocess.run([exe, "-z", "-i", str(src), "-o", str(comp), "-dt", "s", "-dim", "3", "40", "33", "50",
+                        "-em", "rel", "-e", "1e-3", "-s", "inf", "-l", "huffman", "-d", "cuda", "-v", "2"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Compression ratio" in r.stdout and "Satisfied" in r.stdout and "Not Satisfied" not in r.stdout
+    stream = np.fromfile(comp, dtype=np.uint8)
+    lib_stream = mg.compress(u, 1e-3, np.inf, mo.REL)
+    assert stream.tobytes() == lib_stream.tobytes()
+    r = subprocess.run([exe, "-x", "-i", str(comp), "-o", str(back)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = np.fromfile(back, dtype=np.float32).reshape(u.shape)
+    assert np.array_equal(out, mg.decompress(stream))
+    # s = 0, absolute bound, double precision, non-uniform coordinates from a file
+    v = field((30, 41), np.float64, 2)
+    cs = [nonuniform(30, 3, np.float64), nonuniform(41, 5, np.float64)]
+    v.tofile(src)
+    np.concatenate(cs).tofile(tmp_path / "coords.bin")
+    r = subprocess.run([exe, "-z", "-i", str(src), "-o", str(comp), "-dt", "d", "-dim", "2", "30", "41", "-em", "abs",
+                        "-e", "1e-2", "-s", "0", "-u", str(tmp_path / "coords.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    stream = np.fromfile(comp, dtype=np.uint8)
+    lib_stream = mg.compress(v, 1e-2, 0.0, mo.ABS, coords=cs)
+    assert stream.tobytes() == lib_stream.tobytes()

@@ -1079,11 +1079,18 @@ decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
     s_lut[x] = e;
   }
   __syncthreads();
+  // shared-memory addresses as opaque registers: otherwise the compiler
+  // rematerialises every base (S2R + LEA on the CTA's shared window) inside the
+  // decode loop instead of keeping four registers alive
+  auto opaque = [](unsigned x) {
+    asm volatile("mov.u32 %0, %0;" : "+r"(x));
+    return x;
+  };
   FastTables t;
-  t.words = (unsigned)__cvta_generic_to_shared(s_words);
-  t.lut = (unsigned)__cvta_generic_to_shared(s_lut);
-  t.t32 = (unsigned)__cvta_generic_to_shared(s_t32);
-  t.b32 = (unsigned)__cvta_generic_to_shared(s_b32);
+  t.words = opaque((unsigned)__cvta_generic_to_shared(s_words));
+  t.lut = opaque((unsigned)__cvta_generic_to_shared(s_lut));
+  t.t32 = opaque((unsigned)__cvta_generic_to_shared(s_t32));
+  t.b32 = opaque((unsigned)__cvta_generic_to_shared(s_b32));
   t.first = s_first;
   t.entry = s_entry;
   t.keys = decodebook + 128;

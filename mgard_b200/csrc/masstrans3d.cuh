@@ -84,23 +84,29 @@ masstrans3d_kernel(const Params<T> P, const T *__restrict__ in, T *__restrict__ 
   const int pe = pos(kf, false, nf, ff), po = pos(kf, true, nf, ff);
   // rows of this warp: per row the offsets of the lane's E and O element from the
   // plane base (32-bit; -1: nothing to load)
+  // (offsets of missing elements are 0 with a copy size of 0 = zero fill)
   int roff_e[RPW], roff_o[RPW];
-  bool row_odd[RPW];
+  int se_even[RPW], se_odd[RPW], so_any[RPW]; // copy sizes on even-r / odd-r planes
 #pragma unroll
   for (int q = 0; q < RPW; q++) {
     const int row = wid + q * NW;
-    roff_e[q] = roff_o[q] = -1;
-    row_odd[q] = false;
+    roff_e[q] = roff_o[q] = 0;
+    se_even[q] = se_odd[q] = so_any[q] = 0;
     if (row < NROW) {
       const bool odd = row >= TC + 2;
       const int m = kc0 - 1 + (odd ? row - (TC + 2) : row);
       const int pc = pos(m, odd, ncn, cc);
-      row_odd[q] = odd;
       if (pc >= 0) {
-        if (pe >= 0)
+        if (pe >= 0) {
           roff_e[q] = (int)((i64)pc * P.sin[1] + (i64)pe * P.sin[2]);
-        if (po >= 0)
+          se_odd[q] = (int)sizeof(T);
+          // the all-coarse block (even r, even c, even f) counts as zero
+          se_even[q] = odd ? (int)sizeof(T) : 0;
+        }
+        if (po >= 0) {
           roff_o[q] = (int)((i64)pc * P.sin[1] + (i64)po * P.sin[2]);
+          so_any[q] = (int)sizeof(T);
+        }
       }
     }
   }
@@ -130,13 +136,10 @@ masstrans3d_kernel(const Params<T> P, const T *__restrict__ in, T *__restrict__ 
     for (int q = 0; q < RPW; q++) {
       const int row = wid + q * NW;
       if (row < NROW) { // warp uniform
-        // the all-coarse block (even r, even c, even f) counts as zero
-        const bool ve_ok = pr >= 0 && roff_e[q] >= 0 && (rodd || row_odd[q]);
-        const bool vo_ok = pr >= 0 && roff_o[q] >= 0;
         const unsigned d = stage + (unsigned)((row * 64 + lane) * (int)sizeof(T));
-        const T *ge = ve_ok ? base + roff_e[q] : in;
-        const T *go = vo_ok ? base + roff_o[q] : in;
-        const int se = ve_ok ? (int)sizeof(T) : 0, so = vo_ok ? (int)sizeof(T) : 0; // 0: zero fill
+        const T *ge = base + roff_e[q], *go = base + roff_o[q];
+        const int se = pr >= 0 ? (rodd ? se_odd[q] : se_even[q]) : 0; // 0: zero fill
+        const int so = pr >= 0 ? so_any[q] : 0;
         if (sizeof(T) == 4) {
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(ge), "r"(se));
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d + 32 * 4), "l"(go), "r"(so));

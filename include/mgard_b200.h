@@ -55,6 +55,8 @@ typedef struct mgb_config {
   int32_t domain_decomposition_dim;   /* -1: largest dim (MaxDim) */
   uint64_t domain_decomposition_size; /* 0: do not decompose */
   int32_t normalize_coordinates;      /* 1 (only value supported) */
+  int32_t lossless;            /* mgard_x::lossless_type: 0 Huffman (default), 2 Huffman_Zstd */
+  int32_t zstd_compress_level; /* Config::zstd_compress_level, 3 */
   int32_t reserved;
 } mgb_config;
 

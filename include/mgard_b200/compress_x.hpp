@@ -11,7 +11,7 @@
 //   Config (fields the hot path reads)   mgard-x/Config/Config.h:10-42, Config.cpp:14-43
 //   enums                                mgard-x/Utilities/Types.h:18-66
 //
-// Unsupported Config choices (SingleDim / Hybrid decomposition, LZ4 / Zstd second
+// Unsupported Config choices (SingleDim / Hybrid decomposition, LZ4 second
 // stage, reorder, Block / Variable domain decomposition, ZFP) return
 // compress_status_type::Failure instead of silently doing something else.
 #ifndef MGARD_B200_COMPRESS_X_HPP
@@ -57,6 +57,7 @@ struct Config {
   SIZE huff_block_size = 1024 * 20;
   bool normalize_coordinates = true;
   lossless_type lossless = lossless_type::Huffman;
+  int zstd_compress_level = 3;
   int reorder = 0;
   SIZE domain_decomposition_dim = 0;
   // mgard_b200 extension: planes per MaxDim sub-domain (0: decide from free
@@ -69,7 +70,8 @@ namespace detail {
 inline bool supported(const Config &c) {
   return c.compressor == compressor_type::MGARD &&
          c.decomposition == decomposition_type::MultiDim &&
-         c.lossless == lossless_type::Huffman && c.reorder == 0 &&
+         (c.lossless == lossless_type::Huffman || c.lossless == lossless_type::Huffman_Zstd) &&
+         c.reorder == 0 &&
          c.domain_decomposition == domain_decomposition_type::MaxDim &&
          c.normalize_coordinates &&
          (c.dev_type == device_type::AUTO || c.dev_type == device_type::CUDA);
@@ -82,6 +84,8 @@ inline mgb_config to_c(const Config &c) {
   m.huff_block_size = (int32_t)c.huff_block_size;
   m.domain_decomposition_dim = c.domain_decomposition_size ? (int32_t)c.domain_decomposition_dim : -1;
   m.domain_decomposition_size = c.domain_decomposition_size;
+  m.lossless = (int32_t)c.lossless;
+  m.zstd_compress_level = c.zstd_compress_level;
   return m;
 }
 inline compress_status_type status(int rc) {

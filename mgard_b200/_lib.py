@@ -25,7 +25,8 @@ class MgbConfig(C.Structure):
         ("dev_id", C.c_int32), ("huff_dict_size", C.c_int32),
         ("huff_block_size", C.c_int32), ("domain_decomposition_dim", C.c_int32),
         ("domain_decomposition_size", C.c_uint64),
-        ("normalize_coordinates", C.c_int32), ("reserved", C.c_int32),
+        ("normalize_coordinates", C.c_int32), ("lossless", C.c_int32),
+        ("zstd_compress_level", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

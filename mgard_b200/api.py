@@ -40,6 +40,13 @@ class compress_status_type(enum.IntEnum):
     BackendNotAvailableFailure = 5
 
 
+class lossless_type(enum.IntEnum):
+    Huffman = 0
+    Huffman_LZ4 = 1   # not built (nvcomp)
+    Huffman_Zstd = 2
+    CPU_Lossless = 3  # not built
+
+
 class Config:
     """mgard_x::Config defaults (src/mgard-x/Config/Config.cpp:14-43)."""
 
@@ -50,6 +57,8 @@ class Config:
         self.domain_decomposition_dim = -1
         self.domain_decomposition_size = 0
         self.normalize_coordinates = True
+        self.lossless = lossless_type.Huffman
+        self.zstd_compress_level = 3
 
     def _c(self):
         c = MgbConfig()
@@ -60,6 +69,8 @@ class Config:
         c.domain_decomposition_dim = self.domain_decomposition_dim
         c.domain_decomposition_size = self.domain_decomposition_size
         c.normalize_coordinates = 1 if self.normalize_coordinates else 0
+        c.lossless = int(self.lossless)
+        c.zstd_compress_level = int(self.zstd_compress_level)
         return c
 
 

@@ -41,7 +41,7 @@ namespace {
       "\t\t -e / --error-bound <float>\n"
       "\t\t -s / --smoothness <float|inf>\n"
       "\t\t (optional) -u / --coordinates <path>: D coordinate arrays of the data type, concatenated\n"
-      "\t\t (optional) -l / --lossless <huffman>\n"
+      "\t\t (optional) -l / --lossless <huffman|huffman-zstd>\n"
       "\t\t (optional) -dd / --domain-decomposition <max-dim> [-dd-size <planes per sub-domain>]\n"
       "\t\t (optional) -d / --device <auto|cuda>\n"
       "\t\t (optional) -v / --verbose <0|1|2|3>\n"
@@ -138,9 +138,13 @@ int do_compress(int argc, char **argv, mgard_x::data_type dtype, int verbose) {
   const double tol = to_double(arg(argc, argv, "error bound", "-e", "--error-bound"), "-e");
   const double s = to_double(arg(argc, argv, "smoothness", "-s", "--smoothness"), "-s");
   mgard_x::Config config;
-  if (has(argc, argv, "-l", "--lossless") &&
-      arg(argc, argv, "lossless", "-l", "--lossless") != "huffman")
-    usage("only -l huffman is available in this build");
+  if (has(argc, argv, "-l", "--lossless")) {
+    const std::string l = arg(argc, argv, "lossless", "-l", "--lossless");
+    if (l == "huffman-zstd")
+      config.lossless = mgard_x::lossless_type::Huffman_Zstd;
+    else if (l != "huffman")
+      usage("-l huffman | huffman-zstd (huffman-lz4 needs nvcomp and is not built)");
+  }
   if (has(argc, argv, "-dd", "--domain-decomposition")) {
     if (arg(argc, argv, "domain decomposition", "-dd", "--domain-decomposition") != "max-dim")
       usage("only -dd max-dim is available in this build");

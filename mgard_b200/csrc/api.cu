@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <limits>
 #include <map>
 #include <mutex>
@@ -199,6 +200,38 @@ int ensure_bytes(unsigned char **ptr, uint64_t *have, uint64_t need) {
   return MGB_SUCCESS;
 }
 
+
+// ---- second-stage lossless: Zstandard on the host ------------------------------
+// The reference's Huffman_Zstd stage (include/mgard-x/Lossless/Zstd.hpp:64-125)
+// copies the Huffman block to the host, runs ZSTD_compress and stores
+// `size_t input_count | zstd frame`.  Same here, through the system's libzstd
+// (no header in this image: the four stable C entry points are resolved with
+// dlopen).  Without the library the request fails, it is never ignored.
+struct ZstdApi {
+  size_t (*compress)(void *, size_t, const void *, size_t, int) = nullptr;
+  size_t (*decompress)(void *, size_t, const void *, size_t) = nullptr;
+  size_t (*bound)(size_t) = nullptr;
+  unsigned (*is_error)(size_t) = nullptr;
+  bool ok = false;
+};
+const ZstdApi &zstd_api() {
+  static ZstdApi api = [] {
+    ZstdApi a;
+    void *h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!h)
+      h = dlopen("libzstd.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      a.compress = (decltype(a.compress))dlsym(h, "ZSTD_compress");
+      a.decompress = (decltype(a.decompress))dlsym(h, "ZSTD_decompress");
+      a.bound = (decltype(a.bound))dlsym(h, "ZSTD_compressBound");
+      a.is_error = (decltype(a.is_error))dlsym(h, "ZSTD_isError");
+      a.ok = a.compress && a.decompress && a.bound && a.is_error;
+    }
+    return a;
+  }();
+  return api;
+}
+
 // uniform-grid plans are cached like the reference's CompressorCache
 // (CompressionHighLevel.hpp:89-98); non-uniform ones are rebuilt
 // (Hierarchy::can_reuse, Hierarchy.hpp:722-733).
@@ -366,6 +399,7 @@ void header_from(int ndim, int dtype, const uint64_t *shape, double tol, double 
   h.dd_size = pt.size;
   h.dict_size = cfg->huff_dict_size;
   h.block_size = cfg->huff_block_size;
+  h.lossless = cfg->lossless;
   h.coords.clear();
   if (coords) {
     h.coords.resize(ndim);
@@ -445,7 +479,8 @@ int compress_records(int ndim, int dtype, const uint64_t *shape, const Partition
     // device output whose payload position is 8-byte aligned: compress straight
     // into the record (no staging copy); otherwise through an aligned buffer
     unsigned char *direct = nullptr;
-    if (out_on_device && *offset + 8 <= cap && (((uintptr_t)(out + *offset + 8)) & 7) == 0)
+    if (cfg->lossless != 2 && out_on_device && *offset + 8 <= cap &&
+        (((uintptr_t)(out + *offset + 8)) & 7) == 0)
       direct = out + *offset + 8;
     if (!direct) {
       rc = ensure_bytes(&g_cache.d_payload, &g_cache.payload_bytes, pcap);
@@ -460,6 +495,25 @@ int compress_records(int ndim, int dtype, const uint64_t *shape, const Partition
     if (owned)
       mgb_plan_destroy(plan);
     const void *payload = direct ? direct : g_cache.d_payload;
+    std::vector<unsigned char> zbuf; // host: size_t count | zstd frame
+    if (rc == MGB_SUCCESS && cfg->lossless == 2) {
+      const ZstdApi &z = zstd_api();
+      if (!z.ok)
+        return MGB_FAILURE;
+      std::vector<unsigned char> hpay(psize);
+      MGB_CUDA_CHECK(cudaMemcpyAsync(hpay.data(), payload, psize, cudaMemcpyDeviceToHost, st));
+      MGB_CUDA_CHECK(cudaStreamSynchronize(st));
+      zbuf.resize(sizeof(size_t) + z.bound(psize));
+      const size_t zs = z.compress(zbuf.data() + sizeof(size_t), zbuf.size() - sizeof(size_t),
+                                   hpay.data(), psize, cfg->zstd_compress_level);
+      if (z.is_error(zs))
+        return MGB_FAILURE;
+      const size_t count = psize;
+      memcpy(zbuf.data(), &count, sizeof(size_t));
+      zbuf.resize(sizeof(size_t) + zs);
+      payload = zbuf.data(); // host memory from here on
+      psize = zbuf.size();
+    }
     if (rc == MGB_OUTPUT_TOO_LARGE || (rc == MGB_SUCCESS && psize >= raw_bytes)) {
       // GPUPipelines.hpp:139-155: store the sub-domain uncompressed
       payload = d_in;
@@ -518,6 +572,8 @@ extern "C" int mgb_compress(int ndim, int dtype, const uint64_t *shape, double t
     cfg = *cfg_in;
   else
     mgb_config_default(&cfg);
+  if (cfg.lossless != 0 && cfg.lossless != 2)
+    return MGB_FAILURE; // Huffman_LZ4 (nvcomp) / CPU_Lossless are not built
   std::lock_guard<std::mutex> lock(g_cache.mu);
   const bool in_dev = is_device_pointer(in);
   if (in_dev) {
@@ -723,6 +779,7 @@ extern "C" int mgb_decompress(const void *in, size_t in_size, void **out,
   // Metadata.cpp:129-136: the header overrides the configuration
   cfg.huff_dict_size = h.dict_size;
   cfg.huff_block_size = h.block_size;
+  cfg.lossless = h.lossless;
   const int ndim = h.ndim, dtype = h.dtype;
   const size_t tsize = dtype == MGB_F32 ? 4 : 8;
   uint64_t N = 1;
@@ -834,12 +891,42 @@ extern "C" int mgb_decompress(const void *in, size_t in_size, void **out,
       rc = get_plan(ndim, dtype, sub, nonuniform ? subcoords : nullptr, &cfg, &plan, &owned);
       if (rc)
         break;
-      rc = ensure_bytes(&g_cache.d_payload, &g_cache.payload_bytes, psize + 64);
-      if (!rc && cudaMemcpyAsync(g_cache.d_payload, ip + offset, psize, cudaMemcpyDefault,
-                                 st) != cudaSuccess)
-        rc = MGB_CUDA_ERROR;
+      uint64_t hsize = psize; // size of the Huffman block
+      if (h.lossless == 2) {
+        // Zstd.hpp:100-125: `size_t count | zstd frame` -> Huffman block, on the host
+        const ZstdApi &z = zstd_api();
+        std::vector<unsigned char> rec(psize), hpay;
+        if (!z.ok || psize < sizeof(size_t))
+          rc = z.ok ? MGB_BAD_STREAM : MGB_FAILURE;
+        if (!rc && cudaMemcpy(rec.data(), ip + offset, psize, cudaMemcpyDefault) != cudaSuccess)
+          rc = MGB_CUDA_ERROR;
+        if (!rc) {
+          size_t count = 0;
+          memcpy(&count, rec.data(), sizeof(size_t));
+          if (count > (size_t)raw_bytes * 2 + (1u << 24))
+            rc = MGB_BAD_STREAM;
+          if (!rc) {
+            hpay.resize(count);
+            const size_t got = z.decompress(hpay.data(), count, rec.data() + sizeof(size_t),
+                                            psize - sizeof(size_t));
+            if (z.is_error(got) || got != count)
+              rc = MGB_BAD_STREAM;
+          }
+          hsize = count;
+        }
+        if (!rc)
+          rc = ensure_bytes(&g_cache.d_payload, &g_cache.payload_bytes, hsize + 64);
+        if (!rc && cudaMemcpy(g_cache.d_payload, hpay.data(), hsize, cudaMemcpyHostToDevice) !=
+                       cudaSuccess)
+          rc = MGB_CUDA_ERROR;
+      } else {
+        rc = ensure_bytes(&g_cache.d_payload, &g_cache.payload_bytes, psize + 64);
+        if (!rc && cudaMemcpyAsync(g_cache.d_payload, ip + offset, psize, cudaMemcpyDefault,
+                                   st) != cudaSuccess)
+          rc = MGB_CUDA_ERROR;
+      }
       if (!rc)
-        rc = mgb_decompress_lowlevel(plan, g_cache.d_payload, psize, leb, ltol, h.s,
+        rc = mgb_decompress_lowlevel(plan, g_cache.d_payload, hsize, leb, ltol, h.s,
                                      h.norm, d_dst, st);
       if (owned)
         mgb_plan_destroy(plan);

@@ -172,7 +172,7 @@ std::vector<uint8_t> mgb_encode_stream_header(const mgb_header &h) {
   f_varint(quant, 1, 1); // COEFFICIENTWISE_LINEAR
   f_varint(quant, 3, 3); // INT64_T
   std::string enc;
-  f_varint(enc, 2, 3); // X_HUFFMAN
+  f_varint(enc, 2, h.lossless == 2 ? 5 : 3); // X_HUFFMAN / X_HUFFMAN_ZSTD (mgard.proto:139-145)
   f_varint(enc, 3, (uint64_t)h.dict_size);
   f_varint(enc, 4, (uint64_t)h.block_size);
   std::string dev;
@@ -337,9 +337,10 @@ int mgb_parse_stream_header(const uint8_t *data, size_t size, mgb_header &h,
   // Metadata.cpp:501-514: only the major version is checked
   if (major > 1)
     return MGB_BAD_STREAM;
-  // this engine decodes MGARD-X multi-dimensional Huffman streams only
-  if (hierarchy != 1 || compressor != 3 || preprocessor != 0)
+  // this engine decodes MGARD-X multi-dimensional Huffman (+ Zstd) streams only
+  if (hierarchy != 1 || (compressor != 3 && compressor != 5) || preprocessor != 0)
     return MGB_BAD_STREAM;
+  h.lossless = compressor == 5 ? 2 : 0;
   if (geometry == 1) {
     uint64_t tot = 0;
     for (int d = 0; d < h.ndim; d++)

@@ -14,6 +14,7 @@ struct mgb_header {
   bool decomposed = false;
   uint64_t dd_dim = 0, dd_size = 0;
   int dict_size = 8192, block_size = 20480;
+  int lossless = 0; // 0: X_HUFFMAN, 2: X_HUFFMAN_ZSTD (mgard_x::lossless_type values)
   std::vector<std::vector<double>> coords; // empty: uniform grid
 };
 

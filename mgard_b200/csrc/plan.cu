@@ -273,6 +273,8 @@ extern "C" void mgb_config_default(mgb_config *cfg) {
   cfg->domain_decomposition_dim = -1;
   cfg->domain_decomposition_size = 0;
   cfg->normalize_coordinates = 1;
+  cfg->lossless = 0;
+  cfg->zstd_compress_level = 3;
   cfg->reserved = 0;
 }
 

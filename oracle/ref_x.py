@@ -32,6 +32,7 @@ class RefxArgs(C.Structure):
         ("outlier_count", C.c_uint64),
         ("payload", C.c_void_p), ("payload_cap", C.c_uint64),
         ("payload_size", C.c_uint64),
+        ("lossless", C.c_int32), ("zstd_level", C.c_int32),
     ]
 
 
@@ -133,13 +134,14 @@ def recompose(v, coords=None):
     return u
 
 
-def compress(u, ebtype, tol, s, coords=None, dict_size=8192, chunk_size=20480):
+def compress(u, ebtype, tol, s, coords=None, dict_size=8192, chunk_size=20480, lossless=0):
     """Low-level Compressor::Compress staged; returns dict with payload bytes,
     norm, decomposed coefficients, quantized (dict-shifted) int64, outlier count."""
     keep = []
     v = np.array(u, copy=True, order="C")
     a = _base_args(v.shape, v.dtype, coords, dict_size, chunk_size, keep)
     a.op = OP_COMPRESS
+    a.lossless = lossless
     a.ebtype = ebtype
     a.tol = tol
     _set_s(a, s)
@@ -160,11 +162,12 @@ def compress(u, ebtype, tol, s, coords=None, dict_size=8192, chunk_size=20480):
 
 
 def decompress(payload, shape, dtype, ebtype, tol, s, norm, coords=None,
-               dict_size=8192, chunk_size=20480):
+               dict_size=8192, chunk_size=20480, lossless=0):
     keep = []
     out = np.zeros(shape, dtype=dtype)
     a = _base_args(shape, dtype, coords, dict_size, chunk_size, keep)
     a.op = OP_DECOMPRESS
+    a.lossless = lossless
     a.ebtype = ebtype
     a.tol = tol
     a.norm = norm

@@ -45,7 +45,9 @@ constexpr DIM D = REFX_D;
 static Config make_config(const refx_args *a) {
   Config cfg;
   cfg.dev_type = device_type::SERIAL;
-  cfg.lossless = lossless_type::Huffman;
+  cfg.lossless = a->lossless == 2 ? lossless_type::Huffman_Zstd : lossless_type::Huffman;
+  if (a->zstd_level)
+    cfg.zstd_compress_level = a->zstd_level;
   cfg.huff_dict_size = a->dict_size;
   cfg.huff_block_size = a->chunk_size;
   cfg.normalize_coordinates = true;

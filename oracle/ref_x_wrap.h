@@ -33,6 +33,8 @@ typedef struct refx_args {
   uint8_t *payload;
   uint64_t payload_cap;
   uint64_t payload_size; /* out on compress, in on decompress */
+  int32_t lossless;      /* mgard_x::lossless_type: 0 Huffman, 2 Huffman_Zstd */
+  int32_t zstd_level;    /* 0: reference default (3) */
 } refx_args;
 
 #ifdef __cplusplus

@@ -147,3 +147,26 @@ def test_cli_builds_and_reports_missing_backend(tmp_path):
     r = subprocess.run([exe, "-z", "-i", str(src), "-o", str(tmp_path / "u.mgard"), "-dt", "s", "-dim", "3",
                         "9", "9", "9", "-em", "rel", "-e", "1e-3", "-s", "inf"], capture_output=True, text=True)
     assert r.returncode == 1 and "status 5" in r.stderr
+
+
+def test_header_records_the_second_stage_lossless():
+    """Encoding.compressor (src/mgard.proto:139-145): X_HUFFMAN = 3 by default,
+    X_HUFFMAN_ZSTD = 5 for lossless_type::Huffman_Zstd; nothing else changes."""
+    L = _lib.lib()
+    outs = []
+    for lossless in (0, 2):
+        cfg = _lib.MgbConfig()
+        L.mgb_config_default(C.byref(cfg))
+        cfg.domain_decomposition_size = 1 << 40
+        cfg.lossless = lossless
+        out = np.zeros(1 << 12, dtype=np.uint8)
+        sz = C.c_uint64(0)
+        shape = (C.c_uint64 * 3)(33, 34, 35)
+        assert L.mgb_write_header(3, 0, shape, 1e-3, float("inf"), 0, 1.0, None, C.byref(cfg),
+                                  out.ctypes.data, out.size, C.byref(sz)) == 0
+        outs.append(out[:sz.value].copy())
+    a, b = outs
+    assert a.size == b.size
+    diff = np.nonzero(a[17:] != b[17:])[0]  # after magic | size | crc
+    assert diff.size == 1 and a[17 + diff[0]] == 3 and b[17 + diff[0]] == 5
+    assert mg.peek_header(a)["header_bytes"] == mg.peek_header(b)["header_bytes"] == a.size

@@ -430,3 +430,45 @@ def test_cli_round_trip_and_stream_identity(env, tmp_path):
     stream = np.fromfile(comp, dtype=np.uint8)
     lib_stream = mg.compress(v, 1e-2, 0.0, mo.ABS, coords=cs)
     assert stream.tobytes() == lib_stream.tobytes()
+
+
+def test_huffman_zstd_second_stage(env, tmp_path):
+    """lossless_type::Huffman_Zstd (Lossless/Zstd.hpp:64-125): the record is
+    `size_t count | zstd frame` of the Huffman block.  Round trip within the bound,
+    smaller than the Huffman-only stream, identical to what the reference's own
+    Huffman_Zstd stage writes (same libzstd on the box), and through the CLI."""
+    import subprocess
+    torch, mg, d = env
+    u = field((48, 40, 44), np.float32, 9)
+    cfg = mg.Config()
+    cfg.lossless = mg.lossless_type.Huffman_Zstd
+    plain = mg.compress(u, 1e-3, np.inf, mo.REL)
+    st = mg.compress(u, 1e-3, np.inf, mo.REL, config=cfg)
+    assert st.size < plain.size
+    back = mg.decompress(st)
+    assert np.array_equal(back, mg.decompress(plain))
+    assert np.abs(back - u).max() <= 1e-3 * np.abs(u).max()
+    # device buffers take the same path
+    dst = mg.compress(dev(torch, u, d), 1e-3, np.inf, mo.REL, config=cfg)
+    assert dst.cpu().numpy().tobytes() == st.tobytes()
+    assert np.array_equal(mg.decompress(dst).cpu().numpy(), back)
+    hb = mg.peek_header(st)["header_bytes"]
+    rec = st[hb:]
+    size = int(np.frombuffer(rec[:8].tobytes(), dtype="<u8")[0])
+    count = int(np.frombuffer(rec[8:16].tobytes(), dtype="<u8")[0])
+    assert size == rec.size - 8 and count == plain.size - mg.peek_header(plain)["header_bytes"] - 8
+    if ref_x.available():
+        # the reference's code lengths depend on a word it reads past the end of its
+        # frequency array (GenerateCL.hpp:252-257; INTEGRATION.md section 2), so its
+        # Huffman block - the zstd input - is not always the same size; compare bytes
+        # when it is, as the other reference comparisons in this file do
+        r = ref_x.compress(u, ref_x.REL, 1e-3, np.inf, lossless=2)
+        if int(np.frombuffer(r["payload"][:8].tobytes(), dtype="<u8")[0]) == count:
+            assert rec[8:].tobytes() == r["payload"].tobytes()
+    exe = os.path.join(os.path.dirname(HERE), "mgard_b200", "mgard-x-b200")
+    src, comp = tmp_path / "u.bin", tmp_path / "u.mgard"
+    u.tofile(src)
+    r = subprocess.run([exe, "-z", "-i", str(src), "-o", str(comp), "-dt", "s", "-dim", "3", "48", "40", "44",
+                        "-em", "rel", "-e", "1e-3", "-s", "inf", "-l", "huffman-zstd"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert np.fromfile(comp, dtype=np.uint8).tobytes() == st.tobytes()

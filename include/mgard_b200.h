@@ -185,6 +185,15 @@ int mgb_write_header(int ndim, int dtype, const uint64_t *shape, double tol,
                      const void *const *coords, const mgb_config *cfg,
                      uint8_t *out, uint64_t cap, uint64_t *size);
 
+/* Page-lock / query / release a host buffer so that the copies of the high-level
+ * calls run at full PCIe speed: mgard_x::pin_memory / check_memory_pinned /
+ * unpin_memory (reference include/compress_x.hpp:162-178,
+ * CompressionHighLevel/DynamicAPI.cpp:606-740; cudaHostRegister underneath, as in
+ * RuntimeX/DeviceAdapters/DeviceAdapterCuda.h MemoryManager::HostRegister). */
+int mgb_pin_memory(void *ptr, uint64_t num_bytes);
+int mgb_check_memory_pinned(const void *ptr);
+int mgb_unpin_memory(void *ptr);
+
 /* kernel launch counter (bench.py's gpu_launches) */
 uint64_t mgb_launch_count(void);
 /* Per-kernel-family timing with CUDA events on the launching stream

@@ -176,6 +176,11 @@ inline compress_status_type release_cache(Config) {
   return compress_status_type::Success;
 }
 
+// compress_x.hpp:162-178
+inline void pin_memory(void *ptr, SIZE num_bytes, Config) { mgb_pin_memory(ptr, num_bytes); }
+inline bool check_memory_pinned(void *ptr, Config) { return mgb_check_memory_pinned(ptr) != 0; }
+inline void unpin_memory(void *ptr, Config) { mgb_unpin_memory(ptr); }
+
 } // namespace mgard_x
 
 #endif

@@ -62,6 +62,9 @@ SIGNATURES = {
     "mgb_release_cache": (None, []),
     "mgb_compress_subdomains": (_i32, [_i32, _i32, _pu64, _dbl, _dbl, _i32, _dbl, _vp, _u64, _u64, C.POINTER(MgbConfig), _vp, _u64, _pu64]),
     "mgb_write_header": (_i32, [_i32, _i32, _pu64, _dbl, _dbl, _i32, _dbl, C.POINTER(_vp), C.POINTER(MgbConfig), _vp, _u64, _pu64]),
+    "mgb_pin_memory": (_i32, [_vp, _u64]),
+    "mgb_check_memory_pinned": (_i32, [_vp]),
+    "mgb_unpin_memory": (_i32, [_vp]),
     "mgb_launch_count": (_u64, []),
     "mgb_profile_enable": (None, [_i32]),
     "mgb_profile_report": (_i32, [_i32, C.POINTER(C.c_char_p), C.POINTER(C.c_ulonglong), C.POINTER(_dbl), C.POINTER(_dbl)]),

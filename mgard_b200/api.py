@@ -109,6 +109,19 @@ def _shape_arg(shape):
     return (C.c_uint64 * len(shape))(*[int(s) for s in shape])
 
 
+def pin_memory(array):
+    """mgard_x::pin_memory (compress_x.hpp:162-167): page-lock a numpy array in place."""
+    check(_lib.lib().mgb_pin_memory(array.ctypes.data, array.nbytes), "pin_memory")
+
+
+def check_memory_pinned(array):
+    return bool(_lib.lib().mgb_check_memory_pinned(array.ctypes.data))
+
+
+def unpin_memory(array):
+    check(_lib.lib().mgb_unpin_memory(array.ctypes.data), "unpin_memory")
+
+
 def launch_count():
     """Number of kernels this library has launched so far (bench.py gpu_launches)."""
     return int(_lib.lib().mgb_launch_count())

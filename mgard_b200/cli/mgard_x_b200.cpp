@@ -182,6 +182,7 @@ int do_compress(int argc, char **argv, mgard_x::data_type dtype, int verbose) {
     for (auto &c : coord_store)
       coords.push_back((const mgard_x::Byte *)c.data());
   }
+  mgard_x::pin_memory(u.data(), n * sizeof(T), config); // as the reference's CLI does
   void *compressed = nullptr;
   size_t compressed_size = 0;
   auto t0 = std::chrono::steady_clock::now();
@@ -215,6 +216,7 @@ int do_compress(int argc, char **argv, mgard_x::data_type dtype, int verbose) {
     std::cout << std::fixed << "[TIME] compress " << ms(t0, t1) << " ms, decompress " << ms(t2, t3)
               << " ms (host buffers, transfers included)\n";
   }
+  mgard_x::unpin_memory(u.data(), config);
   std::free(compressed);
   std::free(back);
   mgard_x::release_cache(config);

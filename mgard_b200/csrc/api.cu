@@ -1024,5 +1024,37 @@ extern "C" int mgb_write_header(int ndim, int dtype, const uint64_t *shape, doub
   return MGB_SUCCESS;
 }
 
+extern "C" int mgb_pin_memory(void *ptr, uint64_t num_bytes) {
+  if (!ptr || !num_bytes)
+    return MGB_BAD_ARGUMENT;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return MGB_BACKEND_NOT_AVAILABLE;
+  }
+  cudaError_t e = cudaHostRegister(ptr, num_bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return MGB_SUCCESS;
+  }
+  return e == cudaSuccess ? MGB_SUCCESS : MGB_CUDA_ERROR;
+}
+extern "C" int mgb_check_memory_pinned(const void *ptr) {
+  cudaPointerAttributes a;
+  if (!ptr || cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return a.type == cudaMemoryTypeHost ? 1 : 0;
+}
+extern "C" int mgb_unpin_memory(void *ptr) {
+  if (!ptr)
+    return MGB_BAD_ARGUMENT;
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess)
+    cudaGetLastError();
+  return e == cudaSuccess ? MGB_SUCCESS : MGB_CUDA_ERROR;
+}
+
 extern "C" uint64_t mgb_launch_count(void) { return g_mgb_launches; }
 extern "C" const char *mgb_version(void) { return "mgard_b200 0.1 (sm_100a)"; }

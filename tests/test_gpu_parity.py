@@ -472,3 +472,15 @@ def test_huffman_zstd_second_stage(env, tmp_path):
                         "-em", "rel", "-e", "1e-3", "-s", "inf", "-l", "huffman-zstd"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert np.fromfile(comp, dtype=np.uint8).tobytes() == st.tobytes()
+
+
+def test_pin_memory_api(env):
+    """mgard_x::pin_memory / check_memory_pinned / unpin_memory (compress_x.hpp:162-178)."""
+    torch, mg, d = env
+    a = np.zeros(1 << 20, dtype=np.float32)
+    assert not mg.check_memory_pinned(a)
+    mg.pin_memory(a)
+    assert mg.check_memory_pinned(a)
+    mg.pin_memory(a)  # idempotent
+    mg.unpin_memory(a)
+    assert not mg.check_memory_pinned(a)

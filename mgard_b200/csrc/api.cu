@@ -36,6 +36,11 @@ int mgb_huffman_decompress_impl(mgb_plan *p, const uint8_t *d_in, uint64_t size,
                                 const int64_t **d_oval, void *stream, void *d_deq,
                                 double deq_scale, int *fused);
 // quantize.cu internals
+int mgb_quantize_range(mgb_plan *plan, const void *d_coef, int ebtype, double tol, double s,
+                       double norm, uint16_t *d_sym, uint32_t *d_hist,
+                       unsigned long long *d_ocount, uint64_t *d_oidx, int64_t *d_oval,
+                       uint64_t outlier_cap, uint64_t first, uint64_t count, int zero,
+                       unsigned max_blocks, cudaStream_t st);
 int mgb_sort_outliers(const unsigned long long *d_ocount, uint64_t *d_oidx, int64_t *d_oval,
                       uint64_t cap, cudaStream_t st);
 int mgb_linear_dequant_scale(mgb_plan *plan, int ebtype, double tol, double s, double norm,
@@ -91,12 +96,29 @@ extern "C" int mgb_compress_lowlevel(mgb_plan *p, const void *d_in, int ebtype,
     if (rc)
       return rc;
   }
+  // s = inf, 3-D: the upper half of the coefficients is quantized while the coarse
+  // levels are still being decomposed (refactor.cu: decompose_t)
+  p->early_q.armed = is_inf(s) && p->D == 3 && !p->force_generic && p->L >= 3 &&
+                     getenv("MGB_NO_EARLY_QUANTIZE") == nullptr;
+  p->early_q.done = false;
+  p->early_q.ebtype = ebtype;
+  p->early_q.tol = tol;
+  p->early_q.s = s;
+  p->early_q.norm = *norm;
   rc = mgb_decompose_impl(p, d_in, p->d_coef, st);
+  p->early_q.armed = false;
   if (rc)
     return rc;
   for (int attempt = 0; attempt < 2; attempt++) {
-    rc = mgb_quantize(p, p->d_coef, ebtype, tol, s, *norm, p->d_sym, p->d_hist,
-                      p->d_scalars, p->d_oidx, p->d_oval, p->outlier_cap, st);
+    if (attempt == 0 && p->early_q.done) {
+      MGB_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_qjoin, 0));
+      rc = mgb_quantize_range(p, p->d_coef, ebtype, tol, s, *norm, p->d_sym, p->d_hist,
+                              p->d_scalars, p->d_oidx, p->d_oval, p->outlier_cap, 0,
+                              p->early_q.first, 0, 148 * 4, st);
+    } else {
+      rc = mgb_quantize(p, p->d_coef, ebtype, tol, s, *norm, p->d_sym, p->d_hist,
+                        p->d_scalars, p->d_oidx, p->d_oval, p->outlier_cap, st);
+    }
     if (rc)
       return rc;
     // index order, like the reference's SERIAL adapter (deterministic stream)

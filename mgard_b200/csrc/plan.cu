@@ -380,6 +380,12 @@ extern "C" void mgb_plan_destroy(mgb_plan *p) {
   cudaFree(p->d_wB);
   if (p->side)
     cudaStreamDestroy(p->side);
+  if (p->side_q)
+    cudaStreamDestroy(p->side_q);
+  if (p->ev_qfork)
+    cudaEventDestroy(p->ev_qfork);
+  if (p->ev_qjoin)
+    cudaEventDestroy(p->ev_qjoin);
   if (p->ev_fork)
     cudaEventDestroy(p->ev_fork);
   if (p->ev_join)

@@ -77,6 +77,18 @@ struct mgb_plan {
   // next to the latency-bound small levels (refactor.cu: recompose_t)
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // compression, s = inf: the upper half of the coefficient array (slowest index >=
+  // coarse size) holds finest-level coefficients only.  It is quantized on a second
+  // side stream in the shadow of the latency-bound coarse levels; armed by
+  // mgb_compress_lowlevel, consumed by decompose_t
+  cudaStream_t side_q = nullptr;
+  cudaEvent_t ev_qfork = nullptr, ev_qjoin = nullptr;
+  struct {
+    bool armed = false, done = false;
+    int ebtype = 0;
+    double tol = 0, s = 0, norm = 0;
+    uint64_t first = 0; // elements [first, N) were quantized early
+  } early_q;
 
   const unsigned char *dtab(uint64_t off) const { return d_tables + off * tsize; }
 };

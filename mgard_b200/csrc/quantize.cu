@@ -101,7 +101,8 @@ quantize_linear_kernel(const T *__restrict__ v, i64 N, T q, T vol, int dict,
                        uint16_t *__restrict__ sym, unsigned *__restrict__ ghist,
                        unsigned long long *__restrict__ ocount,
                        uint64_t *__restrict__ oidx, i64 *__restrict__ oval,
-                       unsigned long long ocap) {
+                       unsigned long long ocap, unsigned long long base) {
+  // v / sym point at element `base` of the array (outlier indices are global)
   extern __shared__ unsigned sh[];
   typedef typename Vec16<T>::type V;
   constexpr int VN = Vec16<T>::n, PER = 8, NV = PER / VN;
@@ -142,7 +143,7 @@ quantize_linear_kernel(const T *__restrict__ v, i64 N, T q, T vol, int dict,
 #pragma unroll
       for (int k = 0; k < PER; k++) {
         const bool o = valid && !(qi[k] >= 0 && qi[k] < dict);
-        outlier_append(o, (unsigned long long)(gi * PER + k), valid ? qi[k] : 0, ocount, oidx,
+        outlier_append(o, base + (unsigned long long)(gi * PER + k), valid ? qi[k] : 0, ocount, oidx,
                        oval, ocap);
       }
     }
@@ -190,7 +191,7 @@ quantize_linear_kernel(const T *__restrict__ v, i64 N, T q, T vol, int dict,
       sym[i] = (uint16_t)s1;
       atomicAdd(&sh[s1], 1u);
     }
-    outlier_append(o, (unsigned long long)i, q1, ocount, oidx, oval, ocap);
+    outlier_append(o, base + (unsigned long long)i, q1, ocount, oidx, oval, ocap);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < dict; i += blockDim.x) {
@@ -518,24 +519,35 @@ template <typename T>
 int quantize_t(mgb_plan *p, const T *d_coef, int ebtype, double tol, double s,
                double norm, uint16_t *d_sym, uint32_t *d_hist,
                unsigned long long *d_ocount, uint64_t *d_oidx, int64_t *d_oval,
-               uint64_t ocap, cudaStream_t st) {
+               uint64_t ocap, cudaStream_t st, uint64_t first = 0, uint64_t count = ~0ull,
+               bool zero = true, unsigned max_blocks = 148 * 4) {
+  // [first, first + count): part of the array (s = inf only); zero: clear the
+  // histogram and the outlier counter first
   QParams qp;
   Tables<T> tb;
   make_params<T>(p, ebtype, tol, s, norm, false, qp, tb);
   const int dict = qp.dict;
-  MGB_CUDA_CHECK(cudaMemsetAsync(d_hist, 0, dict * sizeof(uint32_t), st));
-  MGB_CUDA_CHECK(cudaMemsetAsync(d_ocount, 0, sizeof(unsigned long long), st));
+  if (count == ~0ull)
+    count = p->N - first;
+  if (zero) {
+    MGB_CUDA_CHECK(cudaMemsetAsync(d_hist, 0, dict * sizeof(uint32_t), st));
+    MGB_CUDA_CHECK(cudaMemsetAsync(d_ocount, 0, sizeof(unsigned long long), st));
+  }
   size_t smem = dict * sizeof(unsigned);
   if (!qp.calc_level) {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(quantize_linear_kernel<T>,
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    unsigned blocks = (unsigned)std::min<i64>((p->N + 2047) / 2048, 148 * 4);
+    if (count == 0)
+      return MGB_SUCCESS;
+    unsigned blocks = (unsigned)std::min<i64>(((i64)count + 2047) / 2048, (i64)max_blocks);
     MGB_LAUNCH(MGB_K_QUANTIZE, st,
                (quantize_linear_kernel<T><<<blocks, 256, smem, st>>>(
-                   d_coef, (i64)p->N, tb.q[0], tb.vol[0], dict, d_sym, d_hist, d_ocount,
-                   d_oidx, (i64 *)d_oval, ocap)));
+                   d_coef + first, (i64)count, tb.q[0], tb.vol[0], dict, d_sym + first, d_hist,
+                   d_ocount, d_oidx, (i64 *)d_oval, ocap, (unsigned long long)first)));
   } else {
+    if (first != 0 || count != p->N)
+      return MGB_BAD_ARGUMENT;
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(quantize_level_kernel<T>,
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -702,6 +714,22 @@ int mgb_outlier_restore(mgb_plan *plan, uint64_t ocount, const uint64_t *d_oidx,
                                (float *)d_coef, st, true);
   return dequantize_t<double>(plan, nullptr, ocount, d_oidx, d_oval, ebtype, tol, s, norm,
                               (double *)d_coef, st, true);
+}
+
+// Part of the array only (s = inf): lets the compressor quantize the level-l_target
+// coefficients that are final early, next to the rest of the decomposition.
+int mgb_quantize_range(mgb_plan *plan, const void *d_coef, int ebtype, double tol, double s,
+                       double norm, uint16_t *d_sym, uint32_t *d_hist,
+                       unsigned long long *d_ocount, uint64_t *d_oidx, int64_t *d_oval,
+                       uint64_t outlier_cap, uint64_t first, uint64_t count, int zero,
+                       unsigned max_blocks, cudaStream_t st) {
+  if (plan->dtype == MGB_F32)
+    return quantize_t<float>(plan, (const float *)d_coef, ebtype, tol, s, norm, d_sym, d_hist,
+                             d_ocount, d_oidx, d_oval, outlier_cap, st, first, count, zero != 0,
+                             max_blocks);
+  return quantize_t<double>(plan, (const double *)d_coef, ebtype, tol, s, norm, d_sym, d_hist,
+                            d_ocount, d_oidx, d_oval, outlier_cap, st, first, count, zero != 0,
+                            max_blocks);
 }
 
 // Outliers are appended with atomics, so their order depends on scheduling.

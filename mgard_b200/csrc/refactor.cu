@@ -29,6 +29,13 @@
 #include "restore3d.cuh"
 #include "plan.h"
 
+// quantize.cu
+int mgb_quantize_range(mgb_plan *plan, const void *d_coef, int ebtype, double tol, double s,
+                       double norm, uint16_t *d_sym, uint32_t *d_hist,
+                       unsigned long long *d_ocount, uint64_t *d_oidx, int64_t *d_oval,
+                       uint64_t outlier_cap, uint64_t first, uint64_t count, int zero,
+                       unsigned max_blocks, cudaStream_t st);
+
 namespace {
 
 typedef long long i64;
@@ -1105,6 +1112,11 @@ void thomas_all(mgb_plan *p, int l, T *w, T *acc, int mode, cudaStream_t st) {
   }
 }
 
+// the tiled 3-D kernels keep per-plane offsets in 32 bits
+static inline bool tiled3d(const mgb_plan *p) {
+  return p->D == 3 && !p->force_generic && p->shape[1] * p->shape[2] < (1ull << 31);
+}
+
 template <typename T>
 int decompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
   int rc = mgb_plan_ensure_workspace(p);
@@ -1131,11 +1143,37 @@ int decompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
     dense_strides(p->lshape[l - 1], D, g.sc);
     fill_tables<T>(p, l, g, false);
     T *coarse = cbuf + p->cbuf_off[l - 1];
-    if (D == 3 && !p->force_generic) {
+    if (tiled3d(p)) {
       T *w = (T *)p->d_wA;
       launch_coef3d<T>(p, l, cur, d_out, coarse, st);
       launch_masstrans3d<T>(p, l, d_out, w, st);
       thomas_all<T>(p, l, w, coarse, 1, st);
+      if (l == p->L && p->early_q.armed && (void *)d_out == (void *)p->d_coef) {
+        // planes r >= coarse size hold level-L coefficients only (final).  Quantize
+        // them now, two blocks per SM, while the coarse levels - a chain of small
+        // latency-bound launches - use a fraction of the machine.  Start at a
+        // multiple of 8 elements so that the 128-bit path applies.
+        const uint64_t plane = (uint64_t)p->shape[1] * p->shape[2];
+        const uint64_t first = (p->lshape[l - 1][0] * plane + 7) / 8 * 8;
+        if (first < p->N) {
+          if (!p->side_q) {
+            MGB_CUDA_CHECK(cudaStreamCreateWithFlags(&p->side_q, cudaStreamNonBlocking));
+            MGB_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_qfork, cudaEventDisableTiming));
+            MGB_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_qjoin, cudaEventDisableTiming));
+          }
+          MGB_CUDA_CHECK(cudaEventRecord(p->ev_qfork, st));
+          MGB_CUDA_CHECK(cudaStreamWaitEvent(p->side_q, p->ev_qfork, 0));
+          rc = mgb_quantize_range(p, p->d_coef, p->early_q.ebtype, p->early_q.tol, p->early_q.s,
+                                  p->early_q.norm, p->d_sym, p->d_hist, p->d_scalars, p->d_oidx,
+                                  p->d_oval, p->outlier_cap, first, p->N - first, 1, 148 * 2,
+                                  p->side_q);
+          if (rc)
+            return rc;
+          MGB_CUDA_CHECK(cudaEventRecord(p->ev_qjoin, p->side_q));
+          p->early_q.first = first;
+          p->early_q.done = true;
+        }
+      }
       cur = coarse;
       continue;
     }
@@ -1200,7 +1238,7 @@ int recompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
   // recursion: the finest level's (throughput bound, most of the work) runs on
   // the caller's stream while the latency-bound chain of the coarse levels runs
   // next to it on a high-priority side stream.
-  const bool fork = D == 3 && !p->force_generic && p->L >= 2;
+  const bool fork = tiled3d(p) && p->L >= 2;
   cudaStream_t sc = st; // stream of the coarse-level chain
   if (fork) {
     if (!p->side) {
@@ -1219,7 +1257,7 @@ int recompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
     T *coarse = cbuf + p->cbuf_off[l - 1];
     T *w = nullptr;
     cudaStream_t sl = (fork && l < p->L) ? sc : st;
-    if (D == 3 && !p->force_generic) {
+    if (tiled3d(p)) {
       if (fork && l == p->L) {
         w = (T *)p->d_wA;
         MGB_CUDA_CHECK(cudaEventRecord(p->ev_join, sc));
@@ -1249,7 +1287,7 @@ int recompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
     dense_strides(p->lshape[l], D, g.sc);
     fill_tables<T>(p, l, g, false);
     T *dst = l == p->L ? d_out : cbuf + p->cbuf_off[l];
-    if (D == 3 && !p->force_generic) {
+    if (tiled3d(p)) {
       launch_restore3d<T>(p, l, coarse, d_in, dst, sl);
       continue;
     }

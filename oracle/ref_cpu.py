@@ -1,0 +1,125 @@
+"""TEST INFRASTRUCTURE — ctypes binding of oracle/_ref/libmgard_cpu_ref.so.
+
+The shared object is the UNMODIFIED reference MGARD-CPU (TensorMeshHierarchy,
+shuffle, decompose/recompose, TensorMultilevelCoefficientQuantizer and the zlib
+leg of src/compressors.cpp) built by oracle/Makefile from /root/reference; see
+ref_cpu_wrap.cpp.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_ref", "libmgard_cpu_ref.so")
+
+INFO, DECOMPOSE, RECOMPOSE, QUANTIZE, DEQUANTIZE, SHUFFLE, UNSHUFFLE = range(7)
+
+
+class RefCpuArgs(C.Structure):
+    _fields_ = [
+        ("op", C.c_int32), ("ndim", C.c_int32), ("dtype", C.c_int32), ("pad", C.c_int32),
+        ("shape", C.POINTER(C.c_uint64)),
+        ("coords", C.c_void_p * 4),
+        ("s", C.c_double), ("tol", C.c_double),
+        ("inp", C.c_void_p), ("out", C.c_void_p),
+        ("L", C.c_uint64), ("ndof", C.c_uint64 * 64),
+    ]
+
+
+_lib = None
+
+
+def available():
+    return os.path.exists(_LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.refcpu_run.argtypes = [C.POINTER(RefCpuArgs)]
+        _lib.refcpu_run.restype = C.c_int
+        _lib.refcpu_zlib_compress.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        _lib.refcpu_zlib_compress.restype = C.c_int64
+        _lib.refcpu_zlib_decompress.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        _lib.refcpu_zlib_decompress.restype = None
+    return _lib
+
+
+def _run(op, shape, dtype, coords, inp, out, s=0.0, tol=0.0):
+    a = RefCpuArgs()
+    keep = []
+    a.op, a.ndim = op, len(shape)
+    a.dtype = 0 if np.dtype(dtype) == np.float32 else 1
+    shp = (C.c_uint64 * len(shape))(*shape)
+    a.shape = shp
+    if coords is not None:
+        for d, c in enumerate(coords):
+            c = np.ascontiguousarray(c, dtype=dtype)
+            keep.append(c)
+            a.coords[d] = c.ctypes.data
+    a.s, a.tol = float(s), float(tol)
+    if inp is not None:
+        a.inp = inp.ctypes.data
+    if out is not None:
+        a.out = out.ctypes.data
+    rc = lib().refcpu_run(C.byref(a))
+    if rc != 0:
+        raise RuntimeError(f"refcpu_run failed: {rc}")
+    return a
+
+
+def info(shape, dtype=np.float64, coords=None):
+    a = _run(INFO, shape, dtype, coords, None, None)
+    return int(a.L), [int(a.ndof[l]) for l in range(int(a.L) + 1)]
+
+
+def _map(op, u, coords, out_dtype=None, in_dtype=None, shape=None, real=None, **kw):
+    shape = u.shape if shape is None else shape
+    real = u.dtype if real is None else real
+    u = np.ascontiguousarray(u)
+    out = np.empty(int(np.prod(shape)), dtype=out_dtype or real)
+    _run(op, shape, real, coords, u, out, **kw)
+    return out
+
+
+def decompose(u, coords=None):
+    """nodal array -> shuffled multilevel coefficients (shuffle + decompose)."""
+    return _map(DECOMPOSE, u, coords)
+
+
+def recompose(c, shape, coords=None):
+    return _map(RECOMPOSE, c, coords, shape=shape).reshape(shape)
+
+
+def shuffle(u, coords=None):
+    return _map(SHUFFLE, u, coords)
+
+
+def unshuffle(c, shape, coords=None):
+    return _map(UNSHUFFLE, c, coords, shape=shape).reshape(shape)
+
+
+def quantize(c, shape, s, tol, coords=None):
+    return _map(QUANTIZE, c, coords, out_dtype=np.int64, shape=shape, s=s, tol=tol)
+
+
+def dequantize(q, shape, dtype, s, tol, coords=None):
+    return _map(DEQUANTIZE, q, coords, out_dtype=dtype, shape=shape, real=dtype, s=s, tol=tol)
+
+
+def zlib_compress(buf):
+    buf = np.ascontiguousarray(buf).view(np.uint8).ravel()
+    cap = buf.size + buf.size // 2 + 4096
+    out = np.empty(cap, dtype=np.uint8)
+    n = lib().refcpu_zlib_compress(buf.ctypes.data, buf.size, out.ctypes.data, cap)
+    assert n >= 0
+    return out[:n].copy()
+
+
+def zlib_decompress(buf, nbytes):
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    out = np.empty(nbytes, dtype=np.uint8)
+    lib().refcpu_zlib_decompress(buf.ctypes.data, buf.size, out.ctypes.data, nbytes)
+    return out

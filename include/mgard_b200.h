@@ -194,6 +194,57 @@ int mgb_pin_memory(void *ptr, uint64_t num_bytes);
 int mgb_check_memory_pinned(const void *ptr);
 int mgb_unpin_memory(void *ptr);
 
+/* ---- MGARD-CPU convention -------------------------------------------------
+ * mgard::compress / mgard::decompress (reference include/compress.hpp:33-72,
+ * include/compress.tpp:35-83) computed on the GPU, bit-identical to the CPU
+ * reference: same multilevel coefficients, same int64 quantisation, same zlib
+ * payload and same protobuf header as a reference build without MGARD_ZSTD.
+ * Any shape (dyadic or not, sizes of 1 allowed), uniform or explicit coordinates. */
+typedef struct mgb_cpu_plan mgb_cpu_plan;
+
+/* mgard::TensorMeshHierarchy<N, Real> (include/TensorMeshHierarchy.tpp:40-166).
+ * coords: NULL for the uniform constructor, else ndim host arrays of dtype T. */
+int mgb_cpu_plan_create(int ndim, const uint64_t *shape, int dtype,
+                        const void *const *coords, mgb_cpu_plan **plan);
+void mgb_cpu_plan_destroy(mgb_cpu_plan *plan);
+/* TensorMeshHierarchy::L, ::ndof(l), ::shapes[l][dim] */
+int mgb_cpu_plan_levels(const mgb_cpu_plan *plan);
+uint64_t mgb_cpu_plan_ndof(const mgb_cpu_plan *plan, int level);
+uint64_t mgb_cpu_plan_level_shape(const mgb_cpu_plan *plan, int level, int dim);
+
+/* stage entry points, device resident (parity tests).  "Shuffled" is the level
+ * order of mgard::shuffle (include/shuffle.tpp:8-37). */
+int mgb_cpu_shuffle(mgb_cpu_plan *plan, const void *d_nodal, void *d_shuffled,
+                    void *stream);
+int mgb_cpu_unshuffle(mgb_cpu_plan *plan, const void *d_shuffled, void *d_nodal,
+                      void *stream);
+/* shuffle + mgard::decompose (include/decompose.tpp:129-174): nodal values ->
+ * shuffled multilevel coefficients; and its inverse, recompose + unshuffle. */
+int mgb_cpu_decompose(mgb_cpu_plan *plan, const void *d_nodal, void *d_coef,
+                      void *stream);
+int mgb_cpu_recompose(mgb_cpu_plan *plan, const void *d_coef, void *d_nodal,
+                      void *stream);
+/* TensorMultilevelCoefficientQuantizer / Dequantizer on shuffled coefficients
+ * (include/TensorMultilevelCoefficientQuantizer.tpp:13-77,242-259).  quantize
+ * synchronises and returns MGB_FAILURE where the reference throws
+ * std::domain_error ("number too large to be quantized"). */
+int mgb_cpu_quantize(mgb_cpu_plan *plan, const void *d_coef, double s, double tol,
+                     int64_t *d_q, void *stream);
+int mgb_cpu_dequantize(mgb_cpu_plan *plan, const int64_t *d_q, double s,
+                       double tol, void *d_coef, void *stream);
+
+/* mgard::compress followed by CompressedDataset::write
+ * (include/CompressedDataset.tpp:26-29): `in` is a host or device array; *out is
+ * a malloc'ed host buffer holding preamble + header + payload (caller frees).
+ * s = +inf selects the L-infinity norm; tol is absolute. */
+int mgb_cpu_compress(int ndim, int dtype, const uint64_t *shape,
+                     const void *const *coords, double s, double tol,
+                     const void *in, void **out, size_t *out_size);
+/* mgard::decompress(void const *, std::size_t) (include/compress.hpp:62-72):
+ * *out is a malloc'ed host array of the decoded dtype and shape. */
+int mgb_cpu_decompress(const void *in, size_t in_size, void **out, int *ndim,
+                       uint64_t *shape, int *dtype);
+
 /* kernel launch counter (bench.py's gpu_launches) */
 uint64_t mgb_launch_count(void);
 /* Per-kernel-family timing with CUDA events on the launching stream

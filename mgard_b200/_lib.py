@@ -65,6 +65,19 @@ SIGNATURES = {
     "mgb_pin_memory": (_i32, [_vp, _u64]),
     "mgb_check_memory_pinned": (_i32, [_vp]),
     "mgb_unpin_memory": (_i32, [_vp]),
+    "mgb_cpu_plan_create": (_i32, [_i32, _pu64, _i32, C.POINTER(_vp), C.POINTER(_vp)]),
+    "mgb_cpu_plan_destroy": (None, [_vp]),
+    "mgb_cpu_plan_levels": (_i32, [_vp]),
+    "mgb_cpu_plan_ndof": (_u64, [_vp, _i32]),
+    "mgb_cpu_plan_level_shape": (_u64, [_vp, _i32, _i32]),
+    "mgb_cpu_shuffle": (_i32, [_vp, _vp, _vp, _vp]),
+    "mgb_cpu_unshuffle": (_i32, [_vp, _vp, _vp, _vp]),
+    "mgb_cpu_decompose": (_i32, [_vp, _vp, _vp, _vp]),
+    "mgb_cpu_recompose": (_i32, [_vp, _vp, _vp, _vp]),
+    "mgb_cpu_quantize": (_i32, [_vp, _vp, _dbl, _dbl, _vp, _vp]),
+    "mgb_cpu_dequantize": (_i32, [_vp, _vp, _dbl, _dbl, _vp, _vp]),
+    "mgb_cpu_compress": (_i32, [_i32, _i32, _pu64, C.POINTER(_vp), _dbl, _dbl, _vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
+    "mgb_cpu_decompress": (_i32, [_vp, C.c_size_t, C.POINTER(_vp), C.POINTER(_i32), _pu64, C.POINTER(_i32)]),
     "mgb_launch_count": (_u64, []),
     "mgb_profile_enable": (None, [_i32]),
     "mgb_profile_report": (_i32, [_i32, C.POINTER(C.c_char_p), C.POINTER(C.c_ulonglong), C.POINTER(_dbl), C.POINTER(_dbl)]),

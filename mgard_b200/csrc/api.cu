@@ -794,6 +794,8 @@ extern "C" int mgb_decompress(const void *in, size_t in_size, void **out,
   int rc = mgb_parse_stream_header(hp, hsize, h, hb);
   if (rc)
     return rc;
+  if (h.convention != 0)
+    return MGB_BAD_STREAM; // MGARD-CPU stream: mgb_cpu_decompress reads those
   mgb_config cfg;
   mgb_config_default(&cfg);
   if (cfg_in)

@@ -122,7 +122,81 @@ double as_double(uint64_t bits) {
 
 } // namespace
 
+namespace {
+std::vector<uint8_t> with_preamble(const std::string &hdr) {
+  std::vector<uint8_t> out;
+  out.insert(out.end(), {'M', 'G', 'A', 'R', 'D'});
+  uint64_t hs = hdr.size();
+  for (int i = 0; i < 8; i++)
+    out.push_back((uint8_t)(hs >> (8 * i)));
+  uint32_t crc = crc32_bytes((const uint8_t *)hdr.data(), hdr.size());
+  for (int i = 0; i < 4; i++)
+    out.push_back((uint8_t)(crc >> (8 * i)));
+  out.insert(out.end(), hdr.begin(), hdr.end());
+  return out;
+}
+
+// Header of mgard::compress (reference include/compress.tpp:41-55):
+// populate_defaults (src/format.cpp:102-140, build without MGARD_ZSTD),
+// TensorMeshHierarchy::populate (include/TensorMeshHierarchy.tpp:293-348) and the
+// error-control block.  Sub-messages that the reference touches through
+// mutable_*() are present even when empty; domain_decomposition and
+// bitplane_encoding are never touched and stay absent.
+std::vector<uint8_t> encode_cpu_header(const mgb_header &h) {
+  std::string ver, fver;
+  f_varint(ver, 1, 1); // MGARD_VERSION 1.6.0 (CMakeLists.txt:13-15)
+  f_varint(ver, 2, 6);
+  f_varint(fver, 1, 1); // MGARD_FILE_VERSION 1.0.0 (:17-19)
+  std::string topo;
+  f_varint(topo, 1, (uint64_t)h.ndim);
+  {
+    std::string packed;
+    for (int d = 0; d < h.ndim; d++)
+      put_varint(packed, h.shape[d]);
+    f_msg(topo, 2, packed);
+  }
+  std::string dom;
+  f_msg(dom, 2, topo);
+  if (!h.coords.empty()) {
+    f_varint(dom, 3, 1); // EXPLICIT_CUBE
+    std::string packed, geo;
+    for (int d = 0; d < h.ndim; d++)
+      packed.append((const char *)h.coords[d].data(), h.coords[d].size() * 8);
+    f_msg(geo, 2, packed);
+    f_msg(dom, 4, geo);
+  }
+  std::string dataset;
+  f_varint(dataset, 1, h.dtype == MGB_F64 ? 1 : 0);
+  f_varint(dataset, 2, 1);
+  std::string err; // mode ABSOLUTE = 0
+  if (!(std::isinf(h.s) && h.s > 0)) {
+    f_varint(err, 2, 1); // S_NORM
+    f_double(err, 3, h.s);
+  }
+  f_double(err, 5, h.tol);
+  std::string quant;
+  f_varint(quant, 1, 1); // COEFFICIENTWISE_LINEAR; PER_COEFFICIENT = 0
+  f_varint(quant, 3, 3); // INT64_T
+  std::string enc;
+  f_varint(enc, 1, 1); // SHUFFLE
+  f_varint(enc, 2, 1); // CPU_HUFFMAN_ZLIB
+  std::string hdr;
+  f_msg(hdr, 2, ver);
+  f_msg(hdr, 3, fver);
+  f_msg(hdr, 4, dom);
+  f_msg(hdr, 5, dataset);
+  f_msg(hdr, 6, err);
+  f_msg(hdr, 8, std::string()); // MULTILEVEL_COEFFICIENTS, POWER_OF_TWO_PLUS_ONE
+  f_msg(hdr, 9, quant);
+  f_msg(hdr, 11, enc);
+  f_msg(hdr, 12, std::string()); // Device::CPU
+  return with_preamble(hdr);
+}
+} // namespace
+
 std::vector<uint8_t> mgb_encode_stream_header(const mgb_header &h) {
+  if (h.convention == 1)
+    return encode_cpu_header(h);
   // VersionNumber: Metadata.cpp:267-271 overwrites mgard_version with the
   // FILE format version (1.0.0, CMakeLists.txt:17-19) and leaves
   // file_format_version empty; reproduced for byte-exactness.
@@ -333,13 +407,18 @@ int mgb_parse_stream_header(const uint8_t *data, size_t size, mgb_header &h,
   }
   if (!r.ok || h.ndim < 1 || h.ndim > MGB_MAX_DIMS)
     return MGB_BAD_STREAM;
-  (void)quant_type;
   // Metadata.cpp:501-514: only the major version is checked
   if (major > 1)
     return MGB_BAD_STREAM;
-  // this engine decodes MGARD-X multi-dimensional Huffman (+ Zstd) streams only
-  if (hierarchy != 1 || (compressor != 3 && compressor != 5) || preprocessor != 0)
+  // MGARD-X multi-dimensional Huffman (+ Zstd) streams, or MGARD-CPU streams
+  // with the zlib payload (CPU_HUFFMAN_ZSTD needs the CPU Huffman coder: not built)
+  if (hierarchy == 0 && compressor == 1) {
+    h.convention = 1;
+    if (quant_type != 3 || h.ebtype != MGB_ABS)
+      return MGB_BAD_STREAM;
+  } else if (hierarchy != 1 || (compressor != 3 && compressor != 5) || preprocessor != 0) {
     return MGB_BAD_STREAM;
+  }
   h.lossless = compressor == 5 ? 2 : 0;
   if (geometry == 1) {
     uint64_t tot = 0;

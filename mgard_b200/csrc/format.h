@@ -15,6 +15,9 @@ struct mgb_header {
   uint64_t dd_dim = 0, dd_size = 0;
   int dict_size = 8192, block_size = 20480;
   int lossless = 0; // 0: X_HUFFMAN, 2: X_HUFFMAN_ZSTD (mgard_x::lossless_type values)
+  // 0: MGARD-X stream (Metadata.cpp); 1: MGARD-CPU stream (src/format.cpp:110-140:
+  // POWER_OF_TWO_PLUS_ONE hierarchy, SHUFFLE preprocessor, CPU_HUFFMAN_ZLIB payload)
+  int convention = 0;
   std::vector<std::vector<double>> coords; // empty: uniform grid
 };
 

@@ -1,0 +1,330 @@
+"""MGARD-CPU convention (mgard::compress / mgard::decompress).
+
+CPU tests pin the numpy restatement (oracle/mgardcpu_oracle.py) to the reference's
+own known-answer vectors and, when it has been built, to the compiled reference
+(oracle/_ref/libmgard_cpu_ref.so).  GPU tests compare the CUDA path, through the
+C ABI, with both -- bit for bit: coefficients, int64 quanta, zlib payload, header.
+"""
+import math
+import os
+import sys
+import zlib
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
+
+import mgardcpu_oracle as mo  # noqa: E402
+import ref_cpu  # noqa: E402
+
+needs_ref = pytest.mark.skipif(not ref_cpu.available(), reason="oracle/_ref/libmgard_cpu_ref.so not built")
+
+
+def bits_equal(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    return a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+def random_coords(rng, shape, dt):
+    """Spacings uniform in [1, 2), as the reference's tests use
+    (tests/src/test_compress.cpp:32-34), scaled to [0, 1]."""
+    out = []
+    for n in shape:
+        if n == 1:
+            out.append(np.zeros(1, dtype=dt))
+            continue
+        x = np.concatenate([[0.0], np.cumsum(rng.uniform(1, 2, n - 1))])
+        out.append((x / x[-1]).astype(dt))
+    return out
+
+
+SHAPES = [
+    ((17,), False), ((33, 17), False), ((9, 9, 9), False), ((20,), True), ((10, 7), True),
+    ((33, 20, 17), True), ((5, 6, 7, 9), True), ((12, 1, 9), False), ((129, 65), False),
+    ((100, 65), True), ((3, 3), False), ((2, 5), False), ((1, 31, 1, 18), True),
+]
+
+
+# ----------------------------------------------------------------------------
+# CPU: oracle vs the reference's known answers and the compiled reference
+# ----------------------------------------------------------------------------
+
+def test_oracle_shuffle_known_answers():
+    # reference tests/src/test_shuffle.cpp:33-50
+    for shape, dt, expected in [
+        ((9,), np.float32, [0, 8, 4, 2, 6, 1, 3, 5, 7]),
+        ((6, 4), np.float32, [0, 3, 8, 11, 20, 23, 1, 4, 5, 7, 9, 12, 13, 15, 21, 2, 6, 10, 14, 16, 17, 18, 19, 22]),
+        ((3, 2, 2), np.float64, list(range(12))),
+    ]:
+        h = mo.Hierarchy(shape, dt)
+        u = np.arange(h.ndof(), dtype=dt).reshape(shape)
+        assert mo.shuffle(h, u).tolist() == expected
+        assert np.array_equal(mo.unshuffle(h, mo.shuffle(h, u)), u)
+
+
+def test_oracle_decompose_known_answers():
+    # reference tests/src/test_decompose.cpp:277-337 (tolerance 1e-4 as there)
+    u1 = [10, 3, -8, -6, 3, 0, -5, 0, 0, -2, -8, -5, -10, -7, 8, -2, 3, -1, 0, 9, -4, -6, -8, -5, -10, 1, 3, 7, -8,
+          1, 10, -2, 8]
+    exp1 = [
+        [10.0, 3.0],
+        [11.0, 2.0, -7.0],
+        [4.4375, 2.0, -14.5, -3.5, -6.687500000000001],
+        [0.4374999999999991, 2.0, -15.678571428571429, -3.5, -4.625000000000002, 1.0, -5.321428571428571, 2.5,
+         -2.4375000000000004],
+        [-0.95703125, 2.0, -15.652199926362297, -3.5, -4.122767857142856, 1.0, -4.978599042709867, 2.5,
+         -4.765625000000001, 2.0, -1.173186671575852, 4.0, -10.689732142857139, -6.0, 9.303985640648008, -7.5,
+         -3.1054687499999987],
+    ]
+    for L, expected in enumerate(exp1):
+        n = (1 << L) + 1
+        h = mo.Hierarchy((n,), np.float32)
+        got = mo.decompose_nodal(h, np.array(u1[:n], dtype=np.float32))
+        assert np.allclose(got, expected, rtol=1e-4, atol=1e-6)
+    u2 = [7, 4, 5, -10, -6, 6, -8, -5, 6, -2, 2, -2, 9, 2, -10, 3, 8, -8, -3, 7, -8, -9, -6, -1, -4]
+    exp2 = [
+        [7.0, 4.0, 5.0, -10.0],
+        [0.9999999999999973, -2.0, 3.9999999999999982, -9.5, -8.5, 0.5, -15.000000000000004, -4.0,
+         3.9999999999999973],
+        [3.8007812499999973, -2.0, -2.9062499999998854, -9.5, -2.910156250000001, 1.5, -13.75, -12.0, 6.5, 6.0,
+         -1.593749999999881, -7.5, 2.8750000000004396, 2.5, -1.0312499999998854, 6.0, 8.75, -9.5, -0.25, 14.0,
+         -2.5039062500000013, -2.0, -10.218749999999885, 4.0, -0.6992187500000024],
+    ]
+    for L, expected in enumerate(exp2):
+        n = (1 << L) + 1
+        h = mo.Hierarchy((n, n), np.float64)
+        got = mo.decompose_nodal(h, np.array(u2[:n * n], dtype=np.float64).reshape(n, n))
+        assert np.allclose(got.ravel(), expected, rtol=1e-4, atol=1e-9)
+        back = mo.recompose_nodal(h, got)
+        assert np.allclose(back.ravel(), u2[:n * n], rtol=1e-12, atol=1e-12)
+
+
+def test_oracle_hierarchy_levels():
+    # level shapes of reference tests/src/test_TensorMeshHierarchy.cpp:19-52 style cases
+    h = mo.Hierarchy((129, 129, 129), np.float64)
+    assert h.L == 7 and h.ndof(0) == 8
+    h = mo.Hierarchy((1000, 1000), np.float32)
+    assert h.L == 10 and h.shapes[9] == (513, 513)
+    h = mo.Hierarchy((5, 3), np.float32)
+    assert h.L == 1 and h.shapes[0] == (3, 2)
+    with pytest.raises(ValueError):
+        mo.Hierarchy((1, 1), np.float32)
+
+
+def test_oracle_header_matches_protobuf_golden():
+    # tests/golden/cpu_headers.npz: bytes produced by python protobuf from the
+    # reference's src/mgard.proto (tests/golden/make_cpu_header_golden.py)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cpu_headers.npz"), allow_pickle=False)
+    n = int(g["count"])
+    assert n >= 4
+    for i in range(n):
+        shape = tuple(int(x) for x in g[f"shape{i}"])
+        dt = np.float64 if int(g[f"dtype{i}"]) == 1 else np.float32
+        coords = None
+        if int(g[f"explicit{i}"]):
+            flat = g[f"coords{i}"]
+            coords, off = [], 0
+            for m in shape:
+                coords.append(flat[off:off + m].astype(dt))
+                off += m
+        h = mo.Hierarchy(shape, dt, coords)
+        got = mo.header_bytes(h, float(g[f"s{i}"]), float(g[f"tol{i}"]))
+        assert got == g[f"bytes{i}"].tobytes()
+
+
+@needs_ref
+@pytest.mark.parametrize("shape,explicit", SHAPES)
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_oracle_matches_reference_build(shape, explicit, dt):
+    rng = np.random.default_rng(hash((shape, explicit)) & 0xffff)
+    coords = random_coords(rng, shape, dt) if explicit else None
+    h = mo.Hierarchy(shape, dt, coords)
+    L, ndof = ref_cpu.info(shape, dt, coords)
+    assert L == h.L and ndof == [h.ndof(l) for l in range(h.L + 1)]
+    u = rng.standard_normal(shape).astype(dt)
+    assert bits_equal(ref_cpu.shuffle(u, coords), mo.shuffle(h, u))
+    c_ref = ref_cpu.decompose(u, coords)
+    assert bits_equal(c_ref, mo.decompose(h, u))
+    assert bits_equal(ref_cpu.recompose(c_ref, shape, coords), mo.recompose(h, c_ref))
+    for s in (math.inf, 0.0, 1.0, -0.5):
+        q_ref = ref_cpu.quantize(c_ref, shape, s, 1e-3, coords)
+        assert np.array_equal(q_ref, mo.quantize(h, s, 1e-3, c_ref))
+        assert bits_equal(ref_cpu.dequantize(q_ref, shape, dt, s, 1e-3, coords), mo.dequantize(h, s, 1e-3, q_ref))
+    q = ref_cpu.quantize(c_ref, shape, math.inf, 1e-3, coords)
+    assert ref_cpu.zlib_compress(q).tobytes() == mo.zlib_payload(q)
+
+
+def test_cpu_convention_symbols_and_no_gpu_behaviour():
+    import torch
+    from mgard_b200 import _lib
+    lib = _lib.lib()
+    for name in ("mgb_cpu_plan_create", "mgb_cpu_compress", "mgb_cpu_decompress", "mgb_cpu_decompose",
+                 "mgb_cpu_recompose", "mgb_cpu_quantize", "mgb_cpu_dequantize", "mgb_cpu_shuffle",
+                 "mgb_cpu_unshuffle"):
+        assert hasattr(lib, name)
+    if not torch.cuda.is_available():
+        import mgard_b200.cpu as mc
+        with pytest.raises(_lib.MgardError) as e:
+            mc.TensorMeshHierarchy((9, 9))
+        assert e.value.status == _lib.BACKEND_NOT_AVAILABLE  # no CPU fallback
+        h = mo.Hierarchy((9, 9), np.float64)
+        blob = mo.compress(h, np.zeros((9, 9)), math.inf, 1e-3)
+        with pytest.raises(_lib.MgardError):
+            mc.decompress(blob)
+
+
+# ----------------------------------------------------------------------------
+# GPU: CUDA path through the C ABI vs the oracle / the compiled reference
+# ----------------------------------------------------------------------------
+
+def _ref_or_oracle_decompose(h, u, coords):
+    return ref_cpu.decompose(u, coords) if ref_cpu.available() else mo.decompose(h, u)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,explicit", SHAPES)
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_gpu_stages_bit_exact(shape, explicit, dt):
+    import torch
+    import mgard_b200.cpu as mc
+    rng = np.random.default_rng(hash((shape, explicit, 7)) & 0xffff)
+    coords = random_coords(rng, shape, dt) if explicit else None
+    h = mo.Hierarchy(shape, dt, coords)
+    H = mc.TensorMeshHierarchy(shape, coords, dt)
+    assert H.L == h.L
+    assert [H.ndof(l) for l in range(h.L + 1)] == [h.ndof(l) for l in range(h.L + 1)]
+    assert [H.level_shape(l) for l in range(h.L + 1)] == [tuple(s) for s in h.shapes]
+    u = rng.standard_normal(shape).astype(dt)
+    du = torch.from_numpy(u).cuda()
+    assert bits_equal(H.shuffle(du).cpu().numpy(), mo.shuffle(h, u))
+    assert bits_equal(H.unshuffle(H.shuffle(du)).cpu().numpy(), u)
+    c_ref = _ref_or_oracle_decompose(h, u, coords)
+    c_gpu = H.decompose(du)
+    assert bits_equal(c_gpu.cpu().numpy(), c_ref)
+    assert bits_equal(c_ref, mo.decompose(h, u))
+    r_ref = ref_cpu.recompose(c_ref, shape, coords) if ref_cpu.available() else mo.recompose(h, c_ref)
+    assert bits_equal(H.recompose(c_gpu).cpu().numpy(), r_ref)
+    for s in (math.inf, 0.0, 1.0, -0.5):
+        q_ref = mo.quantize(h, s, 1e-3, c_ref)
+        if ref_cpu.available():
+            assert np.array_equal(q_ref, ref_cpu.quantize(c_ref, shape, s, 1e-3, coords))
+        q_gpu = H.quantize(c_gpu, s, 1e-3)
+        assert np.array_equal(q_gpu.cpu().numpy(), q_ref)
+        assert bits_equal(H.dequantize(q_gpu, s, 1e-3).cpu().numpy(), mo.dequantize(h, s, 1e-3, q_ref))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,explicit,dt,s,tol", [
+    ((33, 20, 17), True, np.float64, math.inf, 1e-3),
+    ((100, 65), True, np.float32, 0.0, 1e-2),
+    ((65, 65, 65), False, np.float32, math.inf, 1e-3),
+    ((300,), False, np.float64, 1.0, 1e-2),
+    ((5, 6, 7, 9), True, np.float64, -0.5, 1e-2),
+])
+def test_gpu_compress_stream_identical_and_round_trip(shape, explicit, dt, s, tol):
+    import torch
+    import mgard_b200.cpu as mc
+    rng = np.random.default_rng(11)
+    coords = random_coords(rng, shape, dt) if explicit else None
+    grids = np.meshgrid(*[np.linspace(0, 1, n) for n in shape], indexing="ij")
+    u = sum(np.sin((3 + k) * g) for k, g in enumerate(grids)).astype(dt) + 0.01 * rng.standard_normal(shape).astype(dt)
+    h = mo.Hierarchy(shape, dt, coords)
+    H = mc.TensorMeshHierarchy(shape, coords, dt)
+    blob = mc.compress(H, u, s, tol)
+    expect = mo.compress(h, u, s, tol)
+    assert blob == expect  # preamble + protobuf header + zlib payload, byte for byte
+    blob_dev = mc.compress(H, torch.from_numpy(u).cuda(), s, tol)
+    assert blob_dev == blob
+    if ref_cpu.available():
+        q = ref_cpu.quantize(ref_cpu.decompose(u, coords), shape, s, tol, coords)
+        hdr = len(blob) - len(ref_cpu.zlib_compress(q))
+        assert blob[hdr:] == ref_cpu.zlib_compress(q).tobytes()
+        back_ref = ref_cpu.recompose(ref_cpu.dequantize(q, shape, dt, s, tol, coords), shape, coords)
+    else:
+        q = mo.quantize(h, s, tol, mo.decompose(h, u))
+        back_ref = mo.recompose(h, mo.dequantize(h, s, tol, q))
+    back = mc.decompress(blob)
+    assert back.dtype == np.dtype(dt) and back.shape == tuple(shape)
+    assert bits_equal(back, back_ref)
+    if math.isinf(s):
+        assert np.abs(back.astype(np.float64) - u.astype(np.float64)).max() <= tol
+
+
+@pytest.mark.gpu
+def test_gpu_c1_129cubed_fp64():
+    """BASELINE config C1: 129^3 fp64, ABS 1e-4, s = inf, CPU convention."""
+    import mgard_b200.cpu as mc
+    n = 129
+    x = np.arange(n) / (n - 1)
+    x0, x1, x2 = np.meshgrid(x, x, x, indexing="ij")
+    u = np.sin(2 * np.pi * x0) * np.cos(3 * np.pi * x1) + 0.5 * np.sin(5 * np.pi * x2) + 0.25 * x0 * x1
+    H = mc.TensorMeshHierarchy((n, n, n), None, np.float64)
+    assert H.L == 7
+    blob = mc.compress(H, u, math.inf, 1e-4)
+    if ref_cpu.available():
+        q = ref_cpu.quantize(ref_cpu.decompose(u), u.shape, math.inf, 1e-4)
+        payload = ref_cpu.zlib_compress(q).tobytes()
+        h = mo.Hierarchy(u.shape, np.float64)
+        assert blob == mo.stream(h, math.inf, 1e-4, payload)
+    back = mc.decompress(blob)
+    assert np.abs(back - u).max() <= 1e-4
+    assert u.nbytes / len(blob) > 5
+
+
+@pytest.mark.gpu
+def test_gpu_c3_nonuniform_1000sq_fp32():
+    """BASELINE config C3 under the CPU convention: 1000^2 fp32, non-uniform
+    coordinates, s = 0; L = 10 with level 9 = 513^2."""
+    import mgard_b200.cpu as mc
+    n = 1000
+    coords = []
+    for k in (7, 11):
+        hsp = 1 + 0.5 * np.sin(2 * np.pi * k * np.arange(n - 1) / 999)
+        xx = np.concatenate([[0.0], np.cumsum(hsp)])
+        coords.append((xx / xx[-1]).astype(np.float32))
+    x0, x1 = np.meshgrid(coords[0].astype(np.float64), coords[1].astype(np.float64), indexing="ij")
+    u = (np.exp(-8 * ((x0 - .5) ** 2 + (x1 - .4) ** 2)) + 0.1 * np.sin(30 * x0)).astype(np.float32)
+    H = mc.TensorMeshHierarchy((n, n), coords, np.float32)
+    assert H.L == 10 and H.level_shape(9) == (513, 513)
+    blob = mc.compress(H, u, 0.0, 1e-2)
+    if ref_cpu.available():
+        c = ref_cpu.decompose(u, coords)
+        q = ref_cpu.quantize(c, u.shape, 0.0, 1e-2, coords)
+        h = mo.Hierarchy(u.shape, np.float32, coords)
+        assert blob == mo.stream(h, 0.0, 1e-2, ref_cpu.zlib_compress(q).tobytes())
+        back_ref = ref_cpu.recompose(ref_cpu.dequantize(q, u.shape, np.float32, 0.0, 1e-2, coords), u.shape, coords)
+        assert bits_equal(mc.decompress(blob), back_ref)
+    back = mc.decompress(blob)
+    # L2 error well inside the tolerance (the s = 0 bound is on the mass-weighted L2 norm)
+    assert math.sqrt(np.mean((back.astype(np.float64) - u) ** 2)) <= 1e-2
+
+
+@pytest.mark.gpu
+def test_gpu_cpu_convention_errors():
+    import mgard_b200.cpu as mc
+    from mgard_b200 import _lib
+    import mgard_b200 as mg
+    with pytest.raises(_lib.MgardError):
+        mc.TensorMeshHierarchy((1, 1))
+    with pytest.raises(_lib.MgardError):
+        mc.TensorMeshHierarchy((4,), [np.array([0.0, 0.5, 0.25, 1.0])])
+    H = mc.TensorMeshHierarchy((17, 17), None, np.float64)
+    u = np.full((17, 17), 1e300)
+    with pytest.raises(_lib.MgardError):  # "number too large to be quantized"
+        mc.compress(H, u, math.inf, 1e-300)
+    blob = mc.compress(H, np.ones((17, 17)), math.inf, 1e-3)
+    bad = bytearray(blob)
+    bad[20] ^= 0xff
+    with pytest.raises(_lib.MgardError):
+        mc.decompress(bytes(bad))
+    with pytest.raises(_lib.MgardError):
+        mc.decompress(blob[:-5])
+    # an MGARD-X stream is not a CPU stream and vice versa
+    xs = mg.compress(np.ones((17, 17), dtype=np.float32), 1e-3, math.inf, mg.error_bound_type.ABS)
+    with pytest.raises(_lib.MgardError):
+        mc.decompress(bytes(xs))
+    with pytest.raises(_lib.MgardError):
+        mg.decompress(np.frombuffer(blob, dtype=np.uint8))

@@ -236,10 +236,16 @@ int mgb_cpu_dequantize(mgb_cpu_plan *plan, const int64_t *d_q, double s,
 /* mgard::compress followed by CompressedDataset::write
  * (include/CompressedDataset.tpp:26-29): `in` is a host or device array; *out is
  * a malloc'ed host buffer holding preamble + header + payload (caller frees).
- * s = +inf selects the L-infinity norm; tol is absolute. */
+ * s = +inf selects the L-infinity norm; tol is absolute.  `compressor` is the
+ * pb::Encoding::Compressor the reference picks at build time
+ * (src/format.cpp:124-131): 1 = CPU_HUFFMAN_ZLIB (deflate level 9 of the int64
+ * quanta, src/compressors.cpp:552-606), 2 = CPU_HUFFMAN_ZSTD (the reference's
+ * default when libzstd is present: CPU Huffman coder + zstd level 1,
+ * src/compressors.cpp:316-549; histogram and bit packing run on the GPU). */
 int mgb_cpu_compress(int ndim, int dtype, const uint64_t *shape,
                      const void *const *coords, double s, double tol,
-                     const void *in, void **out, size_t *out_size);
+                     int compressor, const void *in, void **out,
+                     size_t *out_size);
 /* mgard::decompress(void const *, std::size_t) (include/compress.hpp:62-72):
  * *out is a malloc'ed host array of the decoded dtype and shape. */
 int mgb_cpu_decompress(const void *in, size_t in_size, void **out, int *ndim,

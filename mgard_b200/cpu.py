@@ -112,9 +112,14 @@ class TensorMeshHierarchy:
         return self._stage(_lib.lib().mgb_cpu_dequantize, q, dt, (float(s), float(tolerance)))
 
 
-def compress(hierarchy, v, s, tolerance):
+CPU_HUFFMAN_ZLIB, CPU_HUFFMAN_ZSTD = 1, 2  # pb::Encoding::Compressor (src/mgard.proto)
+
+
+def compress(hierarchy, v, s, tolerance, compressor=CPU_HUFFMAN_ZLIB):
     """mgard::compress + CompressedDataset::write -> bytes.  `v`: numpy array
-    (host) or torch CUDA tensor of hierarchy.shape; s = math.inf for L-infinity."""
+    (host) or torch CUDA tensor of hierarchy.shape; s = math.inf for L-infinity.
+    `compressor`: the lossless stage the reference fixes at build time --
+    CPU_HUFFMAN_ZLIB (build without zstd) or CPU_HUFFMAN_ZSTD (default build)."""
     is_torch = type(v).__module__.startswith("torch")
     if is_torch:
         v = v.contiguous()
@@ -134,7 +139,7 @@ def compress(hierarchy, v, s, tolerance):
     size = C.c_size_t()
     check(_lib.lib().mgb_cpu_compress(len(hierarchy.shape), _dtype_code(hierarchy.dtype), shp,
                                       _coord_args(hierarchy.coordinates, hierarchy.dtype, keep),
-                                      float(s), float(tolerance), ptr, C.byref(out), C.byref(size)),
+                                      float(s), float(tolerance), int(compressor), ptr, C.byref(out), C.byref(size)),
           "mgard::compress")
     try:
         return C.string_at(out.value, size.value)

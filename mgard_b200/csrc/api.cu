@@ -229,13 +229,7 @@ int ensure_bytes(unsigned char **ptr, uint64_t *have, uint64_t need) {
 // `size_t input_count | zstd frame`.  Same here, through the system's libzstd
 // (no header in this image: the four stable C entry points are resolved with
 // dlopen).  Without the library the request fails, it is never ignored.
-struct ZstdApi {
-  size_t (*compress)(void *, size_t, const void *, size_t, int) = nullptr;
-  size_t (*decompress)(void *, size_t, const void *, size_t) = nullptr;
-  size_t (*bound)(size_t) = nullptr;
-  unsigned (*is_error)(size_t) = nullptr;
-  bool ok = false;
-};
+using ZstdApi = mgb_zstd_fns;
 const ZstdApi &zstd_api() {
   static ZstdApi api = [] {
     ZstdApi a;
@@ -1082,3 +1076,6 @@ extern "C" int mgb_unpin_memory(void *ptr) {
 
 extern "C" uint64_t mgb_launch_count(void) { return g_mgb_launches; }
 extern "C" const char *mgb_version(void) { return "mgard_b200 0.1 (sm_100a)"; }
+
+// shared with cpu_convention.cu (CPU_HUFFMAN_ZSTD payload)
+const mgb_zstd_fns &mgb_zstd() { return zstd_api(); }

@@ -20,6 +20,7 @@
 #include <cstring>
 #include <limits>
 #include <mutex>
+#include <queue>
 #include <vector>
 
 #include <zlib.h>
@@ -274,6 +275,251 @@ __global__ void __launch_bounds__(128) cpu_thomas_kernel(const LevelArgs<T> a, c
     nxt = (*e - cc[j] * nxt) / dv[j];
     *e = nxt;
   }
+}
+
+// ---- CPU_HUFFMAN_ZSTD payload (reference src/compressors.cpp:70-115,140-181,316-512) ----
+// Symbols: q + nql/2 when that lies in (0, nql), else 0 with the value appended to
+// the "miss" list; a Huffman tree over the 131072-bin frequency table; codes packed
+// MSB-first into 32-bit words.  The frequency table and the packed words are built
+// on the GPU; the tree (a few hundred nodes) on the host with the reference's own
+// container (std::priority_queue) so that ties break identically.
+constexpr int NQL = 32768 * 4;
+constexpr int HCH = 4096; // symbols per block in the packing kernels
+constexpr int HTH = 256;
+constexpr int HPER = HCH / HTH;
+
+__device__ __forceinline__ int shifted_symbol(long long q, bool *hit) {
+  // build_ft (:140-160) tests the 64-bit value, huffman_encoding (:343-360) the
+  // value truncated to int; both are kept
+  const int qi = (int)(q + NQL / 2);
+  *hit = qi > 0 && qi < NQL;
+  return qi;
+}
+
+__global__ void __launch_bounds__(256) cpuhuff_hist_kernel(const long long *__restrict__ q, uint64_t n,
+                                                           unsigned *__restrict__ hist) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += stride) {
+    const uint64_t i = base + threadIdx.x;
+    const bool active = i < n;
+    int bin = 0;
+    if (active) {
+      const long long v = q[i] + NQL / 2;
+      bin = (v > 0 && v < NQL) ? (int)v : 0;
+    }
+    // one atomic per distinct bin in the warp (the data are mostly one value)
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    if (active) {
+      const unsigned peers = __match_any_sync(act, bin);
+      if ((threadIdx.x & 31) == __ffs(peers) - 1)
+        atomicAdd(&hist[bin], (unsigned)__popc(peers));
+    }
+  }
+}
+
+// per block of HCH symbols: total code bits and number of misses
+__global__ void __launch_bounds__(HTH) cpuhuff_count_kernel(const long long *__restrict__ q, uint64_t n,
+                                                            const unsigned *__restrict__ code_len,
+                                                            unsigned long long *__restrict__ blk_bits,
+                                                            unsigned *__restrict__ blk_miss) {
+  __shared__ unsigned s_bits[HTH / 32], s_miss[HTH / 32];
+  const uint64_t first = (uint64_t)blockIdx.x * HCH + (uint64_t)threadIdx.x * HPER;
+  unsigned bits = 0, miss = 0;
+  for (int k = 0; k < HPER; k++) {
+    const uint64_t i = first + k;
+    if (i < n) {
+      bool hit;
+      const int qi = shifted_symbol(q[i], &hit);
+      bits += code_len[hit ? qi : 0];
+      miss += hit ? 0u : 1u;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    bits += __shfl_down_sync(0xffffffffu, bits, o);
+    miss += __shfl_down_sync(0xffffffffu, miss, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_bits[threadIdx.x >> 5] = bits;
+    s_miss[threadIdx.x >> 5] = miss;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long b = 0;
+    unsigned m = 0;
+    for (int w = 0; w < HTH / 32; w++) {
+      b += s_bits[w];
+      m += s_miss[w];
+    }
+    blk_bits[blockIdx.x] = b;
+    blk_miss[blockIdx.x] = m;
+  }
+}
+
+// exclusive scan of the per-block totals (one block; the arrays are N / 4096 long)
+__global__ void __launch_bounds__(1024) cpuhuff_scan_kernel(unsigned long long *blk_bits, unsigned *blk_miss,
+                                                            unsigned long long *blk_miss_off, uint64_t nblk,
+                                                            unsigned long long *totals) {
+  __shared__ unsigned long long s_b[1024], s_m[1024];
+  unsigned long long carry_b = 0, carry_m = 0;
+  for (uint64_t base = 0; base < nblk; base += 1024) {
+    const uint64_t i = base + threadIdx.x;
+    const unsigned long long b = i < nblk ? blk_bits[i] : 0, m = i < nblk ? blk_miss[i] : 0;
+    s_b[threadIdx.x] = b;
+    s_m[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      unsigned long long tb = 0, tm = 0;
+      if ((int)threadIdx.x >= o) {
+        tb = s_b[threadIdx.x - o];
+        tm = s_m[threadIdx.x - o];
+      }
+      __syncthreads();
+      s_b[threadIdx.x] += tb;
+      s_m[threadIdx.x] += tm;
+      __syncthreads();
+    }
+    if (i < nblk) {
+      blk_bits[i] = carry_b + s_b[threadIdx.x] - b;
+      blk_miss_off[i] = carry_m + s_m[threadIdx.x] - m;
+    }
+    carry_b += s_b[1023];
+    carry_m += s_m[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    totals[0] = carry_b;
+    totals[1] = carry_m;
+  }
+}
+
+// huffman_encoding's packing loop (:362-384): MSB-first into zeroed 32-bit words
+__global__ void __launch_bounds__(HTH) cpuhuff_pack_kernel(const long long *__restrict__ q, uint64_t n,
+                                                           const unsigned *__restrict__ code_len,
+                                                           const unsigned *__restrict__ code_bits,
+                                                           const unsigned long long *__restrict__ blk_bits,
+                                                           const unsigned long long *__restrict__ blk_miss_off,
+                                                           unsigned *__restrict__ words, int *__restrict__ misses, int *flag) {
+  __shared__ unsigned s_bits[HTH / 32], s_miss[HTH / 32];
+  const uint64_t first = (uint64_t)blockIdx.x * HCH + (uint64_t)threadIdx.x * HPER;
+  unsigned len[HPER], code[HPER];
+  int missv[HPER];
+  unsigned bits = 0, miss = 0, missmask = 0;
+  for (int k = 0; k < HPER; k++) {
+    const uint64_t i = first + k;
+    len[k] = 0;
+    code[k] = 0;
+    if (i < n) {
+      bool hit;
+      const int qi = shifted_symbol(q[i], &hit);
+      // the reference keeps misses as int (:343,356): a wider value cannot be stored
+      if ((long long)qi != q[i] + NQL / 2)
+        *flag = 1;
+      const int sym = hit ? qi : 0;
+      len[k] = code_len[sym];
+      code[k] = code_bits[sym];
+      if (!hit) {
+        missv[k] = qi;
+        missmask |= 1u << k;
+        miss++;
+      }
+    }
+    bits += len[k];
+  }
+  // exclusive scan over the threads of the block
+  unsigned ib = bits, im = miss;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned tb = __shfl_up_sync(0xffffffffu, ib, o), tm = __shfl_up_sync(0xffffffffu, im, o);
+    if (lane >= o) {
+      ib += tb;
+      im += tm;
+    }
+  }
+  if (lane == 31) {
+    s_bits[warp] = ib;
+    s_miss[warp] = im;
+  }
+  __syncthreads();
+  unsigned wb = 0, wm = 0;
+  for (int w = 0; w < warp; w++) {
+    wb += s_bits[w];
+    wm += s_miss[w];
+  }
+  unsigned long long pos = blk_bits[blockIdx.x] + wb + (ib - bits);
+  unsigned long long mpos = blk_miss_off[blockIdx.x] + wm + (im - miss);
+  for (int k = 0; k < HPER; k++) {
+    const unsigned l = len[k];
+    if (l) {
+      const unsigned long long w = pos >> 5;
+      const unsigned room = 32 - (unsigned)(pos & 31);
+      if (room < l) {
+        const unsigned rshift = l - room;
+        atomicOr(&words[w], code[k] >> rshift);
+        atomicOr(&words[w + 1], code[k] << (32 - rshift));
+      } else {
+        atomicOr(&words[w], code[k] << (room - l));
+      }
+      pos += l;
+    }
+    if ((missmask >> k) & 1u)
+      misses[mpos++] = missv[k];
+  }
+}
+
+struct HuffNode {
+  int q;
+  size_t cnt;
+  int left, right;
+};
+
+// build_tree + build_codec (:70-115): returns false when a code would not fit
+// the reference's 32-bit code word
+bool build_cpu_huffman(const std::vector<size_t> &ft, std::vector<unsigned> &code, std::vector<unsigned> &len,
+                       std::vector<HuffNode> &nodes, int &root) {
+  struct ByCount { // LessThanByCnt (:59-63)
+    const std::vector<HuffNode> *nodes;
+    bool operator()(int a, int b) const { return (*nodes)[a].cnt > (*nodes)[b].cnt; }
+  };
+  nodes.clear();
+  nodes.reserve(2 * 4096);
+  std::priority_queue<int, std::vector<int>, ByCount> pq(ByCount{&nodes});
+  for (int i = 0; i < NQL; i++)
+    if (ft[i] != 0) {
+      nodes.push_back(HuffNode{i, ft[i], -1, -1});
+      pq.push((int)nodes.size() - 1);
+    }
+  code.assign(NQL, 0);
+  len.assign(NQL, 0);
+  root = -1;
+  if (pq.empty())
+    return true;
+  while (pq.size() > 1) {
+    const int a = pq.top();
+    pq.pop();
+    const int b = pq.top();
+    pq.pop();
+    nodes.push_back(HuffNode{-1, nodes[a].cnt + nodes[b].cnt, a, b});
+    pq.push((int)nodes.size() - 1);
+  }
+  root = pq.top();
+  // depth-first code assignment: left = 0, right = 1
+  std::vector<std::pair<int, std::pair<unsigned, unsigned>>> stack;
+  stack.push_back({root, {0u, 0u}});
+  bool ok = true;
+  while (!stack.empty()) {
+    const auto cur = stack.back();
+    stack.pop_back();
+    const HuffNode &nd = nodes[cur.first];
+    if (nd.left < 0 && nd.right < 0) {
+      code[nd.q] = cur.second.first;
+      len[nd.q] = cur.second.second;
+      ok = ok && cur.second.second <= 32;
+      continue;
+    }
+    stack.push_back({nd.right, {cur.second.first << 1 | 1u, cur.second.second + 1}});
+    stack.push_back({nd.left, {cur.second.first << 1, cur.second.second + 1}});
+  }
+  return ok;
 }
 
 } // namespace
@@ -694,6 +940,187 @@ bool have_device() {
   return true;
 }
 
+
+struct DeviceBuf {
+  void *p = nullptr;
+  ~DeviceBuf() { cudaFree(p); }
+  int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? MGB_SUCCESS : MGB_CUDA_ERROR; }
+  template <typename U> U *as() { return static_cast<U *>(p); }
+};
+
+// compress_memory_z (compressors.cpp:552-606): one deflate stream, level 9
+int zlib_payload(const void *src, size_t src_bytes, std::vector<uint8_t> &out) {
+  // the reference feeds the whole buffer through a 32-bit avail_in (:560)
+  if (src_bytes > 0xffffffffull)
+    return MGB_OUTPUT_TOO_LARGE;
+  z_stream strm;
+  memset(&strm, 0, sizeof(strm));
+  if (deflateInit(&strm, Z_BEST_COMPRESSION) != Z_OK)
+    return MGB_FAILURE;
+  const size_t bound = deflateBound(&strm, (uLong)src_bytes);
+  if (bound > 0xffffffffull) {
+    deflateEnd(&strm);
+    return MGB_OUTPUT_TOO_LARGE;
+  }
+  out.resize(bound);
+  strm.next_in = const_cast<Bytef *>(static_cast<const Bytef *>(src));
+  strm.avail_in = (uInt)src_bytes;
+  strm.next_out = out.data();
+  strm.avail_out = (uInt)bound;
+  const int zr = deflate(&strm, Z_FINISH);
+  out.resize(bound - strm.avail_out);
+  deflateEnd(&strm);
+  return zr == Z_STREAM_END ? MGB_SUCCESS : MGB_FAILURE;
+}
+
+// compress_memory_huffman, MGARD_ZSTD build (compressors.cpp:421-512): the
+// frequency table and the bit packing run on the GPU over p->d_q
+int huffman_zstd_payload(mgb_cpu_plan *p, cudaStream_t st, std::vector<uint8_t> &out) {
+  const mgb_zstd_fns &z = mgb_zstd();
+  if (!z.ok)
+    return MGB_FAILURE; // libzstd.so.1 not found: the request is never silently downgraded
+  const uint64_t n = p->N;
+  if (n >= (1ull << 32))
+    return MGB_OUTPUT_TOO_LARGE;
+  const uint64_t nblk = (n + HCH - 1) / HCH;
+  DeviceBuf hist, clen, cbits, bbits, bmiss, bmoff, totals, words, misses;
+  if (hist.alloc(NQL * 4) || clen.alloc(NQL * 4) || cbits.alloc(NQL * 4) || bbits.alloc(nblk * 8) ||
+      bmiss.alloc(nblk * 4) || bmoff.alloc(nblk * 8) || totals.alloc(16))
+    return MGB_CUDA_ERROR;
+  MGB_CUDA_CHECK(cudaMemsetAsync(hist.p, 0, NQL * 4, st));
+  MGB_LAUNCH(MGB_K_CODEBOOK, st,
+             (cpuhuff_hist_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(
+                 p->d_q, n, hist.as<unsigned>())));
+  std::vector<unsigned> h32(NQL);
+  MGB_CUDA_CHECK(cudaMemcpyAsync(h32.data(), hist.p, NQL * 4, cudaMemcpyDeviceToHost, st));
+  MGB_CUDA_CHECK(cudaStreamSynchronize(st));
+  std::vector<size_t> ft(h32.begin(), h32.end());
+  std::vector<unsigned> code, len;
+  std::vector<HuffNode> nodes;
+  int root = -1;
+  if (!build_cpu_huffman(ft, code, len, nodes, root))
+    return MGB_FAILURE; // a code longer than the reference's 32-bit code word
+  MGB_CUDA_CHECK(cudaMemcpyAsync(clen.p, len.data(), NQL * 4, cudaMemcpyHostToDevice, st));
+  MGB_CUDA_CHECK(cudaMemcpyAsync(cbits.p, code.data(), NQL * 4, cudaMemcpyHostToDevice, st));
+  MGB_LAUNCH(MGB_K_CHUNK_BITS, st,
+             (cpuhuff_count_kernel<<<(unsigned)nblk, HTH, 0, st>>>(p->d_q, n, clen.as<unsigned>(),
+                                                                  bbits.as<unsigned long long>(), bmiss.as<unsigned>())));
+  MGB_LAUNCH(MGB_K_CHUNK_SCAN, st,
+             (cpuhuff_scan_kernel<<<1, 1024, 0, st>>>(bbits.as<unsigned long long>(), bmiss.as<unsigned>(),
+                                                      bmoff.as<unsigned long long>(), nblk,
+                                                      totals.as<unsigned long long>())));
+  unsigned long long tot[2] = {0, 0};
+  MGB_CUDA_CHECK(cudaMemcpyAsync(tot, totals.p, 16, cudaMemcpyDeviceToHost, st));
+  MGB_CUDA_CHECK(cudaStreamSynchronize(st));
+  const size_t hit_bits = tot[0], nmiss = tot[1];
+  const size_t hit_bytes = hit_bits / 8 + 4; // as the reference copies (:452-453)
+  const size_t word_bytes = ((hit_bits + 31) / 32 + 2) * 4;
+  if (words.alloc(word_bytes) || misses.alloc(nmiss * 4))
+    return MGB_CUDA_ERROR;
+  MGB_CUDA_CHECK(cudaMemsetAsync(words.p, 0, word_bytes, st));
+  MGB_LAUNCH(MGB_K_ENCODE, st,
+             (cpuhuff_pack_kernel<<<(unsigned)nblk, HTH, 0, st>>>(
+                 p->d_q, n, clen.as<unsigned>(), cbits.as<unsigned>(), bbits.as<unsigned long long>(),
+                 bmoff.as<unsigned long long>(), words.as<unsigned>(), misses.as<int>(), p->d_flag)));
+  {
+    const int frc = check_flag(p, st);
+    if (frc)
+      return frc;
+  }
+  // payload = frequency pairs | packed codes | misses (:447-463)
+  size_t nonzero = 0;
+  for (int i = 0; i < NQL; i++)
+    nonzero += ft[i] > 0;
+  const size_t tree_bytes = 2 * nonzero * sizeof(size_t), miss_bytes = nmiss * sizeof(int);
+  std::vector<uint8_t> payload(tree_bytes + hit_bytes + miss_bytes);
+  {
+    size_t *cft = reinterpret_cast<size_t *>(payload.data());
+    size_t off = 0;
+    for (int i = 0; i < NQL; i++)
+      if (ft[i] > 0) {
+        cft[2 * off] = (size_t)i;
+        cft[2 * off + 1] = ft[i];
+        off++;
+      }
+  }
+  MGB_CUDA_CHECK(cudaMemcpyAsync(payload.data() + tree_bytes, words.p, hit_bytes, cudaMemcpyDeviceToHost, st));
+  if (miss_bytes)
+    MGB_CUDA_CHECK(cudaMemcpyAsync(payload.data() + tree_bytes + hit_bytes, misses.p, miss_bytes,
+                                   cudaMemcpyDeviceToHost, st));
+  MGB_CUDA_CHECK(cudaStreamSynchronize(st));
+  // compress_memory_zstd (:542-549): level 1; then the three sizes in front (:494-511)
+  const size_t bound = z.bound(payload.size());
+  out.resize(3 * sizeof(size_t) + bound);
+  const size_t csize = z.compress(out.data() + 3 * sizeof(size_t), bound, payload.data(), payload.size(), 1);
+  if (z.is_error(csize))
+    return MGB_FAILURE;
+  size_t head[3] = {tree_bytes, hit_bits, miss_bytes};
+  memcpy(out.data(), head, sizeof(head));
+  out.resize(3 * sizeof(size_t) + csize);
+  return MGB_SUCCESS;
+}
+
+// decompress_memory_huffman + huffman_decoding (compressors.cpp:183-314): the
+// stream carries no block index, so the bit-serial walk runs on the host
+int huffman_zstd_decode(const uint8_t *src, size_t src_bytes, std::vector<long long> &q) {
+  const mgb_zstd_fns &z = mgb_zstd();
+  if (!z.ok)
+    return MGB_FAILURE;
+  if (src_bytes < 3 * sizeof(size_t))
+    return MGB_BAD_STREAM;
+  size_t head[3];
+  memcpy(head, src, sizeof(head));
+  const size_t tree_bytes = head[0], hit_bits = head[1], miss_bytes = head[2];
+  if (tree_bytes % (2 * sizeof(size_t)) || miss_bytes % sizeof(int) || tree_bytes > (size_t)NQL * 16 ||
+      hit_bits / 8 > q.size() * 4 + 8 || miss_bytes > q.size() * 4)
+    return MGB_BAD_STREAM;
+  const size_t hit_bytes = hit_bits / 8 + 4;
+  std::vector<uint8_t> payload(tree_bytes + hit_bytes + miss_bytes);
+  const size_t got = z.decompress(payload.data(), payload.size(), src + 3 * sizeof(size_t), src_bytes - 3 * sizeof(size_t));
+  if (z.is_error(got) || got != payload.size())
+    return MGB_BAD_STREAM;
+  std::vector<size_t> ft(NQL, 0);
+  {
+    std::vector<size_t> cft(tree_bytes / sizeof(size_t));
+    memcpy(cft.data(), payload.data(), tree_bytes);
+    for (size_t j = 0; j + 1 < cft.size(); j += 2) {
+      if (cft[j] >= (size_t)NQL)
+        return MGB_BAD_STREAM;
+      ft[cft[j]] = cft[j + 1];
+    }
+  }
+  std::vector<unsigned> code, len;
+  std::vector<HuffNode> nodes;
+  int root = -1;
+  build_cpu_huffman(ft, code, len, nodes, root);
+  if (root < 0)
+    return q.empty() ? MGB_SUCCESS : MGB_BAD_STREAM;
+  std::vector<unsigned> words((hit_bytes + 3) / 4 + 1, 0);
+  memcpy(words.data(), payload.data() + tree_bytes, hit_bytes);
+  std::vector<int> miss(miss_bytes / sizeof(int));
+  if (miss_bytes)
+    memcpy(miss.data(), payload.data() + tree_bytes + hit_bytes, miss_bytes);
+  size_t bit = 0, next_miss = 0;
+  for (size_t i = 0; i < q.size(); i++) {
+    int node = root;
+    while (nodes[node].left >= 0) {
+      if (bit >= hit_bits)
+        return MGB_BAD_STREAM;
+      const unsigned flag = words[bit >> 5] & (0x80000000u >> (bit & 31));
+      node = flag ? nodes[node].right : nodes[node].left;
+      bit++;
+    }
+    if (nodes[node].q != 0) {
+      q[i] = (long long)nodes[node].q - NQL / 2;
+    } else {
+      if (next_miss >= miss.size())
+        return MGB_BAD_STREAM;
+      q[i] = (long long)miss[next_miss++] - NQL / 2;
+    }
+  }
+  return bit == hit_bits && next_miss == miss.size() ? MGB_SUCCESS : MGB_BAD_STREAM;
+}
+
 } // namespace
 
 extern "C" {
@@ -838,8 +1265,8 @@ int mgb_cpu_dequantize(mgb_cpu_plan *p, const int64_t *d_q, double s, double tol
 
 // mgard::compress + CompressedDataset::write (compress.tpp:35-67, CompressedDataset.tpp:26-29).
 int mgb_cpu_compress(int ndim, int dtype, const uint64_t *shape, const void *const *coords, double s, double tol,
-                     const void *in, void **out, size_t *out_size) {
-  if (!in || !out || !out_size || !(tol > 0))
+                     int compressor, const void *in, void **out, size_t *out_size) {
+  if (!in || !out || !out_size || !(tol > 0) || (compressor != 1 && compressor != 2))
     return MGB_BAD_ARGUMENT;
   mgb_cpu_plan *p = nullptr;
   int rc = mgb_cpu_plan_create(ndim, shape, dtype, coords, &p);
@@ -849,10 +1276,6 @@ int mgb_cpu_compress(int ndim, int dtype, const uint64_t *shape, const void *con
     mgb_cpu_plan *p;
     ~Guard() { delete p; }
   } guard{p};
-  // compress_memory_z feeds the whole buffer through a 32-bit avail_in
-  // (compressors.cpp:560): larger inputs are not representable in this format
-  if (p->N * sizeof(long long) > 0xffffffffull)
-    return MGB_OUTPUT_TOO_LARGE;
   rc = ensure_workspace(p, true);
   if (rc)
     return rc;
@@ -865,11 +1288,20 @@ int mgb_cpu_compress(int ndim, int dtype, const uint64_t *shape, const void *con
   rc = check_flag(p, st);
   if (rc)
     return rc;
-  std::vector<long long> q(p->N);
-  MGB_CUDA_CHECK(cudaMemcpy(q.data(), p->d_q, p->N * sizeof(long long), cudaMemcpyDeviceToHost));
+  std::vector<uint8_t> payload;
+  if (compressor == 2) {
+    rc = huffman_zstd_payload(p, st, payload);
+  } else {
+    std::vector<long long> q(p->N);
+    MGB_CUDA_CHECK(cudaMemcpy(q.data(), p->d_q, p->N * sizeof(long long), cudaMemcpyDeviceToHost));
+    rc = zlib_payload(q.data(), q.size() * sizeof(long long), payload);
+  }
+  if (rc)
+    return rc;
 
   mgb_header h;
   h.convention = 1;
+  h.cpu_compressor = compressor;
   h.ndim = ndim;
   h.dtype = dtype;
   for (int d = 0; d < ndim; d++)
@@ -881,33 +1313,13 @@ int mgb_cpu_compress(int ndim, int dtype, const uint64_t *shape, const void *con
   if (!p->uniform)
     h.coords = p->coords;
   const std::vector<uint8_t> head = mgb_encode_stream_header(h);
-
-  // compress_memory_z (compressors.cpp:552-606): one deflate stream, level 9
-  z_stream strm;
-  memset(&strm, 0, sizeof(strm));
-  if (deflateInit(&strm, Z_BEST_COMPRESSION) != Z_OK)
+  uint8_t *buf = (uint8_t *)malloc(head.size() + payload.size());
+  if (!buf)
     return MGB_FAILURE;
-  const size_t src_bytes = q.size() * sizeof(long long);
-  const size_t bound = deflateBound(&strm, (uLong)src_bytes);
-  uint8_t *buf = (uint8_t *)malloc(head.size() + bound);
-  if (!buf) {
-    deflateEnd(&strm);
-    return MGB_FAILURE;
-  }
   memcpy(buf, head.data(), head.size());
-  strm.next_in = reinterpret_cast<Bytef *>(q.data());
-  strm.avail_in = (uInt)src_bytes;
-  strm.next_out = buf + head.size();
-  strm.avail_out = (uInt)std::min<size_t>(bound, 0xffffffffu);
-  const int zr = deflate(&strm, Z_FINISH);
-  const size_t payload = bound - strm.avail_out;
-  deflateEnd(&strm);
-  if (zr != Z_STREAM_END) {
-    free(buf);
-    return MGB_FAILURE;
-  }
+  memcpy(buf + head.size(), payload.data(), payload.size());
   *out = buf;
-  *out_size = head.size() + payload;
+  *out_size = head.size() + payload.size();
   return MGB_SUCCESS;
 }
 
@@ -951,9 +1363,12 @@ int mgb_cpu_decompress(const void *in, size_t in_size, void **out, int *ndim, ui
   rc = ensure_workspace(p, true);
   if (rc)
     return rc;
-  // decompress_memory_z (compressors.cpp:608-629)
   std::vector<long long> q(p->N);
-  {
+  if (h.cpu_compressor == 2) {
+    rc = huffman_zstd_decode((const uint8_t *)in + hb, in_size - hb, q);
+    if (rc)
+      return rc;
+  } else { // decompress_memory_z (compressors.cpp:608-629)
     z_stream strm;
     memset(&strm, 0, sizeof(strm));
     strm.next_in = const_cast<Bytef *>((const Bytef *)in + hb);

@@ -179,7 +179,7 @@ std::vector<uint8_t> encode_cpu_header(const mgb_header &h) {
   f_varint(quant, 3, 3); // INT64_T
   std::string enc;
   f_varint(enc, 1, 1); // SHUFFLE
-  f_varint(enc, 2, 1); // CPU_HUFFMAN_ZLIB
+  f_varint(enc, 2, (uint64_t)h.cpu_compressor); // CPU_HUFFMAN_ZLIB = 1 / CPU_HUFFMAN_ZSTD = 2
   std::string hdr;
   f_msg(hdr, 2, ver);
   f_msg(hdr, 3, fver);
@@ -411,9 +411,10 @@ int mgb_parse_stream_header(const uint8_t *data, size_t size, mgb_header &h,
   if (major > 1)
     return MGB_BAD_STREAM;
   // MGARD-X multi-dimensional Huffman (+ Zstd) streams, or MGARD-CPU streams
-  // with the zlib payload (CPU_HUFFMAN_ZSTD needs the CPU Huffman coder: not built)
-  if (hierarchy == 0 && compressor == 1) {
+  // (zlib or CPU Huffman + zstd payload)
+  if (hierarchy == 0 && (compressor == 1 || compressor == 2)) {
     h.convention = 1;
+    h.cpu_compressor = compressor;
     if (quant_type != 3 || h.ebtype != MGB_ABS)
       return MGB_BAD_STREAM;
   } else if (hierarchy != 1 || (compressor != 3 && compressor != 5) || preprocessor != 0) {

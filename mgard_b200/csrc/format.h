@@ -18,6 +18,7 @@ struct mgb_header {
   // 0: MGARD-X stream (Metadata.cpp); 1: MGARD-CPU stream (src/format.cpp:110-140:
   // POWER_OF_TWO_PLUS_ONE hierarchy, SHUFFLE preprocessor, CPU_HUFFMAN_ZLIB payload)
   int convention = 0;
+  int cpu_compressor = 1; // pb::Encoding::Compressor of an MGARD-CPU stream: 1 zlib, 2 Huffman + zstd
   std::vector<std::vector<double>> coords; // empty: uniform grid
 };
 

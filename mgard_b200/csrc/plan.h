@@ -105,6 +105,16 @@ inline bool mgb_first_use_on_device(bool (&seen)[64]) {
   return true;
 }
 
+// api.cu: the system's libzstd resolved with dlopen (no header in this image)
+struct mgb_zstd_fns {
+  size_t (*compress)(void *, size_t, const void *, size_t, int) = nullptr;
+  size_t (*decompress)(void *, size_t, const void *, size_t) = nullptr;
+  size_t (*bound)(size_t) = nullptr;
+  unsigned (*is_error)(size_t) = nullptr;
+  bool ok = false;
+};
+const mgb_zstd_fns &mgb_zstd();
+
 // plan.cu
 int mgb_plan_ensure_workspace(mgb_plan *p);
 uint64_t mgb_level_elems(const mgb_plan *p, int l);

@@ -390,11 +390,12 @@ def _f_msg(field, body):
     return _varint((field << 3) | 2) + _varint(len(body)) + body
 
 
-def header_bytes(h, s, tol):
+def header_bytes(h, s, tol, compressor=1):
     """The protobuf header mgard::compress builds (populate_defaults,
     reference src/format.cpp:102-140; TensorMeshHierarchy::populate,
     include/TensorMeshHierarchy.tpp:293-348; error control, compress.tpp:45-55)
-    in proto3 canonical form (src/mgard.proto), for a build without MGARD_ZSTD."""
+    in proto3 canonical form (src/mgard.proto); compressor 1 = CPU_HUFFMAN_ZLIB
+    (build without MGARD_ZSTD), 2 = CPU_HUFFMAN_ZSTD (default build)."""
     import struct
     topo = _f_varint(1, h.N) + _f_msg(2, b"".join(_varint(n) for n in h.shape))
     dom = _f_msg(2, topo)
@@ -412,20 +413,138 @@ def header_bytes(h, s, tol):
     hdr += _f_msg(6, err)
     hdr += _f_msg(8, b"")
     hdr += _f_msg(9, _f_varint(1, 1) + _f_varint(3, 3))
-    hdr += _f_msg(11, _f_varint(1, 1) + _f_varint(2, 1))
+    hdr += _f_msg(11, _f_varint(1, 1) + _f_varint(2, compressor))
     hdr += _f_msg(12, b"")
     return hdr
 
 
-def stream(h, s, tol, payload):
+def stream(h, s, tol, payload, compressor=1):
     """CompressedDataset::write (reference include/CompressedDataset.tpp:26-29)
     with write_metadata (src/format.cpp:219-233): magic, u64 header size, u32
     CRC32 of the header, header, payload."""
     import struct
-    hdr = header_bytes(h, s, tol)
+    hdr = header_bytes(h, s, tol, compressor)
     return b"MGARD" + struct.pack("<Q", len(hdr)) + struct.pack("<I", zlib.crc32(hdr)) + hdr + bytes(payload)
 
 
-def compress(h, u, s, tol):
+def compress(h, u, s, tol, compressor=1):
     """mgard::compress (reference include/compress.tpp:35-67) + write."""
-    return stream(h, s, tol, zlib_payload(quantize(h, s, tol, decompose(h, u))))
+    q = quantize(h, s, tol, decompose(h, u))
+    return stream(h, s, tol, zlib_payload(q) if compressor == 1 else huffman_zstd_payload(q), compressor)
+
+
+# ---- CPU_HUFFMAN_ZSTD payload (reference src/compressors.cpp, MGARD_ZSTD build) ----
+NQL = 32768 * 4
+
+
+def _push_heap(heap, hole, top, value, cnt):
+    # libstdc++ std::__push_heap with LessThanByCnt (compressors.cpp:59-63): the
+    # reference's std::priority_queue decides how equal counts are ordered, so the
+    # container's algorithm is restated rather than replaced by heapq
+    parent = (hole - 1) // 2
+    while hole > top and cnt[heap[parent]] > cnt[value]:
+        heap[hole] = heap[parent]
+        hole = parent
+        parent = (hole - 1) // 2
+    heap[hole] = value
+
+
+def _pq_push(heap, value, cnt):
+    heap.append(value)
+    _push_heap(heap, len(heap) - 1, 0, value, cnt)
+
+
+def _pq_pop(heap, cnt):
+    # std::pop_heap (std::__pop_heap + std::__adjust_heap) then pop_back
+    top = heap[0]
+    value = heap[-1]
+    length = len(heap) - 1
+    if length > 0:
+        hole, child = 0, 0
+        while child < (length - 1) // 2:
+            child = 2 * (child + 1)
+            if cnt[heap[child]] > cnt[heap[child - 1]]:
+                child -= 1
+            heap[hole] = heap[child]
+            hole = child
+        if (length & 1) == 0 and child == (length - 2) // 2:
+            child = 2 * (child + 1)
+            heap[hole] = heap[child - 1]
+            hole = child - 1
+        _push_heap(heap, hole, 0, value, cnt)
+    heap.pop()
+    return top
+
+
+def huffman_codes(ft):
+    """build_tree + build_codec (compressors.cpp:70-115): {symbol: (code, len)}."""
+    cnt, sym, left, right, heap = [], [], [], [], []
+    for i in np.nonzero(ft)[0]:
+        cnt.append(int(ft[i])); sym.append(int(i)); left.append(-1); right.append(-1)
+        _pq_push(heap, len(cnt) - 1, cnt)
+    if not heap:
+        return {}
+    while len(heap) > 1:
+        a = _pq_pop(heap, cnt)
+        b = _pq_pop(heap, cnt)
+        cnt.append(cnt[a] + cnt[b]); sym.append(-1); left.append(a); right.append(b)
+        _pq_push(heap, len(cnt) - 1, cnt)
+    codes, stack = {}, [(heap[0], 0, 0)]
+    while stack:
+        node, code, length = stack.pop()
+        if left[node] < 0:
+            codes[sym[node]] = (code, length)
+        else:
+            stack.append((left[node], code << 1, length + 1))
+            stack.append((right[node], (code << 1) | 1, length + 1))
+    return codes
+
+
+def huffman_payload(ints):
+    """huffman_encoding + the concatenation of compress_memory_huffman
+    (compressors.cpp:316-463): returns (tree_bytes, hit_bits, miss_bytes, payload)
+    before the zstd stage."""
+    import struct
+    q = np.asarray(ints, dtype=np.int64) + NQL // 2
+    qi = q.astype(np.int32)  # `int q = quantized_data[i]` (:343)
+    inrange64 = (q > 0) & (q < NQL)
+    ft = np.bincount(np.where(inrange64, q, 0), minlength=NQL)
+    codes = huffman_codes(ft)
+    hit = (qi > 0) & (qi < NQL)
+    symbols = np.where(hit, qi, 0)
+    length = np.zeros(NQL, dtype=np.int64)
+    code = np.zeros(NQL, dtype=np.uint64)
+    for sym_, (c, l) in codes.items():
+        code[sym_], length[sym_] = c, l
+    lens = length[symbols]
+    cds = code[symbols]
+    total = int(lens.sum())
+    bits = np.zeros(total, dtype=np.uint8)
+    starts = np.cumsum(lens) - lens
+    for b in range(int(lens.max()) if lens.size else 0):
+        sel = lens > b
+        bits[starts[sel] + b] = ((cds[sel] >> (lens[sel] - 1 - b).astype(np.uint64)) & np.uint64(1)).astype(np.uint8)
+    nwords = (total // 8 + 4 + 3) // 4 + 1
+    padded = np.zeros(nwords * 32, dtype=np.uint8)
+    padded[:total] = bits
+    words = np.packbits(padded).view(">u4").astype("<u4")  # MSB-first 32-bit words
+    hit_bytes = words.tobytes()[: total // 8 + 4]
+    tree = b"".join(struct.pack("<QQ", int(i), int(ft[i])) for i in np.nonzero(ft)[0])
+    miss = qi[~hit].astype("<i4").tobytes()
+    return len(tree), total, len(miss), tree + hit_bytes + miss
+
+
+def huffman_zstd_payload(ints):
+    """compress_memory_huffman (compressors.cpp:421-512): three sizes, then the
+    zstd level-1 frame (compress_memory_zstd, :542-549) from the system libzstd."""
+    import struct
+    tree_bytes, hit_bits, miss_bytes, payload = huffman_payload(ints)
+    z = ctypes.CDLL("libzstd.so.1")
+    z.ZSTD_compressBound.restype = ctypes.c_size_t
+    z.ZSTD_compressBound.argtypes = [ctypes.c_size_t]
+    z.ZSTD_compress.restype = ctypes.c_size_t
+    z.ZSTD_compress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int]
+    cap = z.ZSTD_compressBound(len(payload))
+    dst = ctypes.create_string_buffer(cap)
+    n = z.ZSTD_compress(dst, cap, payload, len(payload), 1)
+    return struct.pack("<QQQ", tree_bytes, hit_bits, miss_bytes) + dst.raw[:n]

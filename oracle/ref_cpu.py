@@ -123,3 +123,41 @@ def zlib_decompress(buf, nbytes):
     out = np.empty(nbytes, dtype=np.uint8)
     lib().refcpu_zlib_decompress(buf.ctypes.data, buf.size, out.ctypes.data, nbytes)
     return out
+
+
+# ---- CPU_HUFFMAN_ZSTD payload: src/compressors.cpp built with -DMGARD_ZSTD ----
+_ZLIB_PATH = os.path.join(_HERE, "_ref", "libmgard_cpu_ref_zstd.so")
+_zlib_lib = None
+
+
+def zstd_available():
+    return os.path.exists(_ZLIB_PATH)
+
+
+def _zstd_lib():
+    global _zlib_lib
+    if _zlib_lib is None:
+        _zlib_lib = C.CDLL(_ZLIB_PATH)
+        _zlib_lib.refcpu_huffman_zstd_compress.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        _zlib_lib.refcpu_huffman_zstd_compress.restype = C.c_int64
+        _zlib_lib.refcpu_huffman_zstd_decompress.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        _zlib_lib.refcpu_huffman_zstd_decompress.restype = None
+    return _zlib_lib
+
+
+def huffman_zstd_compress(q):
+    """compress_memory_huffman (reference src/compressors.cpp:421-512)."""
+    q = np.ascontiguousarray(q, dtype=np.int64)
+    cap = q.nbytes + q.nbytes // 2 + (1 << 22)
+    out = np.empty(cap, dtype=np.uint8)
+    n = _zstd_lib().refcpu_huffman_zstd_compress(q.ctypes.data, q.size, out.ctypes.data, cap)
+    assert n >= 0
+    return out[:n].copy()
+
+
+def huffman_zstd_decompress(buf, count):
+    """decompress_memory_huffman (reference src/compressors.cpp:273-314)."""
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    out = np.empty(count, dtype=np.int64)
+    _zstd_lib().refcpu_huffman_zstd_decompress(buf.ctypes.data, buf.size, out.ctypes.data, out.nbytes)
+    return out

@@ -157,6 +157,42 @@ def test_oracle_matches_reference_build(shape, explicit, dt):
     assert ref_cpu.zlib_compress(q).tobytes() == mo.zlib_payload(q)
 
 
+needs_ref_zstd = pytest.mark.skipif(not ref_cpu.zstd_available(),
+                                    reason="oracle/_ref/libmgard_cpu_ref_zstd.so not built")
+
+
+def _quanta_cases():
+    rng = np.random.default_rng(5)
+    cases = []
+    for n, scale in [(200000, 30), (5000, 3), (17, 1), (1, 1), (70000, 2000), (3000, 0), (40000, 1e5)]:
+        q = np.round(rng.standard_normal(n) * scale).astype(np.int64)
+        if n >= 70000:  # misses, and the edges of the in-range window (0, 131072) after the shift
+            q[::5000] = 10 ** 7
+            q[7], q[9], q[10], q[11], q[12] = -10 ** 6, 65535, 65536, -65536, -65535
+        cases.append(q)
+    return cases
+
+
+@needs_ref_zstd
+def test_oracle_huffman_zstd_matches_reference_build():
+    """CPU_HUFFMAN_ZSTD payload: tree ties (std::priority_queue order), MSB-first
+    32-bit packing, miss list, zstd frame -- byte for byte."""
+    for q in _quanta_cases():
+        ref = ref_cpu.huffman_zstd_compress(q).tobytes()
+        assert mo.huffman_zstd_payload(q) == ref
+        assert np.array_equal(ref_cpu.huffman_zstd_decompress(np.frombuffer(ref, np.uint8), q.size), q)
+
+
+def test_oracle_huffman_codes_are_prefix_free_and_optimal_length():
+    rng = np.random.default_rng(3)
+    ft = np.zeros(mo.NQL, dtype=np.int64)
+    ft[rng.integers(1, mo.NQL, 300)] = rng.integers(1, 1000, 300)
+    codes = mo.huffman_codes(ft)
+    words = sorted(format(c, "b").zfill(l) for c, l in codes.values())
+    assert all(not b.startswith(a) for a, b in zip(words, words[1:]))
+    assert abs(sum(2.0 ** -l for _, l in codes.values()) - 1.0) < 1e-12  # Kraft equality
+
+
 def test_cpu_convention_symbols_and_no_gpu_behaviour():
     import torch
     from mgard_b200 import _lib
@@ -328,3 +364,64 @@ def test_gpu_cpu_convention_errors():
         mc.decompress(bytes(xs))
     with pytest.raises(_lib.MgardError):
         mg.decompress(np.frombuffer(blob, dtype=np.uint8))
+
+
+@pytest.mark.gpu
+def test_gpu_cxx_cpu_api_mirror(tmp_path):
+    """include/mgard_b200/compress.hpp (mgard::compress / decompress mirror)."""
+    import subprocess
+    exe = tmp_path / "cpu_api_roundtrip"
+    subprocess.check_call(["g++", "-std=c++17", f"-I{ROOT}/include", f"{ROOT}/tests/cxx/cpu_api_roundtrip.cpp",
+                           "-o", str(exe), f"-L{ROOT}/mgard_b200", "-lmgard_b200",
+                           f"-Wl,-rpath,{ROOT}/mgard_b200", "-L/usr/local/cuda/lib64", "-lcudart"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "self-describing decompress identical" in out.stdout and "degenerate shape rejected" in out.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,explicit,dt,s,tol", [
+    ((33, 20, 17), True, np.float64, math.inf, 1e-3),
+    ((100, 65), True, np.float32, 0.0, 1e-2),
+    ((65, 65, 65), False, np.float32, math.inf, 1e-6),   # wide quanta: many misses
+    ((300,), False, np.float64, 1.0, 1e-2),
+    ((40, 40), False, np.float64, math.inf, 10.0),       # every quantum is zero: one-leaf tree
+])
+def test_gpu_huffman_zstd_stream_identical_and_round_trip(shape, explicit, dt, s, tol):
+    """CPU_HUFFMAN_ZSTD (the reference's default lossless stage): histogram and bit
+    packing on the GPU, tree on the host -- stream equal to the oracle's and, where
+    built, to the reference's compress_memory_huffman."""
+    import mgard_b200.cpu as mc
+    rng = np.random.default_rng(13)
+    coords = random_coords(rng, shape, dt) if explicit else None
+    grids = np.meshgrid(*[np.linspace(0, 1, n) for n in shape], indexing="ij")
+    u = sum(np.sin((3 + k) * g) for k, g in enumerate(grids)).astype(dt) + 0.01 * rng.standard_normal(shape).astype(dt)
+    h = mo.Hierarchy(shape, dt, coords)
+    H = mc.TensorMeshHierarchy(shape, coords, dt)
+    blob = mc.compress(H, u, s, tol, mc.CPU_HUFFMAN_ZSTD)
+    q = mo.quantize(h, s, tol, mo.decompose(h, u))
+    assert blob == mo.stream(h, s, tol, mo.huffman_zstd_payload(q), 2)
+    if ref_cpu.zstd_available():
+        assert blob.endswith(ref_cpu.huffman_zstd_compress(q).tobytes())
+    back = mc.decompress(blob)
+    assert bits_equal(back, mo.recompose(h, mo.dequantize(h, s, tol, q)))
+    assert bits_equal(back, mc.decompress(mc.compress(H, u, s, tol, mc.CPU_HUFFMAN_ZLIB)))
+    if math.isinf(s):
+        assert np.abs(back.astype(np.float64) - u.astype(np.float64)).max() <= tol
+
+
+@pytest.mark.gpu
+def test_gpu_reads_reference_written_huffman_zstd_stream():
+    """A stream whose payload the reference itself wrote decodes to the
+    reference's reconstruction."""
+    if not (ref_cpu.available() and ref_cpu.zstd_available()):
+        pytest.skip("reference builds not present")
+    import mgard_b200.cpu as mc
+    shape, dt, s, tol = (33, 20, 17), np.float64, math.inf, 1e-3
+    rng = np.random.default_rng(17)
+    u = rng.standard_normal(shape)
+    q = ref_cpu.quantize(ref_cpu.decompose(u), shape, s, tol)
+    h = mo.Hierarchy(shape, dt)
+    blob = mo.stream(h, s, tol, ref_cpu.huffman_zstd_compress(q).tobytes(), 2)
+    expect = ref_cpu.recompose(ref_cpu.dequantize(q, shape, dt, s, tol), shape)
+    assert bits_equal(mc.decompress(blob), expect)

@@ -1095,14 +1095,34 @@ int huffman_zstd_decode(const uint8_t *src, size_t src_bytes, std::vector<long l
   build_cpu_huffman(ft, code, len, nodes, root);
   if (root < 0)
     return q.empty() ? MGB_SUCCESS : MGB_BAD_STREAM;
-  std::vector<unsigned> words((hit_bytes + 3) / 4 + 1, 0);
+  std::vector<unsigned> words((hit_bytes + 3) / 4 + 3, 0);
   memcpy(words.data(), payload.data() + tree_bytes, hit_bytes);
   std::vector<int> miss(miss_bytes / sizeof(int));
   if (miss_bytes)
     memcpy(miss.data(), payload.data() + tree_bytes + hit_bytes, miss_bytes);
+  // the reference walks the tree bit by bit (:211-229); same walk, with the first
+  // LUT_BITS steps of every symbol taken from a table
+  constexpr int LUT_BITS = 12;
+  struct Step {
+    int node;
+    int used;
+  };
+  std::vector<Step> lut(1u << LUT_BITS);
+  for (unsigned v = 0; v < (1u << LUT_BITS); v++) {
+    int node = root, used = 0;
+    while (nodes[node].left >= 0 && used < LUT_BITS) {
+      node = (v >> (LUT_BITS - 1 - used)) & 1u ? nodes[node].right : nodes[node].left;
+      used++;
+    }
+    lut[v] = Step{node, used};
+  }
   size_t bit = 0, next_miss = 0;
   for (size_t i = 0; i < q.size(); i++) {
-    int node = root;
+    const size_t w = bit >> 5;
+    const unsigned long long window = ((unsigned long long)words[w] << 32) | words[w + 1];
+    const unsigned v = (unsigned)(window >> (64 - LUT_BITS - (bit & 31))) & ((1u << LUT_BITS) - 1);
+    int node = lut[v].node;
+    bit += lut[v].used;
     while (nodes[node].left >= 0) {
       if (bit >= hit_bits)
         return MGB_BAD_STREAM;
@@ -1110,6 +1130,8 @@ int huffman_zstd_decode(const uint8_t *src, size_t src_bytes, std::vector<long l
       node = flag ? nodes[node].right : nodes[node].left;
       bit++;
     }
+    if (bit > hit_bits)
+      return MGB_BAD_STREAM;
     if (nodes[node].q != 0) {
       q[i] = (long long)nodes[node].q - NQL / 2;
     } else {
@@ -1125,8 +1147,8 @@ int huffman_zstd_decode(const uint8_t *src, size_t src_bytes, std::vector<long l
 
 extern "C" {
 
-int mgb_cpu_plan_create(int ndim, const uint64_t *shape, int dtype, const void *const *coords,
-                        mgb_cpu_plan **plan) {
+static int cpu_plan_create_impl(int ndim, const uint64_t *shape, int dtype, const void *const *coords,
+                                mgb_cpu_plan **plan) {
   if (!plan || !shape)
     return MGB_BAD_ARGUMENT;
   *plan = nullptr;
@@ -1148,6 +1170,10 @@ int mgb_cpu_plan_create(int ndim, const uint64_t *shape, int dtype, const void *
     p->shape[pad + d] = shape[d];
     p->user_shape[d] = shape[d];
     if (shape[d] == 0 || shape[d] >= (1ull << 32)) {
+      delete p;
+      return MGB_BAD_ARGUMENT;
+    }
+    if (p->N > (1ull << 40) / shape[d]) { // also keeps every product below 2^63
       delete p;
       return MGB_BAD_ARGUMENT;
     }
@@ -1264,8 +1290,8 @@ int mgb_cpu_dequantize(mgb_cpu_plan *p, const int64_t *d_q, double s, double tol
 }
 
 // mgard::compress + CompressedDataset::write (compress.tpp:35-67, CompressedDataset.tpp:26-29).
-int mgb_cpu_compress(int ndim, int dtype, const uint64_t *shape, const void *const *coords, double s, double tol,
-                     int compressor, const void *in, void **out, size_t *out_size) {
+static int cpu_compress_impl(int ndim, int dtype, const uint64_t *shape, const void *const *coords, double s,
+                             double tol, int compressor, const void *in, void **out, size_t *out_size) {
   if (!in || !out || !out_size || !(tol > 0) || (compressor != 1 && compressor != 2))
     return MGB_BAD_ARGUMENT;
   mgb_cpu_plan *p = nullptr;
@@ -1325,7 +1351,8 @@ int mgb_cpu_compress(int ndim, int dtype, const uint64_t *shape, const void *con
 
 // mgard::decompress(void const *, size_t) (compress.tpp:69-83 behind the header
 // dispatch of include/compress.hpp:62-72).  *out is malloc'ed (host).
-int mgb_cpu_decompress(const void *in, size_t in_size, void **out, int *ndim, uint64_t *shape, int *dtype) {
+static int cpu_decompress_impl(const void *in, size_t in_size, void **out, int *ndim, uint64_t *shape,
+                               int *dtype) {
   if (!in || !out)
     return MGB_BAD_ARGUMENT;
   if (!have_device())
@@ -1405,6 +1432,33 @@ int mgb_cpu_decompress(const void *in, size_t in_size, void **out, int *ndim, ui
   if (dtype)
     *dtype = h.dtype;
   return MGB_SUCCESS;
+}
+
+// No exception crosses the ABI (a corrupt header may ask for an absurd allocation).
+int mgb_cpu_plan_create(int ndim, const uint64_t *shape, int dtype, const void *const *coords,
+                        mgb_cpu_plan **plan) {
+  try {
+    return cpu_plan_create_impl(ndim, shape, dtype, coords, plan);
+  } catch (const std::exception &) {
+    return MGB_FAILURE;
+  }
+}
+
+int mgb_cpu_compress(int ndim, int dtype, const uint64_t *shape, const void *const *coords, double s, double tol,
+                     int compressor, const void *in, void **out, size_t *out_size) {
+  try {
+    return cpu_compress_impl(ndim, dtype, shape, coords, s, tol, compressor, in, out, out_size);
+  } catch (const std::exception &) {
+    return MGB_FAILURE;
+  }
+}
+
+int mgb_cpu_decompress(const void *in, size_t in_size, void **out, int *ndim, uint64_t *shape, int *dtype) {
+  try {
+    return cpu_decompress_impl(in, in_size, out, ndim, shape, dtype);
+  } catch (const std::exception &) {
+    return MGB_FAILURE;
+  }
 }
 
 } // extern "C"

@@ -93,7 +93,7 @@ def main():
             r["ref_cpu_quantize_s"] = wall_s(lambda: ref_cpu.quantize(c_ref, u.shape, s, tol, coords), 2)
             r["ref_cpu_zlib_s"] = wall_s(lambda: ref_cpu.zlib_compress(q_ref), 1)
             r["ref_cpu_recompose_s"] = wall_s(lambda: ref_cpu.recompose(c_ref, u.shape, coords), 2)
-            r["ref_cpu_threads"] = 1
+            r["ref_cpu_threads"] = os.cpu_count()  # built with -fopenmp (line loops)
             r["decompose_speedup_vs_ref_cpu"] = r["ref_cpu_decompose_s"] * 1e3 / r["gpu_decompose_ms"]
         out.append(r)
     print(json.dumps(out, indent=1))

@@ -425,3 +425,58 @@ def test_gpu_reads_reference_written_huffman_zstd_stream():
     blob = mo.stream(h, s, tol, ref_cpu.huffman_zstd_compress(q).tobytes(), 2)
     expect = ref_cpu.recompose(ref_cpu.dequantize(q, shape, dt, s, tol), shape)
     assert bits_equal(mc.decompress(blob), expect)
+
+
+def _cli():
+    exe = os.path.join(ROOT, "mgard_b200", "mgard-b200")
+    if not os.path.exists(exe):
+        pytest.skip("CLI not built")
+    return exe
+
+
+def test_mgard_cli_usage_and_missing_backend(tmp_path):
+    """mgard-b200 (the reference `mgard` executable's sub-commands, src/cli/executable.cpp):
+    usage text; without a CUDA device a request fails loudly (status 5), no CPU fallback."""
+    import subprocess
+    import torch
+    exe = _cli()
+    r = subprocess.run([exe, "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "compress" in r.stdout and "decompress" in r.stdout
+    r = subprocess.run([exe, "compress", "--input", "nowhere"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Required argument" in r.stderr
+    if torch.cuda.is_available():
+        return
+    src = tmp_path / "u.bin"
+    np.zeros(81).tofile(src)
+    r = subprocess.run([exe, "compress", "--datatype", "double", "--shape", "9x9", "--smoothness", "inf",
+                        "--tolerance", "1e-3", "--input", str(src), "--output", str(tmp_path / "u.mgard")],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "status 5" in r.stderr
+
+
+@pytest.mark.gpu
+def test_gpu_mgard_cli_round_trip_and_stream_identity(tmp_path):
+    import subprocess
+    import mgard_b200.cpu as mc
+    exe = _cli()
+    shape = (33, 20, 17)
+    rng = np.random.default_rng(23)
+    u = np.cumsum(rng.standard_normal(shape), axis=0)
+    src, mid, dst = tmp_path / "u.bin", tmp_path / "u.mgard", tmp_path / "u.out"
+    u.tofile(src)
+    for lossless, kind in (("zlib", mc.CPU_HUFFMAN_ZLIB), ("zstd", mc.CPU_HUFFMAN_ZSTD)):
+        r = subprocess.run([exe, "compress", "--datatype", "double", "--shape", "33x20x17", "--smoothness", "inf",
+                            "--tolerance", "1e-2", "--input", str(src), "--output", str(mid), "--lossless", lossless],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        blob = mid.read_bytes()
+        h = mo.Hierarchy(shape, np.float64)
+        assert blob == mo.compress(h, u, math.inf, 1e-2, kind)  # the file the reference would write
+        r = subprocess.run([exe, "decompress", "--input", str(mid), "--output", str(dst)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        back = np.fromfile(dst).reshape(shape)
+        assert np.abs(back - u).max() <= 1e-2
+        assert bits_equal(back, mc.decompress(blob))
+    r = subprocess.run([exe, "compress", "--datatype", "double", "--shape", "33x20", "--smoothness", "inf",
+                        "--tolerance", "1e-2", "--input", str(src), "--output", str(mid)], capture_output=True, text=True)
+    assert r.returncode == 1 and "expected" in r.stderr

@@ -12,7 +12,7 @@
 //   enums                                mgard-x/Utilities/Types.h:18-66
 //
 // Unsupported Config choices (SingleDim / Hybrid decomposition, LZ4 second
-// stage, reorder, Block / Variable domain decomposition, ZFP) return
+// stage, Block / Variable domain decomposition, ZFP) return
 // compress_status_type::Failure instead of silently doing something else.
 #ifndef MGARD_B200_COMPRESS_X_HPP
 #define MGARD_B200_COMPRESS_X_HPP
@@ -71,7 +71,7 @@ inline bool supported(const Config &c) {
   return c.compressor == compressor_type::MGARD &&
          c.decomposition == decomposition_type::MultiDim &&
          (c.lossless == lossless_type::Huffman || c.lossless == lossless_type::Huffman_Zstd) &&
-         c.reorder == 0 &&
+         (c.reorder == 0 || c.reorder == 1) &&
          c.domain_decomposition == domain_decomposition_type::MaxDim &&
          c.normalize_coordinates &&
          (c.dev_type == device_type::AUTO || c.dev_type == device_type::CUDA);
@@ -86,6 +86,7 @@ inline mgb_config to_c(const Config &c) {
   m.domain_decomposition_size = c.domain_decomposition_size;
   m.lossless = (int32_t)c.lossless;
   m.zstd_compress_level = c.zstd_compress_level;
+  m.reorder = c.reorder;
   return m;
 }
 inline compress_status_type status(int rc) {

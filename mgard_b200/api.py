@@ -59,6 +59,7 @@ class Config:
         self.normalize_coordinates = True
         self.lossless = lossless_type.Huffman
         self.zstd_compress_level = 3
+        self.reorder = 0
 
     def _c(self):
         c = MgbConfig()
@@ -71,6 +72,7 @@ class Config:
         c.normalize_coordinates = 1 if self.normalize_coordinates else 0
         c.lossless = int(self.lossless)
         c.zstd_compress_level = int(self.zstd_compress_level)
+        c.reorder = int(self.reorder)
         return c
 
 

@@ -41,6 +41,11 @@ int mgb_quantize_range(mgb_plan *plan, const void *d_coef, int ebtype, double to
                        unsigned long long *d_ocount, uint64_t *d_oidx, int64_t *d_oval,
                        uint64_t outlier_cap, uint64_t first, uint64_t count, int zero,
                        unsigned max_blocks, cudaStream_t st);
+int mgb_linearize_symbols(mgb_plan *p, const uint16_t *d_dense, uint16_t *d_linear, const unsigned long long *d_ocount,
+                          uint64_t *d_oidx, uint64_t ocap, cudaStream_t st);
+int mgb_delinearize_symbols(mgb_plan *p, const uint16_t *d_linear, uint16_t *d_dense, uint32_t *d_inverse,
+                            uint64_t ocount, const uint64_t *d_oidx_linear, uint64_t *d_oidx_dense,
+                            cudaStream_t st);
 int mgb_sort_outliers(const unsigned long long *d_ocount, uint64_t *d_oidx, int64_t *d_oval,
                       uint64_t cap, cudaStream_t st);
 int mgb_linear_dequant_scale(mgb_plan *plan, int ebtype, double tol, double s, double norm,
@@ -121,13 +126,23 @@ extern "C" int mgb_compress_lowlevel(mgb_plan *p, const void *d_in, int ebtype,
     }
     if (rc)
       return rc;
-    // index order, like the reference's SERIAL adapter (deterministic stream)
+    const uint16_t *sym = p->d_sym;
+    if (p->cfg.reorder) {
+      // Config::reorder: symbols and outlier positions in level-linearised order
+      // (LinearQuantization.hpp:46-146,232-248); the work buffer is free by now
+      rc = mgb_linearize_symbols(p, p->d_sym, (uint16_t *)p->d_wA, p->d_scalars, p->d_oidx,
+                                 p->outlier_cap, st);
+      if (rc)
+        return rc;
+      sym = (const uint16_t *)p->d_wA;
+    }
+    // index order: deterministic stream
     rc = mgb_sort_outliers(p->d_scalars, p->d_oidx, p->d_oval, p->outlier_cap, st);
     if (rc)
       return rc;
     if (attempt == 0) {
       // speculative: encode assuming the outlier buffer was large enough
-      rc = mgb_huffman_compress_async(p, p->d_sym, p->N, p->d_hist, p->d_scalars, 0,
+      rc = mgb_huffman_compress_async(p, sym, p->N, p->d_hist, p->d_scalars, 0,
                                       p->d_oidx, p->d_oval, d_out, cap, st);
       if (rc)
         return rc;
@@ -145,7 +160,7 @@ extern "C" int mgb_compress_lowlevel(mgb_plan *p, const void *d_in, int ebtype,
       MGB_CUDA_CHECK(cudaMalloc(&p->d_oidx, p->outlier_cap * 8));
       MGB_CUDA_CHECK(cudaMalloc(&p->d_oval, p->outlier_cap * 8));
     } else {
-      rc = mgb_huffman_compress_async(p, p->d_sym, p->N, p->d_hist, p->d_scalars, 0,
+      rc = mgb_huffman_compress_async(p, sym, p->N, p->d_hist, p->d_scalars, 0,
                                       p->d_oidx, p->d_oval, d_out, cap, st);
       if (rc)
         return rc;
@@ -173,10 +188,32 @@ extern "C" int mgb_decompress_lowlevel(mgb_plan *p, const uint8_t *d_in, uint64_
   const int linear = mgb_linear_dequant_scale(p, ebtype, tol, s, norm, &scale);
   int fused = 0;
   rc = mgb_huffman_decompress_impl(p, d_in, size, p->d_sym, p->N, &oc, &oidx, &oval, st,
-                                   linear ? p->d_coef : nullptr, scale, &fused);
+                                   linear && !p->cfg.reorder ? p->d_coef : nullptr, scale, &fused);
   if (rc)
     return rc;
-  if (fused)
+  if (p->cfg.reorder) {
+    // level-linearised symbols back to the array order; the outlier positions are
+    // translated through the inverse map, parked in the coefficient buffer that the
+    // dequantizer overwrites next
+    if (p->N >= (1ull << 32))
+      return MGB_FAILURE;
+    if (oc > p->outlier_cap) {
+      cudaFree(p->d_oidx);
+      cudaFree(p->d_oval);
+      p->d_oidx = nullptr;
+      p->d_oval = nullptr;
+      while (p->outlier_cap < oc)
+        p->outlier_cap <<= 1;
+      MGB_CUDA_CHECK(cudaMalloc(&p->d_oidx, p->outlier_cap * 8));
+      MGB_CUDA_CHECK(cudaMalloc(&p->d_oval, p->outlier_cap * 8));
+    }
+    rc = mgb_delinearize_symbols(p, p->d_sym, (uint16_t *)p->d_wA, (uint32_t *)p->d_coef, oc, oidx,
+                                 p->d_oidx, st);
+    if (rc)
+      return rc;
+    rc = mgb_dequantize(p, (const uint16_t *)p->d_wA, oc, p->d_oidx, oval, ebtype, tol, s, norm,
+                        p->d_coef, st);
+  } else if (fused)
     rc = mgb_outlier_restore(p, oc, oidx, oval, ebtype, tol, s, norm, p->d_coef, st);
   else
     rc = mgb_dequantize(p, p->d_sym, oc, oidx, oval, ebtype, tol, s, norm, p->d_coef, st);
@@ -269,6 +306,7 @@ int get_plan(int ndim, int dtype, const uint64_t *shape, const void *const *coor
   auto it = g_cache.plans.find(k);
   if (it != g_cache.plans.end()) {
     *plan = it->second;
+    (*plan)->cfg.reorder = cfg->reorder; // not part of the key: same tables either way
     *owned = false;
     return MGB_SUCCESS;
   }
@@ -416,6 +454,7 @@ void header_from(int ndim, int dtype, const uint64_t *shape, double tol, double 
   h.dict_size = cfg->huff_dict_size;
   h.block_size = cfg->huff_block_size;
   h.lossless = cfg->lossless;
+  h.reorder = cfg->reorder ? 1 : 0;
   h.coords.clear();
   if (coords) {
     h.coords.resize(ndim);
@@ -798,6 +837,7 @@ extern "C" int mgb_decompress(const void *in, size_t in_size, void **out,
   cfg.huff_dict_size = h.dict_size;
   cfg.huff_block_size = h.block_size;
   cfg.lossless = h.lossless;
+  cfg.reorder = h.reorder;
   const int ndim = h.ndim, dtype = h.dtype;
   const size_t tsize = dtype == MGB_F32 ? 4 : 8;
   uint64_t N = 1;

@@ -246,6 +246,7 @@ std::vector<uint8_t> mgb_encode_stream_header(const mgb_header &h) {
   f_varint(quant, 1, 1); // COEFFICIENTWISE_LINEAR
   f_varint(quant, 3, 3); // INT64_T
   std::string enc;
+  f_varint(enc, 1, h.reorder ? 1 : 0); // SHUFFLE when Config::reorder (Metadata.cpp:408-412)
   f_varint(enc, 2, h.lossless == 2 ? 5 : 3); // X_HUFFMAN / X_HUFFMAN_ZSTD (mgard.proto:139-145)
   f_varint(enc, 3, (uint64_t)h.dict_size);
   f_varint(enc, 4, (uint64_t)h.block_size);
@@ -417,8 +418,10 @@ int mgb_parse_stream_header(const uint8_t *data, size_t size, mgb_header &h,
     h.cpu_compressor = compressor;
     if (quant_type != 3 || h.ebtype != MGB_ABS)
       return MGB_BAD_STREAM;
-  } else if (hierarchy != 1 || (compressor != 3 && compressor != 5) || preprocessor != 0) {
+  } else if (hierarchy != 1 || (compressor != 3 && compressor != 5) || preprocessor > 1) {
     return MGB_BAD_STREAM;
+  } else {
+    h.reorder = preprocessor; // Metadata.cpp:693-698
   }
   h.lossless = compressor == 5 ? 2 : 0;
   if (geometry == 1) {

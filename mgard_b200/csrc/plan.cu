@@ -275,7 +275,7 @@ extern "C" void mgb_config_default(mgb_config *cfg) {
   cfg->normalize_coordinates = 1;
   cfg->lossless = 0;
   cfg->zstd_compress_level = 3;
-  cfg->reserved = 0;
+  cfg->reorder = 0;
 }
 
 extern "C" int mgb_plan_create(int ndim, const uint64_t *shape, int dtype,

@@ -322,6 +322,14 @@ __global__ void outlier_restore_kernel(const QParams p, const Tables<T> tb,
   if (k >= count)
     return;
   uint64_t idx = oidx[k];
+  {
+    // positions come from the stream: never write outside the array
+    uint64_t total = 1;
+    for (int d = 0; d < p.D; d++)
+      total *= p.n[d];
+    if (idx >= total)
+      return;
+  }
   int l = 0;
   if (p.calc_level) {
     uint64_t rem = idx;
@@ -779,6 +787,149 @@ int mgb_sort_outliers(const unsigned long long *d_ocount, uint64_t *d_oidx, int6
                       uint64_t cap, cudaStream_t st) {
   MGB_LAUNCH(MGB_K_OUTLIER_RESTORE, st,
              (sort_outliers_kernel<<<1, 1024, 0, st>>>(d_ocount, d_oidx, (long long *)d_oval, cap)));
+  MGB_CUDA_CHECK(cudaGetLastError());
+  return MGB_SUCCESS;
+}
+
+
+// ---- Config::reorder = 1: level-linearised order of the quantised symbols ------
+// calc_level_offset (LinearQuantization.hpp:46-146) behind the previous levels
+// (:591-604): within a level, the nodes it introduces in the row-major order of
+// that level's un-reordered mesh.
+namespace {
+
+struct LinearizeGeom {
+  int D, L;
+  uint64_t shape[MGB_MAX_DIMS];
+  uint32_t ranges[MGB_MAX_LEVELS + 2][MGB_MAX_DIMS]; // level_ranges (Hierarchy.hpp:243-260)
+  uint64_t base[MGB_MAX_LEVELS + 1];                  // elements of the levels below
+  const int *marks;
+  uint64_t marks_width;
+};
+
+__device__ __forceinline__ uint64_t level_linear_pos(const LinearizeGeom &g, uint64_t i) {
+  uint32_t idx[MGB_MAX_DIMS];
+  int mark[MGB_MAX_DIMS];
+  int level = 0;
+  for (int d = g.D - 1; d >= 0; d--) {
+    idx[d] = (uint32_t)(i % g.shape[d]);
+    i /= g.shape[d];
+    mark[d] = g.marks[(uint64_t)d * g.marks_width + idx[d]];
+    level = max(level, mark[d]);
+  }
+  uint64_t thread_off = 0, coarse_off = 0, stride = 1, cstride = 1;
+  for (int d = g.D - 1; d >= 0; d--) {
+    const uint32_t bit = mark[d] == level;
+    const uint32_t n = g.ranges[level + 1][d];
+    const uint32_t t = bit ? idx[d] - g.ranges[level][d] : idx[d];
+    uint32_t gi;
+    if (level == 0)
+      gi = t;
+    else if (n % 2 == 0 && t == n / 2)
+      gi = n - 1;
+    else
+      gi = t * 2 + bit;
+    thread_off += (uint64_t)gi * stride;
+    stride *= n;
+    if (gi % 2 != 0 && gi != n - 1)
+      coarse_off = 0;
+    if (gi)
+      coarse_off += (uint64_t)((gi - 1) / 2 + 1) * cstride;
+    cstride *= n / 2 + 1;
+  }
+  if (level == 0)
+    coarse_off = 0;
+  return g.base[level] + thread_off - coarse_off;
+}
+
+__global__ void __launch_bounds__(256) linearize_kernel(const __grid_constant__ LinearizeGeom g, uint64_t n,
+                                                        const uint16_t *__restrict__ dense,
+                                                        uint16_t *__restrict__ linear) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    linear[level_linear_pos(g, i)] = dense[i];
+}
+
+__global__ void __launch_bounds__(256) delinearize_kernel(const __grid_constant__ LinearizeGeom g, uint64_t n,
+                                                          const uint16_t *__restrict__ linear,
+                                                          uint16_t *__restrict__ dense,
+                                                          uint32_t *__restrict__ inverse) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const uint64_t pos = level_linear_pos(g, i);
+    dense[i] = linear[pos];
+    inverse[pos] = (uint32_t)i;
+  }
+}
+
+__global__ void __launch_bounds__(256) linearize_outliers_kernel(const __grid_constant__ LinearizeGeom g,
+                                                                 const unsigned long long *d_count, uint64_t cap,
+                                                                 uint64_t *oidx) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t count = min((uint64_t)*d_count, cap);
+  if (k < count)
+    oidx[k] = level_linear_pos(g, oidx[k]);
+}
+
+__global__ void __launch_bounds__(256) delinearize_outliers_kernel(uint64_t count, uint64_t n,
+                                                                   const uint32_t *__restrict__ inverse,
+                                                                   const uint64_t *__restrict__ oidx_linear,
+                                                                   uint64_t *__restrict__ oidx_dense) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < count) {
+    const uint64_t pos = oidx_linear[k];
+    oidx_dense[k] = pos < n ? inverse[pos] : n; // out-of-range entries are dropped by the restore kernel
+  }
+}
+
+LinearizeGeom make_geom(const mgb_plan *p) {
+  LinearizeGeom g;
+  memset(&g, 0, sizeof(g));
+  g.D = p->D;
+  g.L = p->L;
+  for (int d = 0; d < p->D; d++)
+    g.shape[d] = p->shape[d];
+  for (int l = 0; l <= p->L; l++) {
+    uint64_t below = 1;
+    for (int d = 0; d < p->D; d++) {
+      g.ranges[l + 1][d] = (uint32_t)p->lshape[l][d];
+      below *= g.ranges[l][d];
+    }
+    g.base[l] = l == 0 ? 0 : below;
+  }
+  g.marks = p->d_marks;
+  g.marks_width = p->marks_width;
+  return g;
+}
+
+} // namespace
+
+int mgb_linearize_symbols(mgb_plan *p, const uint16_t *d_dense, uint16_t *d_linear,
+                          const unsigned long long *d_ocount, uint64_t *d_oidx, uint64_t ocap, cudaStream_t st) {
+  if (p->w_elems * p->tsize < p->N * sizeof(uint16_t))
+    return MGB_FAILURE;
+  const LinearizeGeom g = make_geom(p);
+  const unsigned blocks = (unsigned)((p->N + 255) / 256);
+  MGB_LAUNCH(MGB_K_QUANTIZE, st, (linearize_kernel<<<blocks, 256, 0, st>>>(g, p->N, d_dense, d_linear)));
+  const unsigned oblocks = (unsigned)std::min<uint64_t>((ocap + 255) / 256, 1u << 20);
+  MGB_LAUNCH(MGB_K_QUANTIZE, st, (linearize_outliers_kernel<<<oblocks, 256, 0, st>>>(g, d_ocount, ocap, d_oidx)));
+  MGB_CUDA_CHECK(cudaGetLastError());
+  return MGB_SUCCESS;
+}
+
+int mgb_delinearize_symbols(mgb_plan *p, const uint16_t *d_linear, uint16_t *d_dense, uint32_t *d_inverse,
+                            uint64_t ocount, const uint64_t *d_oidx_linear, uint64_t *d_oidx_dense,
+                            cudaStream_t st) {
+  if (p->w_elems * p->tsize < p->N * sizeof(uint16_t))
+    return MGB_FAILURE;
+  const LinearizeGeom g = make_geom(p);
+  const unsigned blocks = (unsigned)((p->N + 255) / 256);
+  MGB_LAUNCH(MGB_K_DEQUANTIZE, st,
+             (delinearize_kernel<<<blocks, 256, 0, st>>>(g, p->N, d_linear, d_dense, d_inverse)));
+  if (ocount)
+    MGB_LAUNCH(MGB_K_DEQUANTIZE, st,
+               (delinearize_outliers_kernel<<<(unsigned)((ocount + 255) / 256), 256, 0, st>>>(
+                   ocount, p->N, d_inverse, d_oidx_linear, d_oidx_dense)));
   MGB_CUDA_CHECK(cudaGetLastError());
   return MGB_SUCCESS;
 }

@@ -409,6 +409,71 @@ def node_levels(h):
     return lv
 
 
+def level_linear_index(h):
+    """Config::reorder = 1: position of every element of the decomposed array in
+    the level-linearised quantised array (`calc_level_offset`,
+    LinearQuantization.hpp:46-146, placed behind the previous levels,
+    :591-604).  Within a level the nodes it introduces keep the row-major order
+    of that level's un-reordered mesh."""
+    D = h.D
+    lv = node_levels(h)
+    idx = np.meshgrid(*[np.arange(n, dtype=np.int64) for n in h.shape], indexing="ij")
+    ranges = np.zeros((h.l_target + 2, D), dtype=np.int64)
+    for l in range(h.l_target + 1):
+        ranges[l + 1] = h.level_shape[l]
+    out = np.zeros(h.shape, dtype=np.int64)
+    for l in range(h.l_target + 1):
+        m = lv == l
+        if not m.any():
+            continue
+        g = []
+        for d in range(D):
+            i = idx[d][m]
+            bit = (np.asarray(h.level_marks[d])[i] == l).astype(np.int64)
+            t = np.where(bit == 1, i - ranges[l][d], i)
+            n = ranges[l + 1][d]
+            if l == 0:
+                gd = t
+            else:
+                gd = np.where((n % 2 == 0) & (t == n // 2), n - 1, t * 2 + bit)
+            g.append(gd)
+        cto = np.zeros_like(g[0])
+        stride = 1
+        for d in range(D - 1, -1, -1):
+            cto = cto + g[d] * stride
+            stride *= int(ranges[l + 1][d])
+        clo = np.zeros_like(g[0])
+        stride = 1
+        for d in range(D - 1, -1, -1):
+            n = int(ranges[l + 1][d])
+            clo = np.where((g[d] % 2 != 0) & (g[d] != n - 1), 0, clo)
+            clo = clo + np.where(g[d] != 0, ((g[d] - 1) // 2 + 1) * stride, 0)
+            stride *= n // 2 + 1
+        if l == 0:
+            clo = np.zeros_like(clo)
+        out[m] = int(np.prod(ranges[l])) + cto - clo
+    return out
+
+
+def linearize(h, q, oidx, oval):
+    """Quantised symbols and outlier indices in level-linearised order."""
+    lin = level_linear_index(h).ravel()
+    ql = np.empty(lin.size, dtype=np.asarray(q).dtype)
+    ql[lin] = np.asarray(q).ravel()
+    if len(oidx):
+        # canonical list order: ascending stored (linearised) position.  The
+        # reference appends in the order its thread blocks run (tile by tile in
+        # the SERIAL adapter, atomic arrival on GPUs); decoding is order-blind.
+        new = lin[np.asarray(oidx, dtype=np.int64)]
+        order = np.argsort(new, kind="stable")
+        return ql, new[order].astype(np.uint64), np.asarray(oval)[order]
+    return ql, np.asarray(oidx), np.asarray(oval)
+
+
+def delinearize(h, ql):
+    return np.asarray(ql).ravel()[level_linear_index(h).ravel()].reshape(h.shape)
+
+
 def quantize(h, v, ebtype, tol, s, norm, dict_size=8192):
     """LevelwiseLinearQuantizerKernel<QUANTIZE> (LinearQuantization.hpp:148-248).
     Returns (symbols int64 with outliers zeroed, outlier_idx, outlier_val)."""
@@ -776,7 +841,7 @@ def huffman_decode(p):
 
 
 def compress_lowlevel(h, u, ebtype, tol, s, norm=None, dict_size=8192,
-                      chunk_size=20480, oob_value=0):
+                      chunk_size=20480, oob_value=0, reorder=0):
     T = h.T
     if ebtype == REL and norm is None:
         norm = calc_norm(np.asarray(u, dtype=T), s)
@@ -784,14 +849,22 @@ def compress_lowlevel(h, u, ebtype, tol, s, norm=None, dict_size=8192,
         norm = T(1)
     v = decompose(h, u)
     q, oidx, oval = quantize(h, v, ebtype, tol, s, norm, dict_size)
+    if reorder:
+        q, oidx, oval = linearize(h, q, oidx, oval)
     payload = huffman_compress(q, dict_size, chunk_size, oidx, oval, oob_value)
     return dict(payload=payload, norm=norm, decomposed=v, quantized=q,
                 oidx=oidx, oval=oval)
 
 
-def decompress_lowlevel(h, payload, ebtype, tol, s, norm):
+def decompress_lowlevel(h, payload, ebtype, tol, s, norm, reorder=0):
     p = huffman_parse(payload)
     sym = huffman_decode(p).astype(np.int64)
+    if reorder:  # outliers are indexed in the linearised order: restore them first
+        if len(p["oidx"]):
+            sym[np.asarray(p["oidx"], dtype=np.int64)] = p["oval"]
+        sym = delinearize(h, sym)
+        v = dequantize(h, sym, (), (), ebtype, tol, s, norm, int(p["dict_size"]))
+        return recompose(h, v)
     v = dequantize(h, sym, p["oidx"], p["oval"], ebtype, tol, s, norm,
                    int(p["dict_size"]))
     return recompose(h, v)

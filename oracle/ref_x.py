@@ -33,6 +33,7 @@ class RefxArgs(C.Structure):
         ("payload", C.c_void_p), ("payload_cap", C.c_uint64),
         ("payload_size", C.c_uint64),
         ("lossless", C.c_int32), ("zstd_level", C.c_int32),
+        ("reorder", C.c_int32), ("pad_", C.c_int32),
     ]
 
 
@@ -134,7 +135,7 @@ def recompose(v, coords=None):
     return u
 
 
-def compress(u, ebtype, tol, s, coords=None, dict_size=8192, chunk_size=20480, lossless=0):
+def compress(u, ebtype, tol, s, coords=None, dict_size=8192, chunk_size=20480, lossless=0, reorder=0):
     """Low-level Compressor::Compress staged; returns dict with payload bytes,
     norm, decomposed coefficients, quantized (dict-shifted) int64, outlier count."""
     keep = []
@@ -142,6 +143,7 @@ def compress(u, ebtype, tol, s, coords=None, dict_size=8192, chunk_size=20480, l
     a = _base_args(v.shape, v.dtype, coords, dict_size, chunk_size, keep)
     a.op = OP_COMPRESS
     a.lossless = lossless
+    a.reorder = reorder
     a.ebtype = ebtype
     a.tol = tol
     _set_s(a, s)
@@ -162,12 +164,13 @@ def compress(u, ebtype, tol, s, coords=None, dict_size=8192, chunk_size=20480, l
 
 
 def decompress(payload, shape, dtype, ebtype, tol, s, norm, coords=None,
-               dict_size=8192, chunk_size=20480, lossless=0):
+               dict_size=8192, chunk_size=20480, lossless=0, reorder=0):
     keep = []
     out = np.zeros(shape, dtype=dtype)
     a = _base_args(shape, dtype, coords, dict_size, chunk_size, keep)
     a.op = OP_DECOMPRESS
     a.lossless = lossless
+    a.reorder = reorder
     a.ebtype = ebtype
     a.tol = tol
     a.norm = norm

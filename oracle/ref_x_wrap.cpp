@@ -48,6 +48,7 @@ static Config make_config(const refx_args *a) {
   cfg.lossless = a->lossless == 2 ? lossless_type::Huffman_Zstd : lossless_type::Huffman;
   if (a->zstd_level)
     cfg.zstd_compress_level = a->zstd_level;
+  cfg.reorder = a->reorder;
   cfg.huff_dict_size = a->dict_size;
   cfg.huff_block_size = a->chunk_size;
   cfg.normalize_coordinates = true;

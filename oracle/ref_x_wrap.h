@@ -35,6 +35,8 @@ typedef struct refx_args {
   uint64_t payload_size; /* out on compress, in on decompress */
   int32_t lossless;      /* mgard_x::lossless_type: 0 Huffman, 2 Huffman_Zstd */
   int32_t zstd_level;    /* 0: reference default (3) */
+  int32_t reorder;       /* Config::reorder: 1 = level-linearised quantised order */
+  int32_t pad_;
 } refx_args;
 
 #ifdef __cplusplus

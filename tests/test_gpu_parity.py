@@ -67,8 +67,8 @@ def check_payload(gpu_payload, oracle_payload, compressor=True):
     x, y = sorted_pairs(a["oidx"], a["oval"]), sorted_pairs(b["oidx"], b["oval"])
     assert np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1])
     if compressor and len(b["oidx"]) <= 65536:
-        # the compressor sorts the outlier list by index (the order of the reference's
-        # SERIAL adapter), so the whole block is byte-identical
+        # the compressor sorts the outlier list by index (as the oracle does), so the
+        # whole block is byte-identical
         assert np.array_equal(np.asarray(a["oidx"]).astype(np.uint64), np.asarray(b["oidx"]).astype(np.uint64))
         assert gpu_payload == oracle_payload
     assert a["size"] == b["size"] == len(gpu_payload)
@@ -484,3 +484,42 @@ def test_pin_memory_api(env):
     mg.pin_memory(a)  # idempotent
     mg.unpin_memory(a)
     assert not mg.check_memory_pinned(a)
+
+
+@pytest.mark.parametrize("shape,dtype,s,tol", [
+    ((17,), np.float32, np.inf, 1e-3), ((10, 7), np.float64, np.inf, 1e-3), ((17, 19, 21), np.float32, np.inf, 1e-4),
+    ((12, 13, 14), np.float64, 0.0, 1e-3), ((5, 6, 9), np.float32, np.inf, 1e-6), ((4, 17, 5, 6), np.float64, np.inf, 1e-3),
+    ((33, 20), np.float32, 1.0, 1e-2), ((5, 5, 6, 7, 5), np.float32, np.inf, 1e-3), ((65, 65, 65), np.float32, np.inf, 1e-3)])
+def test_level_linearised_order(env, shape, dtype, s, tol):
+    """Config::reorder = 1 (LevelLinearizer order of the quantised symbols,
+    Encoding.preprocessor = SHUFFLE): payload identical to the oracle's, decodes to the
+    same values as the default order, cross-decodes with the reference build."""
+    torch, mg, d = env
+    # noise: plenty of outliers; the large case is a smooth field
+    u = np.random.default_rng(0).standard_normal(shape).astype(dtype) if np.prod(shape) < 10000 else field(shape, dtype, 5)
+    h = mo.Hierarchy(shape, dtype)
+    cfg = mg.Config()
+    cfg.reorder = 1
+    p = mg.Plan(shape, dtype, config=cfg)
+    du = dev(torch, u, d)
+    pay, norm = p.compress(du, mo.REL, tol, s)
+    m = mo.compress_lowlevel(h, u, mo.REL, tol, s, dtype(norm), reorder=1)
+    check_payload(pay.cpu().numpy().tobytes(), m["payload"])
+    back = p.decompress(pay, mo.REL, tol, s, norm).cpu().numpy()
+    assert np.array_equal(back, mo.decompress_lowlevel(h, m["payload"], mo.REL, tol, s, dtype(norm), reorder=1))
+    p0 = mg.Plan(shape, dtype)
+    pay0, norm0 = p0.compress(du, mo.REL, tol, s)
+    assert np.array_equal(back, p0.decompress(pay0, mo.REL, tol, s, norm0).cpu().numpy())
+    # high-level stream: header says SHUFFLE, the decoder follows the header
+    st = mg.compress(u, tol, s, mo.REL, config=cfg)
+    hdr = mo.encode_header(shape, dtype, mo.REL, tol, s, dtype(norm), reorder=1)
+    assert st.tobytes().startswith(mo.encode_preamble(hdr))
+    out = mg.decompress(st)  # tiny noisy inputs take the raw fall-back (CR < 1)
+    assert np.array_equal(out, back) or np.array_equal(out, u)
+    if ref_x.available():
+        r = ref_x.compress(u, ref_x.REL, tol, s, reorder=1)
+        ours = p.decompress(dev(torch, r["payload"], d), mo.REL, tol, s, r["norm"]).cpu().numpy()
+        theirs = ref_x.decompress(pay.cpu().numpy(), shape, dtype, ref_x.REL, tol, s, norm, reorder=1)
+        # each side decodes the other's block to what the writer's own decoder gives
+        assert np.array_equal(theirs, back)
+        assert np.array_equal(ours, ref_x.decompress(r["payload"], shape, dtype, ref_x.REL, tol, s, r["norm"], reorder=1))

@@ -88,3 +88,32 @@ def test_huffman_standalone_against_reference():
     assert ref.tobytes() in mine
     assert np.array_equal(mo.huffman_decode(mo.huffman_parse(ref.tobytes())).astype(np.int64), sym)
     assert np.array_equal(ref_x.huffman_decompress(np.frombuffer(mine[0], dtype=np.uint8), sym.size).astype(np.int64), sym)
+
+
+@pytest.mark.parametrize("case", [
+    ((17,), np.float32, np.inf, 1e-3), ((10, 7), np.float64, np.inf, 1e-3), ((17, 19, 21), np.float32, np.inf, 1e-4),
+    ((12, 13, 14), np.float64, 0.0, 1e-3), ((5, 6, 9), np.float32, np.inf, 1e-6), ((4, 17, 5, 6), np.float64, np.inf, 1e-3),
+    ((33, 20), np.float32, 1.0, 1e-2), ((5, 5, 6, 7, 5), np.float32, np.inf, 1e-3)])
+def test_level_linearised_order(case):
+    """Config::reorder = 1 (LevelLinearizer order, LinearQuantization.hpp:46-146): the
+    reference's linearised quantised array and Huffman block; outliers as a set (the
+    reference appends them in thread-block order)."""
+    shape, dt, s, tol = case
+    u = np.random.default_rng(0).standard_normal(shape).astype(dt)
+    h = mo.Hierarchy(shape, dt)
+    lin = mo.level_linear_index(h)
+    assert np.array_equal(np.sort(lin.ravel()), np.arange(lin.size))
+    r = ref_x.compress(u, ref_x.REL, tol, s, reorder=1)
+    m = mo.compress_lowlevel(h, u, mo.REL, tol, s, dt(r["norm"]), reorder=1)
+    assert np.array_equal(r["quantized"].ravel(), m["quantized"].ravel())
+    ref = mo.huffman_parse(r["payload"].tobytes())
+    ok = False
+    for oob in (0, 0xFFFFFFFF):
+        mine = mo.huffman_parse(mo.huffman_compress(m["quantized"], 8192, 20480, m["oidx"], m["oval"], oob))
+        ok = ok or all(np.array_equal(mine[k], ref[k]) for k in
+                       ("bits", "word_offset", "first", "entry", "keys", "ddata"))
+    assert ok
+    o = np.argsort(ref["oidx"])
+    assert np.array_equal(ref["oidx"][o], m["oidx"]) and np.array_equal(ref["oval"][o], m["oval"])
+    back = mo.decompress_lowlevel(h, r["payload"].tobytes(), mo.REL, tol, s, dt(r["norm"]), reorder=1)
+    assert np.array_equal(back, ref_x.decompress(r["payload"], shape, dt, ref_x.REL, tol, s, r["norm"], reorder=1))

@@ -58,6 +58,8 @@ typedef struct mgb_config {
   int32_t lossless;            /* mgard_x::lossless_type: 0 Huffman (default), 2 Huffman_Zstd */
   int32_t zstd_compress_level; /* Config::zstd_compress_level, 3 */
   int32_t reorder;             /* Config::reorder: 1 = quantised symbols in level-linearised order (LevelLinearizer) */
+  int32_t decomposition;       /* mgard_x::decomposition_type: 0 MultiDim (default), 1 SingleDim (D <= 3) */
+  int32_t reserved;
 } mgb_config;
 
 void mgb_config_default(mgb_config *cfg);

@@ -11,7 +11,7 @@
 //   Config (fields the hot path reads)   mgard-x/Config/Config.h:10-42, Config.cpp:14-43
 //   enums                                mgard-x/Utilities/Types.h:18-66
 //
-// Unsupported Config choices (SingleDim / Hybrid decomposition, LZ4 second
+// Unsupported Config choices (Hybrid decomposition, SingleDim beyond 3-D, LZ4 second
 // stage, Block / Variable domain decomposition, ZFP) return
 // compress_status_type::Failure instead of silently doing something else.
 #ifndef MGARD_B200_COMPRESS_X_HPP
@@ -69,7 +69,7 @@ struct Config {
 namespace detail {
 inline bool supported(const Config &c) {
   return c.compressor == compressor_type::MGARD &&
-         c.decomposition == decomposition_type::MultiDim &&
+         (c.decomposition == decomposition_type::MultiDim || c.decomposition == decomposition_type::SingleDim) &&
          (c.lossless == lossless_type::Huffman || c.lossless == lossless_type::Huffman_Zstd) &&
          (c.reorder == 0 || c.reorder == 1) &&
          c.domain_decomposition == domain_decomposition_type::MaxDim &&
@@ -87,6 +87,7 @@ inline mgb_config to_c(const Config &c) {
   m.lossless = (int32_t)c.lossless;
   m.zstd_compress_level = c.zstd_compress_level;
   m.reorder = c.reorder;
+  m.decomposition = c.decomposition == decomposition_type::SingleDim ? 1 : 0;
   return m;
 }
 inline compress_status_type status(int rc) {

@@ -27,6 +27,7 @@ class MgbConfig(C.Structure):
         ("domain_decomposition_size", C.c_uint64),
         ("normalize_coordinates", C.c_int32), ("lossless", C.c_int32),
         ("zstd_compress_level", C.c_int32), ("reorder", C.c_int32),
+        ("decomposition", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -40,6 +40,12 @@ class compress_status_type(enum.IntEnum):
     BackendNotAvailableFailure = 5
 
 
+class decomposition_type(enum.IntEnum):
+    MultiDim = 0
+    SingleDim = 1  # D <= 3
+    Hybrid = 2     # not built
+
+
 class lossless_type(enum.IntEnum):
     Huffman = 0
     Huffman_LZ4 = 1   # not built (nvcomp)
@@ -60,6 +66,7 @@ class Config:
         self.lossless = lossless_type.Huffman
         self.zstd_compress_level = 3
         self.reorder = 0
+        self.decomposition = decomposition_type.MultiDim
 
     def _c(self):
         c = MgbConfig()
@@ -73,6 +80,7 @@ class Config:
         c.lossless = int(self.lossless)
         c.zstd_compress_level = int(self.zstd_compress_level)
         c.reorder = int(self.reorder)
+        c.decomposition = int(self.decomposition)
         return c
 
 

@@ -104,7 +104,7 @@ extern "C" int mgb_compress_lowlevel(mgb_plan *p, const void *d_in, int ebtype,
   // s = inf, 3-D: the upper half of the coefficients is quantized while the coarse
   // levels are still being decomposed (refactor.cu: decompose_t)
   p->early_q.armed = is_inf(s) && p->D == 3 && !p->force_generic && p->L >= 3 &&
-                     getenv("MGB_NO_EARLY_QUANTIZE") == nullptr;
+                     getenv("MGB_NO_EARLY_QUANTIZE") == nullptr && p->cfg.decomposition == 0;
   p->early_q.done = false;
   p->early_q.ebtype = ebtype;
   p->early_q.tol = tol;
@@ -307,6 +307,7 @@ int get_plan(int ndim, int dtype, const uint64_t *shape, const void *const *coor
   if (it != g_cache.plans.end()) {
     *plan = it->second;
     (*plan)->cfg.reorder = cfg->reorder; // not part of the key: same tables either way
+    (*plan)->cfg.decomposition = cfg->decomposition;
     *owned = false;
     return MGB_SUCCESS;
   }
@@ -455,6 +456,7 @@ void header_from(int ndim, int dtype, const uint64_t *shape, double tol, double 
   h.block_size = cfg->huff_block_size;
   h.lossless = cfg->lossless;
   h.reorder = cfg->reorder ? 1 : 0;
+  h.decomposition = cfg->decomposition == 1 ? 1 : 0;
   h.coords.clear();
   if (coords) {
     h.coords.resize(ndim);
@@ -838,6 +840,7 @@ extern "C" int mgb_decompress(const void *in, size_t in_size, void **out,
   cfg.huff_block_size = h.block_size;
   cfg.lossless = h.lossless;
   cfg.reorder = h.reorder;
+  cfg.decomposition = h.decomposition;
   const int ndim = h.ndim, dtype = h.dtype;
   const size_t tsize = dtype == MGB_F32 ? 4 : 8;
   uint64_t N = 1;

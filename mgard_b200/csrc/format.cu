@@ -241,7 +241,7 @@ std::vector<uint8_t> mgb_encode_stream_header(const mgb_header &h) {
   f_varint(dd, 2, h.dd_dim);
   f_varint(dd, 3, h.dd_size);
   std::string fd;
-  f_varint(fd, 2, 1); // MULTIDIMENSION_WITH_GHOST_NODES
+  f_varint(fd, 2, h.decomposition == 1 ? 2 : 1); // MULTIDIMENSION / ONE_DIM_AT_A_TIME _WITH_GHOST_NODES (Metadata.cpp:360-370)
   std::string quant;
   f_varint(quant, 1, 1); // COEFFICIENTWISE_LINEAR
   f_varint(quant, 3, 3); // INT64_T
@@ -418,10 +418,11 @@ int mgb_parse_stream_header(const uint8_t *data, size_t size, mgb_header &h,
     h.cpu_compressor = compressor;
     if (quant_type != 3 || h.ebtype != MGB_ABS)
       return MGB_BAD_STREAM;
-  } else if (hierarchy != 1 || (compressor != 3 && compressor != 5) || preprocessor > 1) {
+  } else if ((hierarchy != 1 && hierarchy != 2) || (compressor != 3 && compressor != 5) || preprocessor > 1) {
     return MGB_BAD_STREAM;
   } else {
     h.reorder = preprocessor; // Metadata.cpp:693-698
+    h.decomposition = hierarchy == 2 ? 1 : 0; // Metadata.cpp:620-631
   }
   h.lossless = compressor == 5 ? 2 : 0;
   if (geometry == 1) {

@@ -17,6 +17,7 @@ struct mgb_header {
   int lossless = 0; // 0: X_HUFFMAN, 2: X_HUFFMAN_ZSTD (mgard_x::lossless_type values)
   // 0: MGARD-X stream (Metadata.cpp); 1: MGARD-CPU stream (src/format.cpp:110-140:
   // POWER_OF_TWO_PLUS_ONE hierarchy, SHUFFLE preprocessor, CPU_HUFFMAN_ZLIB payload)
+  int decomposition = 0; // 0 MULTIDIMENSION_WITH_GHOST_NODES, 1 ONE_DIM_AT_A_TIME_WITH_GHOST_NODES
   int reorder = 0; // Encoding.preprocessor = SHUFFLE (Metadata.cpp:408-412)
   int convention = 0;
   int cpu_compressor = 1; // pb::Encoding::Compressor of an MGARD-CPU stream: 1 zlib, 2 Huffman + zstd

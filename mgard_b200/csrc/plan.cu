@@ -276,6 +276,7 @@ extern "C" void mgb_config_default(mgb_config *cfg) {
   cfg->lossless = 0;
   cfg->zstd_compress_level = 3;
   cfg->reorder = 0;
+  cfg->decomposition = 0;
 }
 
 extern "C" int mgb_plan_create(int ndim, const uint64_t *shape, int dtype,
@@ -377,6 +378,7 @@ extern "C" void mgb_plan_destroy(mgb_plan *p) {
   cudaFree(p->d_coef);
   cudaFree(p->d_cbuf);
   cudaFree(p->d_wA);
+  cudaFree(p->d_sd);
   cudaFree(p->d_wB);
   if (p->side)
     cudaStreamDestroy(p->side);

@@ -57,6 +57,7 @@ struct mgb_plan {
   uint64_t cbuf_off[MGB_MAX_LEVELS]; // element offsets per level
   uint64_t cbuf_elems = 0;
   unsigned char *d_wA = nullptr, *d_wB = nullptr;
+  unsigned char *d_sd = nullptr; // N * T scratch of the SingleDim decomposition (on demand)
   uint64_t w_elems = 0;
   uint16_t *d_sym = nullptr;
   uint32_t *d_hist = nullptr;

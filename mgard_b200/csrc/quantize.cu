@@ -463,7 +463,10 @@ void calc_quantizers(const mgb_plan *p, int ebtype, double tol_, double s_,
   const size_t dof = p->N;
   if (s == std::numeric_limits<T>::infinity()) {
     for (int l = 0; l < p->L + 1; l++) {
-      out[l] = (abs_tol) / ((l_target + 1) * (1 + std::pow(3, p->D)));
+      if (p->cfg.decomposition == 1) // SingleDim (LinearQuantization.hpp:516-520)
+        out[l] = (abs_tol) / ((l_target + 1) * (uint8_t)p->D * (1 + std::pow(3, 1)));
+      else
+        out[l] = (abs_tol) / ((l_target + 1) * (1 + std::pow(3, p->D)));
       if (reciprocal)
         out[l] = 1.0f / out[l];
     }

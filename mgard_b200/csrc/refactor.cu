@@ -1303,14 +1303,359 @@ int recompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
   return MGB_SUCCESS;
 }
 
+
+// ---------------------------------------------------------------------------
+// decomposition_type::SingleDim (reference DataRefactoring/SingleDimension/*.hpp):
+// per level, one dimension after another (fastest first): coefficients by 1-D
+// interpolation along that dimension into the coarse-first layout
+// (CoefficientKernel.hpp:44-134), load vector of the coefficients
+// (MassTransKernel.hpp:36-101) with the 13-argument mass_trans
+// (LPKFunctor.h:14-66), Thomas solve with the level l-1 tables, added to the
+// coarse part.  D <= 3 (the reference's own D >= 4 variant does not round-trip).
+// Generic kernels over a strided 3-D box; this mode is not a bench line.
+// ---------------------------------------------------------------------------
+struct SdGeom {
+  int n[3];      // box extents, with the active axis holding the COARSE size
+  int ax;        // active axis (0..2, dimensions left-padded to 3)
+  int nfine, nc; // fine / coarse size along the axis
+  i64 sa[3];     // strides of array A
+  i64 sb[3];     // strides of array B
+};
+
+__device__ __forceinline__ bool sd_index(const SdGeom &g, i64 t, int (&i)[3]) {
+  const i64 total = (i64)g.n[0] * g.n[1] * g.n[2];
+  if (t >= total)
+    return false;
+  i[2] = (int)(t % g.n[2]);
+  t /= g.n[2];
+  i[1] = (int)(t % g.n[1]);
+  i[0] = (int)(t / g.n[1]);
+  return true;
+}
+
+// A = interleaved source, B = destination in coarse-first layout
+template <typename T>
+__global__ void __launch_bounds__(256) sd_coef_kernel(const SdGeom g, const T *__restrict__ A, T *__restrict__ B,
+                                                      const T *__restrict__ ratio) {
+  int i[3];
+  if (!sd_index(g, (i64)blockIdx.x * blockDim.x + threadIdx.x, i))
+    return;
+  const int j = i[g.ax], ncoef = g.nfine - g.nc;
+  i64 a = 0, b = 0;
+  for (int d = 0; d < 3; d++)
+    if (d != g.ax) {
+      a += i[d] * g.sa[d];
+      b += i[d] * g.sb[d];
+    }
+  const i64 sa = g.sa[g.ax], sb = g.sb[g.ax];
+  const int sj = j <= ncoef ? 2 * j : g.nfine - 1; // even nodes, then the last node of an even size
+  const T left = A[a + sj * sa];
+  B[b + j * sb] = left;
+  if (j < ncoef) {
+    const T mid = A[a + (2 * j + 1) * sa], right = A[a + (2 * j + 2) * sa];
+    B[b + (g.nc + j) * sb] = mid - lerp_ref(left, right, ratio[2 * j]);
+  }
+}
+
+// A = coarse-first source (coarse part and coefficients), B = interleaved destination
+template <typename T>
+__global__ void __launch_bounds__(256) sd_restore_kernel(const SdGeom g, const T *__restrict__ A, T *__restrict__ B,
+                                                         const T *__restrict__ ratio) {
+  int i[3];
+  if (!sd_index(g, (i64)blockIdx.x * blockDim.x + threadIdx.x, i))
+    return;
+  const int j = i[g.ax], ncoef = g.nfine - g.nc;
+  i64 a = 0, b = 0;
+  for (int d = 0; d < 3; d++)
+    if (d != g.ax) {
+      a += i[d] * g.sa[d];
+      b += i[d] * g.sb[d];
+    }
+  const i64 sa = g.sa[g.ax], sb = g.sb[g.ax];
+  const int sj = j <= ncoef ? 2 * j : g.nfine - 1;
+  const T left = A[a + j * sa];
+  B[b + sj * sb] = left;
+  if (j < ncoef) {
+    const T right = A[a + (j + 1) * sa];
+    B[b + (2 * j + 1) * sb] = A[a + (g.nc + j) * sa] + lerp_ref(left, right, ratio[2 * j]);
+  }
+}
+
+// A = array holding the coefficients (coarse-first), B = dense load vector (coarse shape)
+template <typename T>
+__global__ void __launch_bounds__(256) sd_masstrans_kernel(const SdGeom g, const T *__restrict__ A,
+                                                           T *__restrict__ B, const T *__restrict__ dist) {
+  int i[3];
+  if (!sd_index(g, (i64)blockIdx.x * blockDim.x + threadIdx.x, i))
+    return;
+  const int j = i[g.ax], ncoef = g.nfine - g.nc;
+  i64 a = 0, bo = 0;
+  for (int d = 0; d < 3; d++) {
+    if (d != g.ax)
+      a += i[d] * g.sa[d];
+    bo += i[d] * g.sb[d];
+  }
+  const i64 sa = g.sa[g.ax];
+  const T va = 0, vc = 0, ve = 0;
+  T vb = 0, vd = 0;
+  if (j > 0 && j < ncoef)
+    vb = A[a + (g.nc + j - 1) * sa];
+  if (j < ncoef)
+    vd = A[a + (g.nc + j) * sa];
+  T h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+  if (j > 0 && 2 * j < g.nfine - 1) {
+    h1 = dist[2 * j - 2];
+    h2 = dist[2 * j - 1];
+  }
+  if (2 * j < g.nfine - 1) {
+    h3 = dist[2 * j];
+    h4 = dist[2 * j + 1];
+  }
+  T r1 = 0, r4 = 0;
+  if (h1 + h2 != 0)
+    r1 = h1 / (h1 + h2);
+  if (h3 + h4 != 0)
+    r4 = h4 / (h3 + h4);
+  const T tb = va * (h1 / 6) + vb * ((h1 + h2) / 3) + vc * (h2 / 6);
+  T tc = vb * (h2 / 6) + vc * ((h2 + h3) / 3) + vd * (h3 / 6);
+  const T td = vc * (h3 / 6) + vd * ((h3 + h4) / 3) + ve * (h4 / 6);
+  tc += tb * r1 + td * r4;
+  B[bo] = tc;
+}
+
+// B (strided) += / -= A (dense), or plain copies between a strided box and a dense one
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) sd_box_kernel(const SdGeom g, const T *__restrict__ A, T *__restrict__ B) {
+  int i[3];
+  if (!sd_index(g, (i64)blockIdx.x * blockDim.x + threadIdx.x, i))
+    return;
+  i64 a = 0, b = 0;
+  for (int d = 0; d < 3; d++) {
+    a += i[d] * g.sa[d];
+    b += i[d] * g.sb[d];
+  }
+  if (MODE == 0)
+    B[b] = A[a];
+  else if (MODE == 1)
+    B[b] = B[b] + A[a];
+  else
+    B[b] = B[b] - A[a];
+}
+
+struct SdLevelDim {
+  int fine[3], nc, ncoef;
+};
+
+inline void sd_dense_strides(const int (&n)[3], i64 (&s)[3]) {
+  s[2] = 1;
+  s[1] = n[2];
+  s[0] = (i64)n[1] * n[2];
+}
+
+template <typename T> int sd_prepare(mgb_plan *p, int (&full)[3], i64 (&sfull)[3], int &pad) {
+  if (p->D > 3)
+    return MGB_TOO_MANY_DIMS;
+  int rc = mgb_plan_ensure_workspace(p);
+  if (rc)
+    return rc;
+  if (!p->d_sd)
+    MGB_CUDA_CHECK(cudaMalloc(&p->d_sd, p->N * p->tsize));
+  pad = 3 - p->D;
+  for (int d = 0; d < 3; d++)
+    full[d] = d < pad ? 1 : (int)p->shape[d - pad];
+  sd_dense_strides(full, sfull);
+  return MGB_SUCCESS;
+}
+
+// load vector of the coefficients held in V (coarse-first along ax) -> solved
+// correction in the dense buffer `corr`
+template <typename T>
+void sd_correction(mgb_plan *p, const T *V, const i64 (&sfull)[3], const int (&fine)[3], int ax, int pad, int l,
+                   T *corr, cudaStream_t st) {
+  const int dim = ax - pad;
+  SdGeom g;
+  g.ax = ax;
+  g.nfine = fine[ax];
+  g.nc = (int)p->lshape[l - 1][dim];
+  for (int d = 0; d < 3; d++) {
+    g.n[d] = d == ax ? g.nc : fine[d];
+    g.sa[d] = sfull[d];
+  }
+  sd_dense_strides(g.n, g.sb);
+  const i64 total = (i64)g.n[0] * g.n[1] * g.n[2];
+  const T *dist = (const T *)p->dtab(p->tab[l][dim].dist);
+  MGB_LAUNCH(MGB_K_MASSTRANS, st,
+             (sd_masstrans_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, V, corr, dist)));
+  // Thomas along ax with the level l-1 tables (Ipk kernels, CalcCorrection.hpp:44-93)
+  i64 outer = 1, inner = 1;
+  for (int d = 0; d < ax; d++)
+    outer *= g.n[d];
+  for (int d = ax + 1; d < 3; d++)
+    inner *= g.n[d];
+  const mgb_dim_tables &tc = p->tab[l - 1][dim];
+  const i64 lines = outer * inner;
+  MGB_LAUNCH(MGB_K_THOMAS_STRIDED, st,
+             (thomas_strided_kernel<T><<<(unsigned)((lines + 127) / 128), 128, 0, st>>>(
+                 corr, g.nc, inner, lines, (const T *)p->dtab(tc.fw), (const T *)p->dtab(tc.am),
+                 (const T *)p->dtab(tc.bm), nullptr, 0)));
+}
+
+template <typename T>
+void sd_accumulate(const i64 (&sfull)[3], const int (&coarse)[3], const T *corr, T *V, bool subtract,
+                   cudaStream_t st) {
+  SdGeom g;
+  g.ax = 0;
+  g.nfine = g.nc = 0;
+  for (int d = 0; d < 3; d++) {
+    g.n[d] = coarse[d];
+    g.sb[d] = sfull[d];
+  }
+  sd_dense_strides(g.n, g.sa);
+  const i64 total = (i64)g.n[0] * g.n[1] * g.n[2];
+  if (subtract)
+    MGB_LAUNCH(MGB_K_AXPY, st, (sd_box_kernel<T, 2><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, corr, V)));
+  else
+    MGB_LAUNCH(MGB_K_AXPY, st, (sd_box_kernel<T, 1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, corr, V)));
+}
+
+// single_dimension::decompose (SingleDimension/DataRefactoring.hpp:25-108)
+template <typename T> int decompose_single_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
+  int full[3], pad;
+  i64 sfull[3];
+  int rc = sd_prepare<T>(p, full, sfull, pad);
+  if (rc)
+    return rc;
+  if (p->L == 0)
+    MGB_CUDA_CHECK(cudaMemcpyAsync(d_out, d_in, p->N * sizeof(T), cudaMemcpyDeviceToDevice, st));
+  T *tmp = (T *)p->d_sd, *corr = (T *)p->d_wB;
+  bool first = true;
+  for (int l = p->L; l > 0; l--) {
+    for (int ax = 2; ax >= pad; ax--) {
+      const int dim = ax - pad;
+      int fine[3];
+      for (int d = 0; d < 3; d++)
+        fine[d] = d < pad ? 1 : (int)(d > ax ? p->lshape[l - 1][d - pad] : p->lshape[l][d - pad]);
+      // source: the input itself for the very first step, else a dense copy of the box
+      SdGeom g;
+      g.ax = ax;
+      g.nfine = fine[ax];
+      g.nc = (int)p->lshape[l - 1][dim];
+      for (int d = 0; d < 3; d++) {
+        g.n[d] = fine[d];
+        g.sb[d] = sfull[d];
+      }
+      const T *src = d_in;
+      if (first) {
+        for (int d = 0; d < 3; d++)
+          g.sa[d] = sfull[d];
+      } else {
+        SdGeom c = g;
+        for (int d = 0; d < 3; d++)
+          c.sa[d] = sfull[d];
+        sd_dense_strides(c.n, c.sb);
+        const i64 tot = (i64)c.n[0] * c.n[1] * c.n[2];
+        MGB_LAUNCH(MGB_K_BOXCOPY, st,
+                   (sd_box_kernel<T, 0><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(c, d_out, tmp)));
+        sd_dense_strides(g.n, g.sa);
+        src = tmp;
+      }
+      first = false;
+      g.n[ax] = g.nc;
+      const i64 total = (i64)g.n[0] * g.n[1] * g.n[2];
+      const T *ratio = (const T *)p->dtab(p->tab[l][dim].ratio);
+      MGB_LAUNCH(MGB_K_COEF, st,
+                 (sd_coef_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, src, d_out, ratio)));
+      sd_correction<T>(p, d_out, sfull, fine, ax, pad, l, corr, st);
+      int coarse[3];
+      for (int d = 0; d < 3; d++)
+        coarse[d] = d == ax ? g.nc : fine[d];
+      sd_accumulate<T>(sfull, coarse, corr, d_out, false, st);
+    }
+  }
+  MGB_CUDA_CHECK(cudaGetLastError());
+  return MGB_SUCCESS;
+}
+
+// single_dimension::recompose (SingleDimension/DataRefactoring.hpp:110-194)
+template <typename T> int recompose_single_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
+  int full[3], pad;
+  i64 sfull[3];
+  int rc = sd_prepare<T>(p, full, sfull, pad);
+  if (rc)
+    return rc;
+  T *V = (T *)p->d_sd, *corr = (T *)p->d_wB;
+  if (p->L == 0) {
+    MGB_CUDA_CHECK(cudaMemcpyAsync(d_out, d_in, p->N * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    return MGB_SUCCESS;
+  }
+  MGB_CUDA_CHECK(cudaMemcpyAsync(V, d_in, p->N * sizeof(T), cudaMemcpyDeviceToDevice, st));
+  for (int l = 0; l < p->L; l++) {
+    for (int ax = pad; ax < 3; ax++) {
+      const int dim = ax - pad;
+      int fine[3], coarse[3];
+      for (int d = 0; d < 3; d++)
+        fine[d] = d < pad ? 1 : (int)(d > ax ? p->lshape[l][d - pad] : p->lshape[l + 1][d - pad]);
+      const int nc = (int)p->lshape[l][dim];
+      for (int d = 0; d < 3; d++)
+        coarse[d] = d == ax ? nc : fine[d];
+      sd_correction<T>(p, V, sfull, fine, ax, pad, l + 1, corr, st);
+      sd_accumulate<T>(sfull, coarse, corr, V, true, st);
+      const bool last = l == p->L - 1 && ax == 2;
+      SdGeom g;
+      g.ax = ax;
+      g.nfine = fine[ax];
+      g.nc = nc;
+      for (int d = 0; d < 3; d++) {
+        g.n[d] = coarse[d];
+        g.sa[d] = sfull[d];
+      }
+      if (last) {
+        for (int d = 0; d < 3; d++)
+          g.sb[d] = sfull[d];
+      } else {
+        sd_dense_strides(fine, g.sb);
+      }
+      const i64 total = (i64)g.n[0] * g.n[1] * g.n[2];
+      const T *ratio = (const T *)p->dtab(p->tab[l + 1][dim].ratio);
+      MGB_LAUNCH(MGB_K_RESTORE, st,
+                 (sd_restore_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, V, d_out, ratio)));
+      if (!last) { // the output buffer served as the dense temporary: back into V
+        SdGeom c;
+        c.ax = 0;
+        c.nfine = c.nc = 0;
+        for (int d = 0; d < 3; d++) {
+          c.n[d] = fine[d];
+          c.sb[d] = sfull[d];
+        }
+        sd_dense_strides(c.n, c.sa);
+        const i64 tot = (i64)c.n[0] * c.n[1] * c.n[2];
+        MGB_LAUNCH(MGB_K_BOXCOPY, st,
+                   (sd_box_kernel<T, 0><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(c, d_out, V)));
+      }
+    }
+  }
+  MGB_CUDA_CHECK(cudaGetLastError());
+  return MGB_SUCCESS;
+}
+
 } // namespace
 
 int mgb_decompose_impl(mgb_plan *p, const void *d_in, void *d_out, cudaStream_t st) {
+  if (p->cfg.decomposition == 1) {
+    if (p->dtype == MGB_F32)
+      return decompose_single_t<float>(p, (const float *)d_in, (float *)d_out, st);
+    return decompose_single_t<double>(p, (const double *)d_in, (double *)d_out, st);
+  }
   if (p->dtype == MGB_F32)
     return decompose_t<float>(p, (const float *)d_in, (float *)d_out, st);
   return decompose_t<double>(p, (const double *)d_in, (double *)d_out, st);
 }
 int mgb_recompose_impl(mgb_plan *p, const void *d_in, void *d_out, cudaStream_t st) {
+  if (p->cfg.decomposition == 1) {
+    if (p->dtype == MGB_F32)
+      return recompose_single_t<float>(p, (const float *)d_in, (float *)d_out, st);
+    return recompose_single_t<double>(p, (const double *)d_in, (double *)d_out, st);
+  }
   if (p->dtype == MGB_F32)
     return recompose_t<float>(p, (const float *)d_in, (float *)d_out, st);
   return recompose_t<double>(p, (const double *)d_in, (double *)d_out, st);

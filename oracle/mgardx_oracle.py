@@ -369,6 +369,106 @@ def recompose(h, v):
 # --------------------------------------------------------------------------
 
 
+
+# --------------------------------------------------------------------------
+# decomposition_type::SingleDim (DataRefactoring/SingleDimension/*.hpp)
+# --------------------------------------------------------------------------
+
+
+def _mass_trans_13(a, b, c, d, e, h1, h2, h3, h4):
+    """mass_trans with explicit spacings (LPKFunctor.h:14-66, non-FMA branch):
+    r1, r4 are recomputed from the spacings."""
+    T = b.dtype.type
+    with np.errstate(all="ignore"):
+        r1 = np.where(h1 + h2 != 0, h1 / (h1 + h2), T(0)).astype(T)
+        r4 = np.where(h3 + h4 != 0, h4 / (h3 + h4), T(0)).astype(T)
+    tb = a * (h1 / 6) + b * ((h1 + h2) / 3) + c * (h2 / 6)
+    tc = b * (h2 / 6) + c * ((h2 + h3) / 3) + d * (h3 / 6)
+    td = c * (h3 / 6) + d * ((h3 + h4) / 3) + e * (h4 / 6)
+    return tc + (tb * r1 + td * r4)
+
+
+def _single_dim_correction(h, coeff, nc, l, ax):
+    """CalcCorrection (SingleDimension/Correction/CalcCorrection.hpp:26-96): the
+    load vector of the coefficients along one dimension (MassTransKernel.hpp:36-101,
+    including its treatment of the last coarse nodes) and the Thomas solve with the
+    level l-1 tables."""
+    T = h.T
+    nd = coeff.ndim
+    ncoef = coeff.shape[ax]
+    n = ncoef + nc
+    dist = h.dist[l][ax]
+    j = np.arange(nc)
+    zero = np.zeros((), dtype=T)
+    has_b = (j > 0) & (j < ncoef)
+    has_d = j < ncoef
+    b = np.where(_bshape(has_b, ax, nd), np.take(coeff, np.clip(j - 1, 0, ncoef - 1), axis=ax), zero)
+    d = np.where(_bshape(has_d, ax, nd), np.take(coeff, np.clip(j, 0, ncoef - 1), axis=ax), zero)
+    left = (j > 0) & (2 * j < n - 1)
+    right = 2 * j < n - 1
+    pick = lambda k, m: np.where(m, dist[np.clip(k, 0, len(dist) - 1)], T(0)).astype(T)
+    h1, h2 = pick(2 * j - 2, left), pick(2 * j - 1, left)
+    h3, h4 = pick(2 * j, right), pick(2 * j + 1, right)
+    z = np.zeros_like(b)
+    w = _mass_trans_13(z, b, z, d, z, *(_bshape(x, ax, nd) for x in (h1, h2, h3, h4))).astype(T)
+    return _thomas_axis(w, ax, h.am[l - 1][ax], h.bm[l - 1][ax])
+
+
+def decompose_single(h, u):
+    """single_dimension::decompose (SingleDimension/DataRefactoring.hpp:25-108)."""
+    T = h.T
+    v = np.array(u, dtype=T, copy=True)
+    D = h.D
+    for l in range(h.l_target, 0, -1):
+        for ax in range(D - 1, -1, -1):
+            fine = [h.level_shape[l - 1][d] if d > ax else h.level_shape[l][d] for d in range(D)]
+            box = tuple(slice(0, m) for m in fine)
+            w = v[box].copy()
+            n, nc = fine[ax], h.level_shape[l - 1][ax]
+            ncoef = n - nc
+            i = np.arange(ncoef)
+            ratio = _bshape(h.ratio[l][ax][2 * i], ax, D)
+            left, mid, right = (np.take(w, 2 * i + k, axis=ax) for k in (0, 1, 2))
+            coeff = mid - _lerp(left, right, ratio)
+            # CoefficientKernel.hpp:88-104: coarse = even nodes (+ the last node of an even size)
+            cidx = list(2 * i) + [2 * ncoef] + ([2 * ncoef + 1] if n % 2 == 0 else [])
+            coarse = np.take(w, cidx, axis=ax)
+            coarse = coarse + _single_dim_correction(h, coeff, nc, l, ax)
+            v[box] = np.concatenate([coarse, coeff], axis=ax)
+    return v
+
+
+def recompose_single(h, c):
+    """single_dimension::recompose (SingleDimension/DataRefactoring.hpp:110-194)."""
+    T = h.T
+    v = np.array(c, dtype=T, copy=True)
+    D = h.D
+    for l in range(h.l_target):
+        for ax in range(D):
+            fine = [h.level_shape[l][d] if d > ax else h.level_shape[l + 1][d] for d in range(D)]
+            box = tuple(slice(0, m) for m in fine)
+            cur = v[box]
+            n, nc = fine[ax], h.level_shape[l][ax]
+            ncoef = n - nc
+            coarse = np.take(cur, np.arange(nc), axis=ax)
+            coeff = np.take(cur, np.arange(nc, n), axis=ax)
+            coarse = coarse - _single_dim_correction(h, coeff, nc, l + 1, ax)
+            i = np.arange(ncoef)
+            ratio = _bshape(h.ratio[l + 1][ax][2 * i], ax, D)
+            left = np.take(coarse, i, axis=ax)
+            right = np.take(coarse, i + 1, axis=ax)
+            mid = coeff + _lerp(left, right, ratio)
+            out = np.empty_like(cur)
+            sl = lambda idx: tuple(idx if d == ax else slice(None) for d in range(D))
+            out[sl(2 * i)] = left
+            out[sl(2 * i + 1)] = mid
+            out[sl([2 * ncoef])] = np.take(coarse, [ncoef], axis=ax)
+            if n % 2 == 0:
+                out[sl([2 * ncoef + 1])] = np.take(coarse, [ncoef + 1], axis=ax)
+            v[box] = out
+    return v
+
+
 def calc_norm(u, s):
     T = u.dtype.type
     if np.isinf(s):
@@ -381,7 +481,7 @@ def calc_norm(u, s):
     return T(norm)
 
 
-def calc_quantizers(h, ebtype, tol, s, norm, reciprocal):
+def calc_quantizers(h, ebtype, tol, s, norm, reciprocal, single_dim=False):
     """LinearQuantizer::CalcQuantizers (LinearQuantization.hpp:495-545)."""
     T = h.T
     abs_tol = float(T(tol))
@@ -391,7 +491,9 @@ def calc_quantizers(h, ebtype, tol, s, norm, reciprocal):
     L = h.l_target
     q = np.zeros(L + 1, dtype=T)
     for l in range(L + 1):
-        if np.isinf(s):
+        if np.isinf(s) and single_dim:
+            q[l] = T(abs_tol / ((L + 1) * h.D * (1 + 3.0 ** 1)))
+        elif np.isinf(s):
             q[l] = T(abs_tol / ((L + 1) * (1 + 3.0 ** h.D)))
         else:
             # std::exp2(s * l) is evaluated in T (float overload for fp32)
@@ -474,11 +576,11 @@ def delinearize(h, ql):
     return np.asarray(ql).ravel()[level_linear_index(h).ravel()].reshape(h.shape)
 
 
-def quantize(h, v, ebtype, tol, s, norm, dict_size=8192):
+def quantize(h, v, ebtype, tol, s, norm, dict_size=8192, single_dim=False):
     """LevelwiseLinearQuantizerKernel<QUANTIZE> (LinearQuantization.hpp:148-248).
     Returns (symbols int64 with outliers zeroed, outlier_idx, outlier_val)."""
     T = h.T
-    quantizers = calc_quantizers(h, ebtype, tol, s, norm, True)
+    quantizers = calc_quantizers(h, ebtype, tol, s, norm, True, single_dim)
     with np.errstate(all="ignore"):
         if np.isinf(s):
             x = v * quantizers[0] * T(1)
@@ -501,11 +603,11 @@ def quantize(h, v, ebtype, tol, s, norm, dict_size=8192):
     return q, oidx, oval
 
 
-def dequantize(h, q, oidx, oval, ebtype, tol, s, norm, dict_size=8192):
+def dequantize(h, q, oidx, oval, ebtype, tol, s, norm, dict_size=8192, single_dim=False):
     """OutlierRestore + LevelwiseLinearQuantizerKernel<DEQUANTIZE>
     (LinearQuantization.hpp:251-264,304-350)."""
     T = h.T
-    quantizers = calc_quantizers(h, ebtype, tol, s, norm, False)
+    quantizers = calc_quantizers(h, ebtype, tol, s, norm, False, single_dim)
     q = np.array(q, dtype=np.int64, copy=True).reshape(-1)
     if len(oidx):
         q[np.asarray(oidx, dtype=np.int64)] = oval
@@ -841,14 +943,14 @@ def huffman_decode(p):
 
 
 def compress_lowlevel(h, u, ebtype, tol, s, norm=None, dict_size=8192,
-                      chunk_size=20480, oob_value=0, reorder=0):
+                      chunk_size=20480, oob_value=0, reorder=0, single_dim=False):
     T = h.T
     if ebtype == REL and norm is None:
         norm = calc_norm(np.asarray(u, dtype=T), s)
     if norm is None:
         norm = T(1)
-    v = decompose(h, u)
-    q, oidx, oval = quantize(h, v, ebtype, tol, s, norm, dict_size)
+    v = decompose_single(h, u) if single_dim else decompose(h, u)
+    q, oidx, oval = quantize(h, v, ebtype, tol, s, norm, dict_size, single_dim)
     if reorder:
         q, oidx, oval = linearize(h, q, oidx, oval)
     payload = huffman_compress(q, dict_size, chunk_size, oidx, oval, oob_value)
@@ -856,17 +958,19 @@ def compress_lowlevel(h, u, ebtype, tol, s, norm=None, dict_size=8192,
                 oidx=oidx, oval=oval)
 
 
-def decompress_lowlevel(h, payload, ebtype, tol, s, norm, reorder=0):
+def decompress_lowlevel(h, payload, ebtype, tol, s, norm, reorder=0, single_dim=False):
     p = huffman_parse(payload)
     sym = huffman_decode(p).astype(np.int64)
     if reorder:  # outliers are indexed in the linearised order: restore them first
         if len(p["oidx"]):
             sym[np.asarray(p["oidx"], dtype=np.int64)] = p["oval"]
         sym = delinearize(h, sym)
-        v = dequantize(h, sym, (), (), ebtype, tol, s, norm, int(p["dict_size"]))
-        return recompose(h, v)
+        v = dequantize(h, sym, (), (), ebtype, tol, s, norm, int(p["dict_size"]), single_dim)
+        return recompose_single(h, v) if single_dim else recompose(h, v)
     v = dequantize(h, sym, p["oidx"], p["oval"], ebtype, tol, s, norm,
-                   int(p["dict_size"]))
+                   int(p["dict_size"]), single_dim)
+    if single_dim:
+        return recompose_single(h, v)
     return recompose(h, v)
 
 

@@ -33,7 +33,7 @@ class RefxArgs(C.Structure):
         ("payload", C.c_void_p), ("payload_cap", C.c_uint64),
         ("payload_size", C.c_uint64),
         ("lossless", C.c_int32), ("zstd_level", C.c_int32),
-        ("reorder", C.c_int32), ("pad_", C.c_int32),
+        ("reorder", C.c_int32), ("decomposition", C.c_int32),
     ]
 
 
@@ -115,27 +115,29 @@ def tables(shape, dtype, coords=None):
     return res
 
 
-def decompose(u, coords=None):
+def decompose(u, coords=None, decomposition=0):
     keep = []
     v = np.array(u, copy=True, order="C")
     a = _base_args(v.shape, v.dtype, coords, 8192, 20480, keep)
     a.op = OP_DECOMPOSE
+    a.decomposition = decomposition
     a.data = v.ctypes.data
     assert lib().refx_run(C.byref(a)) == 0
     return v
 
 
-def recompose(v, coords=None):
+def recompose(v, coords=None, decomposition=0):
     keep = []
     u = np.array(v, copy=True, order="C")
     a = _base_args(u.shape, u.dtype, coords, 8192, 20480, keep)
     a.op = OP_RECOMPOSE
+    a.decomposition = decomposition
     a.data = u.ctypes.data
     assert lib().refx_run(C.byref(a)) == 0
     return u
 
 
-def compress(u, ebtype, tol, s, coords=None, dict_size=8192, chunk_size=20480, lossless=0, reorder=0):
+def compress(u, ebtype, tol, s, coords=None, dict_size=8192, chunk_size=20480, lossless=0, reorder=0, decomposition=0):
     """Low-level Compressor::Compress staged; returns dict with payload bytes,
     norm, decomposed coefficients, quantized (dict-shifted) int64, outlier count."""
     keep = []
@@ -144,6 +146,7 @@ def compress(u, ebtype, tol, s, coords=None, dict_size=8192, chunk_size=20480, l
     a.op = OP_COMPRESS
     a.lossless = lossless
     a.reorder = reorder
+    a.decomposition = decomposition
     a.ebtype = ebtype
     a.tol = tol
     _set_s(a, s)
@@ -164,13 +167,14 @@ def compress(u, ebtype, tol, s, coords=None, dict_size=8192, chunk_size=20480, l
 
 
 def decompress(payload, shape, dtype, ebtype, tol, s, norm, coords=None,
-               dict_size=8192, chunk_size=20480, lossless=0, reorder=0):
+               dict_size=8192, chunk_size=20480, lossless=0, reorder=0, decomposition=0):
     keep = []
     out = np.zeros(shape, dtype=dtype)
     a = _base_args(shape, dtype, coords, dict_size, chunk_size, keep)
     a.op = OP_DECOMPRESS
     a.lossless = lossless
     a.reorder = reorder
+    a.decomposition = decomposition
     a.ebtype = ebtype
     a.tol = tol
     a.norm = norm

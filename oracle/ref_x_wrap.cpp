@@ -49,6 +49,7 @@ static Config make_config(const refx_args *a) {
   if (a->zstd_level)
     cfg.zstd_compress_level = a->zstd_level;
   cfg.reorder = a->reorder;
+  cfg.decomposition = a->decomposition == 1 ? decomposition_type::SingleDim : decomposition_type::MultiDim;
   cfg.huff_dict_size = a->dict_size;
   cfg.huff_block_size = a->chunk_size;
   cfg.normalize_coordinates = true;

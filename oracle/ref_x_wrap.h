@@ -36,7 +36,7 @@ typedef struct refx_args {
   int32_t lossless;      /* mgard_x::lossless_type: 0 Huffman, 2 Huffman_Zstd */
   int32_t zstd_level;    /* 0: reference default (3) */
   int32_t reorder;       /* Config::reorder: 1 = level-linearised quantised order */
-  int32_t pad_;
+  int32_t decomposition; /* decomposition_type: 0 MultiDim, 1 SingleDim */
 } refx_args;
 
 #ifdef __cplusplus

@@ -523,3 +523,57 @@ def test_level_linearised_order(env, shape, dtype, s, tol):
         # each side decodes the other's block to what the writer's own decoder gives
         assert np.array_equal(theirs, back)
         assert np.array_equal(ours, ref_x.decompress(r["payload"], shape, dtype, ref_x.REL, tol, s, r["norm"], reorder=1))
+
+
+@pytest.mark.parametrize("shape,dtype,nonuniform", [
+    ((17,), np.float32, False), ((6,), np.float64, False), ((100,), np.float64, True), ((10, 7), np.float64, False),
+    ((9, 9), np.float32, True), ((64, 33), np.float32, False), ((17, 19, 21), np.float32, False),
+    ((12, 13, 14), np.float64, True), ((5, 6, 9), np.float32, False), ((65, 65, 65), np.float32, False),
+    ((33, 40, 65), np.float64, False)])
+def test_single_dimension_decomposition(env, shape, dtype, nonuniform):
+    """decomposition_type::SingleDim (hierarchy ONE_DIM_AT_A_TIME_WITH_GHOST_NODES), D <= 3:
+    coefficients and recomposition bit-exact, payload identical to the oracle's, error bound,
+    header, cross-decoding with the reference build."""
+    torch, mg, d = env
+    rng = np.random.default_rng(2)
+    coords = None
+    if nonuniform:
+        coords = []
+        for n in shape:
+            x = np.concatenate([[0.0], np.cumsum(rng.uniform(1, 2, n - 1))])
+            coords.append((x / x[-1]).astype(dtype))
+    u = field(shape, dtype, 6)
+    h = mo.Hierarchy(shape, dtype, coords)
+    cfg = mg.Config()
+    cfg.decomposition = mg.decomposition_type.SingleDim
+    p = mg.Plan(shape, dtype, coords, config=cfg)
+    du = dev(torch, u, d)
+    coef = p.decompose(du)
+    ref_coef = mo.decompose_single(h, u)
+    assert np.array_equal(coef.cpu().numpy(), ref_coef)
+    assert np.array_equal(p.recompose(coef).cpu().numpy(), mo.recompose_single(h, ref_coef))
+    for s, tol in ((np.inf, 1e-3), (0.0, 1e-2)):
+        pay, norm = p.compress(du, mo.REL, tol, s)
+        m = mo.compress_lowlevel(h, u, mo.REL, tol, s, dtype(norm), single_dim=True)
+        check_payload(pay.cpu().numpy().tobytes(), m["payload"])
+        back = p.decompress(pay, mo.REL, tol, s, norm).cpu().numpy()
+        assert np.array_equal(back, mo.decompress_lowlevel(h, m["payload"], mo.REL, tol, s, dtype(norm), single_dim=True))
+        if np.isinf(s):
+            assert np.abs(back - u).max() <= tol * np.abs(u).max()
+        if ref_x.available():
+            theirs = ref_x.decompress(pay.cpu().numpy(), shape, dtype, ref_x.REL, tol, s, norm, coords, decomposition=1)
+            assert np.array_equal(theirs, back)
+    st = mg.compress(u, 1e-3, np.inf, mo.REL, coords=coords, config=cfg)
+    out = mg.decompress(st)
+    assert np.abs(out - u).max() <= 1e-3 * np.abs(u).max()
+    # FunctionDecomposition.hierarchy = ONE_DIM_AT_A_TIME_WITH_GHOST_NODES (field 8.2 = 2)
+    hb = mg.peek_header(st)["header_bytes"]
+    assert bytes([0x42, 0x02, 0x10, 0x02]) in st[:hb].tobytes()
+
+
+def test_single_dimension_rejects_more_than_three_dimensions(env):
+    torch, mg, d = env
+    cfg = mg.Config()
+    cfg.decomposition = mg.decomposition_type.SingleDim
+    with pytest.raises(mg.MgardError):
+        mg.compress(field((5, 6, 7, 9), np.float32, 1), 1e-3, np.inf, mo.REL, config=cfg)

@@ -117,3 +117,41 @@ def test_level_linearised_order(case):
     assert np.array_equal(ref["oidx"][o], m["oidx"]) and np.array_equal(ref["oval"][o], m["oval"])
     back = mo.decompress_lowlevel(h, r["payload"].tobytes(), mo.REL, tol, s, dt(r["norm"]), reorder=1)
     assert np.array_equal(back, ref_x.decompress(r["payload"], shape, dt, ref_x.REL, tol, s, r["norm"], reorder=1))
+
+
+def _rand_coords(rng, shape, dt):
+    out = []
+    for n in shape:
+        x = np.concatenate([[0.0], np.cumsum(rng.uniform(1, 2, n - 1))])
+        out.append((x / x[-1]).astype(dt))
+    return out
+
+
+@pytest.mark.parametrize("shape,dt,nonuniform", [
+    ((17,), np.float32, False), ((6,), np.float64, False), ((10, 7), np.float64, False), ((9, 9), np.float32, True),
+    ((17, 19, 21), np.float32, False), ((12, 13, 14), np.float64, True), ((5, 6, 9), np.float32, False),
+    ((64, 33), np.float32, False)])
+def test_single_dimension_decomposition(shape, dt, nonuniform):
+    """decomposition_type::SingleDim (DataRefactoring/SingleDimension/*.hpp), D <= 3:
+    coefficients, recomposition, quantised values and Huffman block vs the reference."""
+    rng = np.random.default_rng(1)
+    coords = _rand_coords(rng, shape, dt) if nonuniform else None
+    u = field(shape, dt, 4)
+    h = mo.Hierarchy(shape, dt, coords)
+    a = ref_x.decompose(u, coords, decomposition=1)
+    assert np.array_equal(a, mo.decompose_single(h, u))
+    assert np.array_equal(ref_x.recompose(a, coords, decomposition=1), mo.recompose_single(h, a))
+    for s, tol in ((np.inf, 1e-3), (0.0, 1e-2)):
+        r = ref_x.compress(u, ref_x.REL, tol, s, coords, decomposition=1)
+        m = mo.compress_lowlevel(h, u, mo.REL, tol, s, dt(r["norm"]), single_dim=True)
+        assert np.array_equal(m["quantized"], r["quantized"])
+        ref = mo.huffman_parse(r["payload"].tobytes())
+        ok = False
+        for oob in (0, 0xFFFFFFFF):
+            mine = mo.huffman_parse(mo.huffman_compress(m["quantized"], 8192, 20480, m["oidx"], m["oval"], oob))
+            ok = ok or all(np.array_equal(mine[k], ref[k]) for k in
+                           ("bits", "word_offset", "first", "entry", "keys", "ddata"))
+        assert ok
+        back = mo.decompress_lowlevel(h, r["payload"].tobytes(), mo.REL, tol, s, dt(r["norm"]), single_dim=True)
+        assert np.array_equal(back, ref_x.decompress(r["payload"], shape, dt, ref_x.REL, tol, s, r["norm"], coords,
+                                                     decomposition=1))

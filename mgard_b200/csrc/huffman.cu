@@ -838,6 +838,14 @@ decode_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__restr
     const u64 B64 = bits[c];
     const u64 w0 = woff[c];
     const u64 nw = (B64 - 1) / 64 + 1;
+    // the per-chunk fields come from the stream: a chunk that does not lie inside the
+    // bit stream (or is longer than `chunk` codewords of 64 bits can be) decodes to zeros
+    if (B64 == 0 || B64 > (u64)chunk * 64 || w0 > total_words || nw > total_words - w0) {
+      const u64 cnt_ = min((u64)chunk, n - c * (u64)chunk);
+      for (u64 i = tid; i < cnt_; i += DEC_T)
+        out[c * (u64)chunk + i] = (OUT)0;
+      continue;
+    }
     const u64 *src = ddata + w0;
     const unsigned B = (unsigned)B64;
     const unsigned NS = (B + DEC_SB - 1) / DEC_SB;
@@ -1020,7 +1028,7 @@ __device__ __forceinline__ unsigned fast_decode_one(const FastTables &t, unsigne
 
 template <int NT, typename OUT>
 __global__ void __launch_bounds__(NT, NT <= 512 ? 2 : 1)
-decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
+decode_fast_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__restrict__ bits,
                    const u64 *__restrict__ woff, u64 nchunk, int chunk, u64 n,
                    const u64 *__restrict__ decodebook, int dict, unsigned bufw,
                    const unsigned *__restrict__ n_work, const unsigned *__restrict__ work,
@@ -1102,7 +1110,9 @@ decode_fast_kernel(const u64 *__restrict__ ddata, const u64 *__restrict__ bits,
     const u64 c = work ? (u64)work[wk] : wk;
     const u64 B64 = bits[c];
     const u64 nw64 = (B64 - 1) / 64 + 1;
-    if (nw64 > bufw || B64 == 0) {
+    // too large for this launch's buffer, or fields (they come from the stream) that
+    // point outside the bit stream: left to decode_kernel, which rejects the latter
+    if (nw64 > bufw || B64 == 0 || woff[c] > total_words || nw64 > total_words - woff[c]) {
       if (tid == 0)
         skipped[atomicAdd(n_skipped, 1u)] = (unsigned)c;
       continue;
@@ -1294,14 +1304,14 @@ int launch_decoders(mgb_plan *p, const u64 *ddata, u64 total_words, const u64 *b
     unsigned fblocks = (unsigned)std::min<u64>(nchunk, 148 * 2);
     MGB_LAUNCH(MGB_K_DECODE, st,
                (decode_fast_kernel<DF_T, OUT><<<fblocks, DF_T, fast_smem(fast_bufw, DF_T), st>>>(
-                   ddata, bits, woff, nchunk, chunk, n, decodebook, dict, fast_bufw, nullptr, nullptr,
-                   cnt1, list1, out, scale)));
+                   ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict, fast_bufw, nullptr,
+                   nullptr, cnt1, list1, out, scale)));
   }
   if (big_bufw) {
     unsigned fblocks = (unsigned)std::min<u64>(nchunk, 148);
     MGB_LAUNCH(MGB_K_DECODE, st,
                (decode_fast_kernel<DF_TBIG, OUT><<<fblocks, DF_TBIG, fast_smem(big_bufw, DF_TBIG), st>>>(
-                   ddata, bits, woff, nchunk, chunk, n, decodebook, dict, big_bufw,
+                   ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict, big_bufw,
                    fast_bufw ? cnt1 : nullptr, fast_bufw ? list1 : nullptr, cnt2, list2, out, scale)));
   }
   // what decode_kernel has to look at: the second list, else the first

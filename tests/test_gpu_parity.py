@@ -577,3 +577,34 @@ def test_single_dimension_rejects_more_than_three_dimensions(env):
     cfg.decomposition = mg.decomposition_type.SingleDim
     with pytest.raises(mg.MgardError):
         mg.compress(field((5, 6, 7, 9), np.float32, 1), 1e-3, np.inf, mo.REL, config=cfg)
+
+
+def test_corrupted_streams_fail_cleanly(env):
+    """Bytes of a stream are untrusted input: flipping any of them must give an error or
+    garbage of the right shape, never an out-of-bounds access (the CUDA context must
+    survive: a clean stream still decodes afterwards)."""
+    torch, mg, d = env
+    u = field((40, 33, 37), np.float32, 8) + 0.05 * np.random.default_rng(1).standard_normal((40, 33, 37)).astype(np.float32)
+    for cfg in (None, "reorder"):
+        c = mg.Config()
+        if cfg == "reorder":
+            c.reorder = 1
+        st = mg.compress(u, 1e-4, np.inf, mo.REL, config=c)
+        hb = mg.peek_header(st)["header_bytes"]
+        good = mg.decompress(st)
+        rng = np.random.default_rng(99)
+        # the per-chunk tables, the decode tables, the bit stream and the outlier list
+        regions = [(hb + 8, hb + 8 + 24 + 64), (hb + 8 + 24, hb + 8 + 24 + 2200), (hb, st.size)]
+        for trial in range(60):
+            lo, hi = regions[trial % len(regions)]
+            bad = st.copy()
+            for _ in range(int(rng.integers(1, 5))):
+                k = int(rng.integers(lo, min(hi, st.size)))
+                bad[k] = np.uint8(rng.integers(0, 256))
+            try:
+                out = mg.decompress(bad)
+                assert out.shape == u.shape
+            except mg.MgardError:
+                pass
+        torch.cuda.synchronize()
+        assert np.array_equal(mg.decompress(st), good)

@@ -1259,14 +1259,24 @@ int recompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
     cudaStream_t sl = (fork && l < p->L) ? sc : st;
     if (tiled3d(p)) {
       if (fork && l == p->L) {
+        // the finest level's solves do not need the coarse values either: they run
+        // beside the coarse-level chain too, and only the subtraction waits for it
+        // (same arithmetic as the subtraction fused into the last solve)
+        static const bool early_solve = getenv("MGB_NO_EARLY_SOLVE") == nullptr;
         w = (T *)p->d_wA;
+        if (early_solve)
+          thomas_all<T>(p, l, w, (T *)nullptr, 0, st);
         MGB_CUDA_CHECK(cudaEventRecord(p->ev_join, sc));
         MGB_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_join, 0));
+        if (early_solve)
+          axpy<T>(coarse, w, (i64)mgb_level_elems(p, l - 1), 1, st);
+        else
+          thomas_all<T>(p, l, w, coarse, 2, sl);
       } else {
         w = (T *)(fork ? p->d_wB : p->d_wA);
         launch_masstrans3d<T>(p, l, d_in, w, sl);
+        thomas_all<T>(p, l, w, coarse, 2, sl);
       }
-      thomas_all<T>(p, l, w, coarse, 2, sl);
     } else {
       rc = correction<T>(p, l, d_in, &w, coarse, 2, st);
     }

@@ -94,8 +94,23 @@ extern "C" int mgb_compress_lowlevel(mgb_plan *p, const void *d_in, int ebtype,
   int rc = ensure_lowlevel_workspace(p);
   if (rc)
     return rc;
-  // Compressor.hpp:121-129: the norm is only computed for relative bounds
-  if (ebtype == MGB_REL) {
+  // Compressor.hpp:121-129: the norm is only computed for relative bounds.  For the
+  // L-infinity norm of fp32 data on the tiled 3-D path it is a by-product of the
+  // finest level's coefficient kernel (no separate pass, no synchronisation up front)
+  const bool fuse_norm = ebtype == MGB_REL && is_inf(s) && p->dtype == MGB_F32 && p->D == 3 &&
+                         !p->force_generic && p->shape[1] * p->shape[2] < (1ull << 31) && p->L >= 1 &&
+                         p->cfg.decomposition == 0 && getenv("MGB_NO_FUSED_NORM") == nullptr;
+  p->fused_norm.armed = false;
+  if (fuse_norm) {
+    if (!p->d_absmax) {
+      MGB_CUDA_CHECK(cudaMalloc(&p->d_absmax, 8));
+      MGB_CUDA_CHECK(cudaMallocHost(&p->h_absmax, 8));
+      MGB_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_norm, cudaEventDisableTiming));
+    }
+    MGB_CUDA_CHECK(cudaMemsetAsync(p->d_absmax, 0, 8, st));
+    p->fused_norm.armed = true;
+    p->fused_norm.collected = false;
+  } else if (ebtype == MGB_REL) {
     MGB_CUDA_CHECK(cudaStreamSynchronize(st));
     rc = mgb_norm(p, d_in, s, norm);
     if (rc)
@@ -112,6 +127,11 @@ extern "C" int mgb_compress_lowlevel(mgb_plan *p, const void *d_in, int ebtype,
   p->early_q.norm = *norm;
   rc = mgb_decompose_impl(p, d_in, p->d_coef, st);
   p->early_q.armed = false;
+  if (rc == MGB_SUCCESS && fuse_norm) {
+    rc = mgb_fused_norm_collect(p);
+    *norm = p->fused_norm.value;
+  }
+  p->fused_norm.armed = false;
   if (rc)
     return rc;
   for (int attempt = 0; attempt < 2; attempt++) {

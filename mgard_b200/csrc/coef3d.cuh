@@ -51,10 +51,13 @@ __device__ __forceinline__ int src_index(int j, int n, int np) {
   return j;
 }
 
-template <typename T>
+// ABSMAX (fp32 only): max |x| over the input as a by-product -- every node is the
+// "own" node of exactly one thread -- so that a relative L-infinity bound needs no
+// separate pass over the input (norm_calculator, NormCalculator.hpp:13-83).
+template <typename T, bool ABSMAX>
 __global__ void __launch_bounds__(NT)
 coef3d_kernel(const Params<T> P, const T *__restrict__ in, T *__restrict__ coef,
-       T *__restrict__ coarse) {
+       T *__restrict__ coarse, unsigned *__restrict__ absmax_bits) {
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   int bid = blockIdx.x;
   const int tf = bid % P.tiles_f;
@@ -102,6 +105,7 @@ coef3d_kernel(const Params<T> P, const T *__restrict__ in, T *__restrict__ coef,
     return e;
   };
   Even lo = load_even(src_index(2 * kr0, P.n[0], P.np[0]));
+  float amax = 0.0f;
 #pragma unroll
   for (int lr = 0; lr < TR; lr++) {
     const int kr = kr0 + lr;
@@ -126,6 +130,10 @@ coef3d_kernel(const Params<T> P, const T *__restrict__ in, T *__restrict__ coef,
     // even-sized dimension the odd plane in front of the ghost plane is a hole)
     if (kr + 1 < rr)
       hi = load_even(src_index(2 * kr + 2, P.n[0], P.np[0]));
+    if (ABSMAX)
+      amax = fmaxf(fmaxf(fmaxf(amax, fabsf((float)lo.v00)), fmaxf(fabsf((float)lo.v01), fabsf((float)lo.v10))),
+                   fmaxf(fmaxf(fabsf((float)lo.v11), fabsf((float)o00)),
+                         fmaxf(fabsf((float)o01), fmaxf(fabsf((float)o10), fabsf((float)o11)))));
     coarse[(i64)kr * P.sc[0] + c_col] = lo.v00;
     const i64 b_re = (i64)kr * P.sb[0], b_ro = (i64)(rr + kr) * P.sb[0];
     const T lf0 = lerp_ref(lo.v00, lo.v02, rf), lf1 = lerp_ref(lo.v20, lo.v22, rf);
@@ -151,6 +159,13 @@ coef3d_kernel(const Params<T> P, const T *__restrict__ in, T *__restrict__ coef,
       }
     }
     lo = hi;
+  }
+  if (ABSMAX) {
+    // non-negative floats order like their bit patterns
+    const unsigned mask = __activemask();
+    const unsigned m = __reduce_max_sync(mask, __float_as_uint(amax));
+    if ((threadIdx.x & 31) == __ffs(mask) - 1)
+      atomicMax(absmax_bits, m);
   }
 }
 

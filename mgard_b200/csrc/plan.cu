@@ -379,6 +379,11 @@ extern "C" void mgb_plan_destroy(mgb_plan *p) {
   cudaFree(p->d_cbuf);
   cudaFree(p->d_wA);
   cudaFree(p->d_sd);
+  cudaFree(p->d_absmax);
+  if (p->h_absmax)
+    cudaFreeHost(p->h_absmax);
+  if (p->ev_norm)
+    cudaEventDestroy(p->ev_norm);
   cudaFree(p->d_wB);
   if (p->side)
     cudaStreamDestroy(p->side);

@@ -91,6 +91,17 @@ struct mgb_plan {
     uint64_t first = 0; // elements [first, N) were quantized early
   } early_q;
 
+  // relative L-infinity bound, fp32, tiled 3-D path: max |x| comes out of the finest
+  // level's coefficient kernel instead of a separate pass (armed by
+  // mgb_compress_lowlevel, produced and collected in refactor.cu)
+  unsigned *d_absmax = nullptr;
+  float *h_absmax = nullptr; // pinned
+  cudaEvent_t ev_norm = nullptr;
+  struct {
+    bool armed = false, collected = false;
+    double value = 0;
+  } fused_norm;
+
   const unsigned char *dtab(uint64_t off) const { return d_tables + off * tsize; }
 };
 
@@ -121,6 +132,7 @@ int mgb_plan_ensure_workspace(mgb_plan *p);
 uint64_t mgb_level_elems(const mgb_plan *p, int l);
 
 // refactor.cu
+int mgb_fused_norm_collect(mgb_plan *p);
 int mgb_decompose_impl(mgb_plan *p, const void *d_in, void *d_out,
                        cudaStream_t st);
 int mgb_recompose_impl(mgb_plan *p, const void *d_in, void *d_out,

@@ -23,6 +23,7 @@
 // D == 3 takes the tiled kernels of coef3d.cuh / masstrans3d.cuh / restore3d.cuh.
 #include <algorithm>
 #include <cstdint>
+#include <limits>
 
 #include "coef3d.cuh"
 #include "masstrans3d.cuh"
@@ -944,7 +945,8 @@ bool launch_thomas_smem(T *w, int n, i64 inner, i64 outer, const T *fw, const T 
 
 // D == 3: coefficients (coef3d.cuh) and load vector (masstrans3d.cuh)
 template <typename T>
-void launch_coef3d(mgb_plan *p, int l, const T *in, T *coef, T *coarse, cudaStream_t st) {
+void launch_coef3d(mgb_plan *p, int l, const T *in, T *coef, T *coarse, cudaStream_t st,
+                   unsigned *absmax = nullptr) {
   coef3d::Params<T> P;
   i64 full[5], dc[5], dn[5];
   dense_strides(p->shape, 3, full);
@@ -963,7 +965,12 @@ void launch_coef3d(mgb_plan *p, int l, const T *in, T *coef, T *coarse, cudaStre
   P.tiles_c = (P.nc[1] + coef3d::TC - 1) / coef3d::TC;
   P.tiles_f = (P.nc[2] + coef3d::TF - 1) / coef3d::TF;
   unsigned grid = (unsigned)(tiles_r * P.tiles_c * P.tiles_f);
-  MGB_LAUNCH(MGB_K_COEF, st, (coef3d::coef3d_kernel<T><<<grid, coef3d::NT, 0, st>>>(P, in, coef, coarse)));
+  if (absmax && sizeof(T) == 4)
+    MGB_LAUNCH(MGB_K_COEF, st,
+               (coef3d::coef3d_kernel<T, true><<<grid, coef3d::NT, 0, st>>>(P, in, coef, coarse, absmax)));
+  else
+    MGB_LAUNCH(MGB_K_COEF, st,
+               (coef3d::coef3d_kernel<T, false><<<grid, coef3d::NT, 0, st>>>(P, in, coef, coarse, nullptr)));
 }
 template <typename T>
 void launch_masstrans3d(mgb_plan *p, int l, const T *coef, T *w_out, cudaStream_t st) {
@@ -1145,9 +1152,22 @@ int decompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
     T *coarse = cbuf + p->cbuf_off[l - 1];
     if (tiled3d(p)) {
       T *w = (T *)p->d_wA;
-      launch_coef3d<T>(p, l, cur, d_out, coarse, st);
+      const bool with_norm = l == p->L && p->fused_norm.armed && sizeof(T) == 4;
+      launch_coef3d<T>(p, l, cur, d_out, coarse, st, with_norm ? p->d_absmax : nullptr);
+      if (with_norm) {
+        MGB_CUDA_CHECK(cudaMemcpyAsync(p->h_absmax, p->d_absmax, sizeof(float), cudaMemcpyDeviceToHost, st));
+        MGB_CUDA_CHECK(cudaEventRecord(p->ev_norm, st));
+      }
       launch_masstrans3d<T>(p, l, d_out, w, st);
       thomas_all<T>(p, l, w, coarse, 1, st);
+      if (with_norm && p->early_q.armed) {
+        // the quantizer launched below needs the norm on the host: wait for the
+        // coefficient kernel only (the load vector and the solves are already queued)
+        rc = mgb_fused_norm_collect(p);
+        if (rc)
+          return rc;
+        p->early_q.norm = p->fused_norm.value;
+      }
       if (l == p->L && p->early_q.armed && (void *)d_out == (void *)p->d_coef) {
         // planes r >= coarse size hold level-L coefficients only (final).  Quantize
         // them now, two blocks per SM, while the coarse levels - a chain of small
@@ -1649,6 +1669,20 @@ template <typename T> int recompose_single_t(mgb_plan *p, const T *d_in, T *d_ou
 }
 
 } // namespace
+
+// max |x| produced by the finest level's coefficient kernel -> norm in T
+// (zero replaced by epsilon, NormCalculator.hpp:72-80)
+int mgb_fused_norm_collect(mgb_plan *p) {
+  if (!p->fused_norm.armed || p->fused_norm.collected)
+    return MGB_SUCCESS;
+  MGB_CUDA_CHECK(cudaEventSynchronize(p->ev_norm));
+  float f = *p->h_absmax;
+  if (f == 0)
+    f = std::numeric_limits<float>::epsilon();
+  p->fused_norm.value = f;
+  p->fused_norm.collected = true;
+  return MGB_SUCCESS;
+}
 
 int mgb_decompose_impl(mgb_plan *p, const void *d_in, void *d_out, cudaStream_t st) {
   if (p->cfg.decomposition == 1) {

@@ -609,3 +609,30 @@ def test_corrupted_streams_fail_cleanly(env):
                 pass
         torch.cuda.synchronize()
         assert np.array_equal(mg.decompress(st), good)
+
+
+def test_fused_norm_equals_norm_pass(env, monkeypatch):
+    """Relative L-infinity bound, fp32, 3-D: max|x| comes out of the finest level's
+    coefficient kernel.  Same norm and same payload as with the separate norm pass
+    (norm_calculator, NormCalculator.hpp:13-83), including even sizes (ghost nodes),
+    an all-zero field (norm -> epsilon) and a maximum on the last node."""
+    torch, mg, d = env
+    for shape in ((33, 40, 65), (34, 41, 66), (17, 19, 21), (6, 6, 6)):
+        for kind in ("field", "zeros", "corner"):
+            u = field(shape, np.float32, 3)
+            if kind == "zeros":
+                u = np.zeros(shape, dtype=np.float32)
+            elif kind == "corner":
+                u[-1, -1, -1] = -37.5
+            du = dev(torch, u, d)
+            p = mg.Plan(shape, np.float32)
+            monkeypatch.delenv("MGB_NO_FUSED_NORM", raising=False)
+            pay1, n1 = p.compress(du, mo.REL, 1e-3, np.inf)
+            pay1 = pay1.cpu().numpy().copy()
+            monkeypatch.setenv("MGB_NO_FUSED_NORM", "1")
+            pay2, n2 = p.compress(du, mo.REL, 1e-3, np.inf)
+            assert n1 == n2 == p.norm(du, np.inf)
+            expect = float(np.abs(u).max()) if kind != "zeros" else float(np.finfo(np.float32).eps)
+            assert n1 == expect
+            assert pay1.tobytes() == pay2.cpu().numpy().tobytes()
+    monkeypatch.delenv("MGB_NO_FUSED_NORM", raising=False)

@@ -49,6 +49,9 @@ enum Op {
   OP_ZERO_OLD_COPY_NEW,     // decompose.tpp:93-107
   OP_SUB_OLD_ZERO_NEW,      // decompose.tpp:43-57
   OP_NEG_OLD_SUB_NEW,       // decompose.tpp:59-76
+  OP_COEF_FUSED,            // copy_on_old_zero_on_new + prolongation + subtract in one pass
+  OP_RECOMP_OLD,            // subtract_on_old + copy_negation_on_old (old nodes)
+  OP_RECOMP_NEW,            // prolongation + subtract_on_new (new nodes)
   OP_SHUFFLE,               // shuffle.tpp:8-21
   OP_UNSHUFFLE,             // shuffle.tpp:23-37
   OP_QUANT_NODAL,           // nodal coefficients -> shuffled int64
@@ -111,6 +114,39 @@ template <typename T> __device__ __forceinline__ long long quantize_one(const Le
   return (long long)copysign(mag, (double)x);
 }
 
+// Value the dimension-by-dimension TensorProlongationAddition (TensorProlongation.tpp:22-69,
+// TensorLinearOperator.tpp:71-109) leaves on a new node of the level-l mesh when the new
+// nodes start from zero: nested 1-D interpolations from the surrounding old nodes, the
+// lowest new dimension innermost (it is the first pass to run), each stage added to zero
+// exactly as the passes do.  `src` holds the values on the old nodes.
+template <typename T>
+__device__ __forceinline__ T nested_interpolation(const LevelArgs<T> &a, const T *__restrict__ src,
+                                                  const uint32_t *j, uint64_t off) {
+  int dims[CD], nd = 0;
+#pragma unroll
+  for (int d = 0; d < CD; d++)
+    if (a.info[d][j[d]] & 1u)
+      dims[nd++] = d;
+  T val[1 << CD];
+  for (int c = 0; c < (1 << nd); c++) {
+    long long o = (long long)off;
+    for (int k = 0; k < nd; k++) {
+      const int d = dims[k];
+      const uint32_t jj = ((c >> k) & 1) ? j[d] + 1 : j[d] - 1;
+      o += ((long long)a.pos[d][jj] - (long long)a.pos[d][j[d]]) * (long long)a.stride[d];
+    }
+    val[c] = src[o];
+  }
+  for (int k = 0; k < nd; k++) {
+    const int d = dims[k];
+    const T xl = a.x[d][j[d] - 1], xm = a.x[d][j[d]], xr = a.x[d][j[d] + 1];
+    const T wr = (T)1 / (xr - xl);
+    for (int c = 0; c < (1 << (nd - k - 1)); c++)
+      val[c] = (T)0 + (val[2 * c] * (xr - xm) + val[2 * c + 1] * (xm - xl)) * wr;
+  }
+  return val[0];
+}
+
 template <typename T, int OP> __global__ void __launch_bounds__(256) cpu_level_kernel(const LevelArgs<T> a) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.total)
@@ -150,6 +186,23 @@ template <typename T, int OP> __global__ void __launch_bounds__(256) cpu_level_k
     a.buf[off] = allold ? a.buf[off] + (T)(-1) * a.v[off] : (T)0;
   } else if (OP == OP_NEG_OLD_SUB_NEW) {
     a.v[off] = allold ? -a.buf[off] : a.v[off] + (T)(-1) * a.buf[off];
+  } else if (OP == OP_COEF_FUSED) {
+    // old nodes are only read, new nodes only written: in place
+    if (allold) {
+      a.buf[off] = 0;
+    } else {
+      const T r = a.v[off] - nested_interpolation<T>(a, a.v, j, off);
+      a.v[off] = r;
+      a.buf[off] = r;
+    }
+  } else if (OP == OP_RECOMP_OLD) {
+    // level l-1 box: buf = projection - v (kept for the interpolation), v = -buf
+    const T t = a.buf[off] + (T)(-1) * a.v[off];
+    a.buf[off] = t;
+    a.v[off] = -t;
+  } else if (OP == OP_RECOMP_NEW) {
+    if (!allold)
+      a.v[off] = a.v[off] + (T)(-1) * nested_interpolation<T>(a, a.buf, j, off);
   } else if (OP == OP_ADD_OLD) {
     a.v[off] = a.v[off] + (T)1 * a.buf[off];
   } else if (OP == OP_PROLONG) {
@@ -830,6 +883,13 @@ template <typename T> T *project(mgb_cpu_plan *p, int l, T *b0, T *b1, cudaStrea
   return cur;
 }
 
+// One pass instead of copy / D prolongation passes / subtract (MGB_CPU_UNFUSED=1: the
+// reference's pass-by-pass sequence; both give the same bits)
+inline bool fused_passes() {
+  static const bool on = getenv("MGB_CPU_UNFUSED") == nullptr;
+  return on;
+}
+
 // mgard::decompose on the nodal array `v` (decompose.tpp:129-174)
 template <typename T> void decompose_nodal(mgb_cpu_plan *p, T *v, cudaStream_t st) {
   T *b0 = reinterpret_cast<T *>(p->d_b0), *b1 = reinterpret_cast<T *>(p->d_b1);
@@ -837,15 +897,19 @@ template <typename T> void decompose_nodal(mgb_cpu_plan *p, T *v, cudaStream_t s
     LevelArgs<T> a = level_args<T>(p, l, -1, SEL_ALL);
     a.v = v;
     a.buf = b0;
-    launch_level<T, OP_COPY_OLD_ZERO_NEW>(a, st);
-    for (int d = 0; d < CD; d++) {
-      if ((p->flat >> d) & 1)
-        continue;
-      LevelArgs<T> pa = level_args<T>(p, l, d, SEL_NEW);
-      pa.buf = b0;
-      launch_level<T, OP_PROLONG>(pa, st);
+    if (fused_passes()) {
+      launch_level<T, OP_COEF_FUSED>(a, st);
+    } else {
+      launch_level<T, OP_COPY_OLD_ZERO_NEW>(a, st);
+      for (int d = 0; d < CD; d++) {
+        if ((p->flat >> d) & 1)
+          continue;
+        LevelArgs<T> pa = level_args<T>(p, l, d, SEL_NEW);
+        pa.buf = b0;
+        launch_level<T, OP_PROLONG>(pa, st);
+      }
+      launch_level<T, OP_SUB_NEW>(a, st);
     }
-    launch_level<T, OP_SUB_NEW>(a, st);
     T *corr = project<T>(p, l, b0, b1, st);
     LevelArgs<T> c = level_args<T>(p, l - 1, -1, SEL_ALL);
     c.v = v;
@@ -865,6 +929,14 @@ template <typename T> void recompose_nodal(mgb_cpu_plan *p, T *v, cudaStream_t s
     launch_level<T, OP_ZERO_OLD_COPY_NEW>(a, st);
     T *corr = project<T>(p, l, b0, b1, st);
     a.buf = corr;
+    if (fused_passes()) {
+      LevelArgs<T> c = level_args<T>(p, l - 1, -1, SEL_ALL);
+      c.v = v;
+      c.buf = corr;
+      launch_level<T, OP_RECOMP_OLD>(c, st);
+      launch_level<T, OP_RECOMP_NEW>(a, st);
+      continue;
+    }
     launch_level<T, OP_SUB_OLD_ZERO_NEW>(a, st);
     for (int d = 0; d < CD; d++) {
       if ((p->flat >> d) & 1)

@@ -480,3 +480,18 @@ def test_gpu_mgard_cli_round_trip_and_stream_identity(tmp_path):
     r = subprocess.run([exe, "compress", "--datatype", "double", "--shape", "33x20", "--smoothness", "inf",
                         "--tolerance", "1e-2", "--input", str(src), "--output", str(mid)], capture_output=True, text=True)
     assert r.returncode == 1 and "expected" in r.stderr
+
+
+def test_cxx_cpu_api_mirror_compiles(tmp_path):
+    """include/mgard_b200/compress.hpp compiles and links against the C ABI (without a
+    GPU the program stops at the hierarchy constructor: no CPU fallback)."""
+    import subprocess
+    import torch
+    exe = tmp_path / "cpu_api_roundtrip"
+    for define in ([], ["-DMGARD_ZSTD"]):
+        subprocess.check_call(["g++", "-std=c++17", *define, f"-I{ROOT}/include", f"{ROOT}/tests/cxx/cpu_api_roundtrip.cpp",
+                               "-o", str(exe), f"-L{ROOT}/mgard_b200", "-lmgard_b200",
+                               f"-Wl,-rpath,{ROOT}/mgard_b200", "-L/usr/local/cuda/lib64", "-lcudart"])
+    if not torch.cuda.is_available():
+        out = subprocess.run([str(exe)], capture_output=True, text=True)
+        assert out.returncode != 0

@@ -170,3 +170,30 @@ def test_header_records_the_second_stage_lossless():
     diff = np.nonzero(a[17:] != b[17:])[0]  # after magic | size | crc
     assert diff.size == 1 and a[17 + diff[0]] == 3 and b[17 + diff[0]] == 5
     assert mg.peek_header(a)["header_bytes"] == mg.peek_header(b)["header_bytes"] == a.size
+
+
+def test_header_records_reorder_and_single_dimension():
+    """Config::reorder -> Encoding.preprocessor = SHUFFLE, decomposition_type::SingleDim ->
+    FunctionDecomposition.hierarchy = ONE_DIM_AT_A_TIME_WITH_GHOST_NODES
+    (Metadata.cpp:360-370,408-412): header bytes equal to the oracle's proto3 encoding."""
+    import mgardx_oracle as mo
+    L = _lib.lib()
+    shape = (33, 34, 35)
+    for reorder, decomposition in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        cfg = _lib.MgbConfig()
+        L.mgb_config_default(C.byref(cfg))
+        cfg.domain_decomposition_size = 1 << 40
+        cfg.reorder = reorder
+        cfg.decomposition = decomposition
+        out = np.zeros(1 << 12, dtype=np.uint8)
+        sz = C.c_uint64(0)
+        cshape = (C.c_uint64 * 3)(*shape)
+        assert L.mgb_write_header(3, 0, cshape, 1e-3, float("inf"), 0, 2.5, None, C.byref(cfg),
+                                  out.ctypes.data, out.size, C.byref(sz)) == 0
+        got = out[:sz.value].tobytes()
+        hdr = mo.encode_header(shape, np.float32, mo.REL, 1e-3, float("inf"), np.float32(2.5), reorder=reorder)
+        if decomposition:  # field 8 (FunctionDecomposition), field 2 (hierarchy): 1 -> 2
+            assert hdr.count(b"\x42\x02\x10\x01") == 1
+            hdr = hdr.replace(b"\x42\x02\x10\x01", b"\x42\x02\x10\x02")
+        assert got == mo.encode_preamble(hdr)
+        assert mg.peek_header(np.frombuffer(got, dtype=np.uint8))["header_bytes"] == len(got)

@@ -174,3 +174,28 @@ def test_round_trip_and_error_bound():
             r = mo.compress_lowlevel(h, u, mo.REL, tol, np.inf)
             back = mo.decompress_lowlevel(h, r["payload"], mo.REL, tol, np.inf, r["norm"])
             assert np.abs(back - u).max() <= tol * np.abs(u).max()
+
+
+def test_reorder_and_single_dimension_fixtures():
+    """tests/golden/x_modes.npz (make_golden_modes.py): Config::reorder = 1 and
+    decomposition_type::SingleDim outputs of the unmodified reference build."""
+    z = np.load(os.path.join(HERE, "golden", "x_modes.npz"))
+    for i in range(int(z["count"])):
+        shape = tuple(int(x) for x in z[f"shape{i}"])
+        dt = np.float64 if int(z[f"dtype{i}"]) == 1 else np.float32
+        coords = None
+        if int(z[f"explicit{i}"]):
+            flat, coords, off = z[f"coords{i}"], [], 0
+            for m in shape:
+                coords.append(flat[off:off + m].astype(dt))
+                off += m
+        tol, s = float(z[f"tol{i}"]), float(z[f"s{i}"])
+        reorder, sd = int(z[f"reorder{i}"]), bool(int(z[f"single{i}"]))
+        h = mo.Hierarchy(shape, dt, coords)
+        u = z[f"u{i}"]
+        dec = mo.decompose_single(h, u) if sd else mo.decompose(h, u)
+        assert np.array_equal(dec, z[f"decomposed{i}"])
+        m = mo.compress_lowlevel(h, u, mo.REL, tol, s, dt(z[f"norm{i}"]), reorder=reorder, single_dim=sd)
+        assert np.array_equal(np.asarray(m["quantized"]).ravel(), z[f"quantized{i}"])
+        back = mo.decompress_lowlevel(h, m["payload"], mo.REL, tol, s, dt(z[f"norm{i}"]), reorder=reorder, single_dim=sd)
+        assert np.array_equal(back, z[f"decompressed{i}"])

@@ -1,5 +1,6 @@
 /*
- * mgard_b200 — C ABI of the B200-native MGARD-X hot path.
+ * mgard_b200 — C ABI of the B200-native MGARD hot path: the MGARD-X convention
+ * (mgb_*) and the MGARD-CPU convention (mgb_cpu_*, further down).
  *
  * Plain C: pointers, sizes and status codes only.  This is the drop-in
  * boundary: every entry point names the reference interface it replaces

@@ -147,24 +147,33 @@ __device__ __forceinline__ T nested_interpolation(const LevelArgs<T> &a, const T
   return val[0];
 }
 
-template <typename T, int OP> __global__ void __launch_bounds__(256) cpu_level_kernel(const LevelArgs<T> a) {
+// IDX: type of the linear thread index (uint32_t whenever the box has < 2^32 nodes: the
+// index decoding is a chain of divisions)
+template <typename T, int OP, typename IDX>
+__global__ void __launch_bounds__(256) cpu_level_kernel(const LevelArgs<T> a) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.total)
     return;
   uint32_t j[CD];
-  uint64_t rem = t, off = 0;
+  IDX rem = (IDX)t;
+  uint64_t off = 0;
   bool allold = true;
+  // operations that never look at the "introduced by an earlier level" flag skip its loads
+  constexpr bool NEED_OLD = !(OP == OP_PROLONG || OP == OP_MASS || OP == OP_RESTRICT || OP == OP_ADD_OLD ||
+                              OP == OP_RECOMP_OLD);
 #pragma unroll
   for (int d = CD - 1; d >= 0; d--) {
     const uint32_t c = a.cnt[d];
     uint32_t i = 0;
     if (c > 1) {
-      i = (uint32_t)(rem % c);
-      rem /= c;
+      const IDX q = rem / c;
+      i = (uint32_t)(rem - q * c);
+      rem = q;
     }
     j[d] = a.sel[d] ? a.sel[d][i] : i;
     off += (uint64_t)a.pos[d][j[d]] * a.stride[d];
-    allold = allold && !(a.info[d][j[d]] & 1u);
+    if (NEED_OLD)
+      allold = allold && !(a.info[d][j[d]] & 1u);
   }
   if (a.level0)
     allold = false;
@@ -846,7 +855,10 @@ template <typename T, int OP> void launch_level(const LevelArgs<T> &a, cudaStrea
   if (a.total == 0)
     return;
   const uint64_t blocks = (a.total + 255) / 256;
-  MGB_LAUNCH(MGB_K_AXPY, st, (cpu_level_kernel<T, OP><<<(unsigned)blocks, 256, 0, st>>>(a)));
+  if (a.total <= 0xffffffffull)
+    MGB_LAUNCH(MGB_K_AXPY, st, (cpu_level_kernel<T, OP, uint32_t><<<(unsigned)blocks, 256, 0, st>>>(a)));
+  else
+    MGB_LAUNCH(MGB_K_AXPY, st, (cpu_level_kernel<T, OP, uint64_t><<<(unsigned)blocks, 256, 0, st>>>(a)));
 }
 
 // M, R on level l, M^-1 on level l - 1 (decompose.tpp:156-163): the projection of

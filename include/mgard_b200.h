@@ -249,6 +249,15 @@ int mgb_cpu_compress(int ndim, int dtype, const uint64_t *shape,
                      const void *const *coords, double s, double tol,
                      int compressor, const void *in, void **out,
                      size_t *out_size);
+/* Preamble + header of an MGARD-CPU stream alone (host only, no device needed):
+ * write_metadata (src/format.cpp:219-233) -- "MGARD", header size (u64) and
+ * CRC32 (u32) BIG-endian (include/format.tpp:27-41), then the protobuf header of
+ * populate_defaults / TensorMeshHierarchy::populate (src/format.cpp:102-140,
+ * include/TensorMeshHierarchy.tpp:293-348). */
+int mgb_cpu_write_header(int ndim, int dtype, const uint64_t *shape,
+                         const void *const *coords, double s, double tol,
+                         int compressor, uint8_t *out, uint64_t cap,
+                         uint64_t *size);
 /* mgard::decompress(void const *, std::size_t) (include/compress.hpp:62-72):
  * *out is a malloc'ed host array of the decoded dtype and shape. */
 int mgb_cpu_decompress(const void *in, size_t in_size, void **out, int *ndim,

@@ -78,6 +78,7 @@ SIGNATURES = {
     "mgb_cpu_quantize": (_i32, [_vp, _vp, _dbl, _dbl, _vp, _vp]),
     "mgb_cpu_dequantize": (_i32, [_vp, _vp, _dbl, _dbl, _vp, _vp]),
     "mgb_cpu_compress": (_i32, [_i32, _i32, _pu64, C.POINTER(_vp), _dbl, _dbl, _i32, _vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
+    "mgb_cpu_write_header": (_i32, [_i32, _i32, _pu64, C.POINTER(_vp), _dbl, _dbl, _i32, _vp, _u64, _pu64]),
     "mgb_cpu_decompress": (_i32, [_vp, C.c_size_t, C.POINTER(_vp), C.POINTER(_i32), _pu64, C.POINTER(_i32)]),
     "mgb_launch_count": (_u64, []),
     "mgb_profile_enable": (None, [_i32]),

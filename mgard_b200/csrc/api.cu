@@ -84,7 +84,7 @@ bool is_inf(double s) { return std::isinf(s) && s > 0; }
 
 } // namespace
 
-extern "C" int mgb_compress_lowlevel(mgb_plan *p, const void *d_in, int ebtype,
+static int compress_lowlevel_impl(mgb_plan *p, const void *d_in, int ebtype,
                                      double tol, double s, double *norm,
                                      uint8_t *d_out, uint64_t cap, uint64_t *size,
                                      void *stream) {
@@ -190,7 +190,7 @@ extern "C" int mgb_compress_lowlevel(mgb_plan *p, const void *d_in, int ebtype,
   return MGB_FAILURE;
 }
 
-extern "C" int mgb_decompress_lowlevel(mgb_plan *p, const uint8_t *d_in, uint64_t size,
+static int decompress_lowlevel_impl(mgb_plan *p, const uint8_t *d_in, uint64_t size,
                                        int ebtype, double tol, double s, double norm,
                                        void *d_out, void *stream) {
   if (!p || !d_in || !d_out)
@@ -635,7 +635,7 @@ int check_args(int ndim, int dtype, const uint64_t *shape) {
 
 } // namespace
 
-extern "C" int mgb_compress(int ndim, int dtype, const uint64_t *shape, double tol,
+static int compress_impl(int ndim, int dtype, const uint64_t *shape, double tol,
                             double s, int ebtype, const void *in, void **out,
                             size_t *out_size, const void *const *coords,
                             const mgb_config *cfg_in, int output_pre_allocated) {
@@ -661,9 +661,9 @@ extern "C" int mgb_compress(int ndim, int dtype, const uint64_t *shape, double t
     cudaSetDevice(cfg.dev_id);
   }
   const size_t tsize = dtype == MGB_F32 ? 4 : 8;
-  uint64_t N = 1;
-  for (int d = 0; d < ndim; d++)
-    N *= shape[d];
+  uint64_t N = 0;
+  if (!mgb_checked_elems(ndim, shape, tsize, &N))
+    return MGB_BAD_ARGUMENT;
   Partition pt;
   rc = make_partition(ndim, shape, tsize, &cfg, pt);
   if (rc)
@@ -766,7 +766,7 @@ extern "C" int mgb_compress(int ndim, int dtype, const uint64_t *shape, double t
   return MGB_SUCCESS;
 }
 
-extern "C" int mgb_peek_header(const void *in, size_t in_size, int *ndim, uint64_t *shape,
+static int peek_header_impl(const void *in, size_t in_size, int *ndim, uint64_t *shape,
                                int *dtype, int *ebtype, double *tol, double *s,
                                double *norm, uint64_t *header_bytes) {
   if (!in || in_size < 17)
@@ -777,10 +777,8 @@ extern "C" int mgb_peek_header(const void *in, size_t in_size, int *ndim, uint64
     uint8_t pre[17];
     if (cudaMemcpy(pre, in, 17, cudaMemcpyDeviceToHost) != cudaSuccess)
       return MGB_CUDA_ERROR;
-    uint64_t hs = 0;
-    for (int i = 0; i < 8; i++)
-      hs |= (uint64_t)pre[5 + i] << (8 * i);
-    if (memcmp(pre, "MGARD", 5) != 0 || hs > in_size - 17)
+    const uint64_t hs = mgb_preamble_header_size(pre, in_size);
+    if (hs == UINT64_MAX)
       return MGB_BAD_STREAM;
     head.resize(17 + hs);
     if (cudaMemcpy(head.data(), in, 17 + hs, cudaMemcpyDeviceToHost) != cudaSuccess)
@@ -806,7 +804,7 @@ extern "C" int mgb_peek_header(const void *in, size_t in_size, int *ndim, uint64
   return MGB_SUCCESS;
 }
 
-extern "C" int mgb_decompress(const void *in, size_t in_size, void **out,
+static int decompress_impl(const void *in, size_t in_size, void **out,
                               const mgb_config *cfg_in, int output_pre_allocated,
                               int *ndim_out, uint64_t *shape_out, int *dtype_out) {
   if (!in || !out || (output_pre_allocated && !*out))
@@ -834,10 +832,8 @@ extern "C" int mgb_decompress(const void *in, size_t in_size, void **out,
       return MGB_BAD_STREAM;
     uint8_t pre[17];
     MGB_CUDA_CHECK(cudaMemcpy(pre, in, 17, cudaMemcpyDeviceToHost));
-    uint64_t hs = 0;
-    for (int i = 0; i < 8; i++)
-      hs |= (uint64_t)pre[5 + i] << (8 * i);
-    if (memcmp(pre, "MGARD", 5) != 0 || hs > in_size - 17)
+    const uint64_t hs = mgb_preamble_header_size(pre, in_size);
+    if (hs == UINT64_MAX)
       return MGB_BAD_STREAM;
     head.resize(17 + hs);
     MGB_CUDA_CHECK(cudaMemcpy(head.data(), in, 17 + hs, cudaMemcpyDeviceToHost));
@@ -863,12 +859,13 @@ extern "C" int mgb_decompress(const void *in, size_t in_size, void **out,
   cfg.decomposition = h.decomposition;
   const int ndim = h.ndim, dtype = h.dtype;
   const size_t tsize = dtype == MGB_F32 ? 4 : 8;
-  uint64_t N = 1;
-  for (int d = 0; d < ndim; d++) {
+  uint64_t N = 0;
+  for (int d = 0; d < ndim; d++)
     if (h.shape[d] < 3)
       return MGB_BAD_STREAM;
-    N *= h.shape[d];
-  }
+  // a header that passes its CRC can still announce an absurd shape
+  if (!mgb_checked_elems(ndim, h.shape, tsize, &N))
+    return MGB_BAD_STREAM;
   Partition pt;
   pt.decomposed = h.decomposed;
   pt.dim = (int)h.dd_dim;
@@ -1055,7 +1052,7 @@ extern "C" void mgb_release_cache(void) {
   g_cache.stage_bytes = g_cache.payload_bytes = 0;
 }
 
-extern "C" int mgb_compress_subdomains(int ndim, int dtype, const uint64_t *shape,
+static int compress_subdomains_impl(int ndim, int dtype, const uint64_t *shape,
                                        double tol, double s, int ebtype, double norm,
                                        const void *d_in_first, uint64_t first,
                                        uint64_t count, const mgb_config *cfg_in,
@@ -1067,6 +1064,9 @@ extern "C" int mgb_compress_subdomains(int ndim, int dtype, const uint64_t *shap
     return MGB_BAD_ARGUMENT;
   std::lock_guard<std::mutex> lock(g_cache.mu);
   const size_t tsize = dtype == MGB_F32 ? 4 : 8;
+  uint64_t nall = 0;
+  if (!mgb_checked_elems(ndim, shape, tsize, &nall))
+    return MGB_BAD_ARGUMENT;
   Partition pt;
   rc = make_partition(ndim, shape, tsize, cfg_in, pt);
   if (rc)
@@ -1084,7 +1084,7 @@ extern "C" int mgb_compress_subdomains(int ndim, int dtype, const uint64_t *shap
   return MGB_SUCCESS;
 }
 
-extern "C" int mgb_write_header(int ndim, int dtype, const uint64_t *shape, double tol,
+static int write_header_impl(int ndim, int dtype, const uint64_t *shape, double tol,
                                 double s, int ebtype, double norm,
                                 const void *const *coords, const mgb_config *cfg_in,
                                 uint8_t *out, uint64_t cap, uint64_t *size) {
@@ -1135,6 +1135,44 @@ extern "C" int mgb_unpin_memory(void *ptr) {
   if (e != cudaSuccess)
     cudaGetLastError();
   return e == cudaSuccess ? MGB_SUCCESS : MGB_CUDA_ERROR;
+}
+
+// ---- exported entry points: no exception crosses the C ABI --------------------
+extern "C" int mgb_compress_lowlevel(mgb_plan *p, const void *d_in, int ebtype, double tol, double s,
+                                     double *norm, uint8_t *d_out, uint64_t cap, uint64_t *size,
+                                     void *stream) {
+  MGB_NOEXCEPT_CALL(compress_lowlevel_impl(p, d_in, ebtype, tol, s, norm, d_out, cap, size, stream));
+}
+extern "C" int mgb_decompress_lowlevel(mgb_plan *p, const uint8_t *d_in, uint64_t size, int ebtype,
+                                       double tol, double s, double norm, void *d_out, void *stream) {
+  MGB_NOEXCEPT_CALL(decompress_lowlevel_impl(p, d_in, size, ebtype, tol, s, norm, d_out, stream));
+}
+extern "C" int mgb_compress(int ndim, int dtype, const uint64_t *shape, double tol, double s, int ebtype,
+                            const void *in, void **out, size_t *out_size, const void *const *coords,
+                            const mgb_config *cfg_in, int output_pre_allocated) {
+  MGB_NOEXCEPT_CALL(
+      compress_impl(ndim, dtype, shape, tol, s, ebtype, in, out, out_size, coords, cfg_in, output_pre_allocated));
+}
+extern "C" int mgb_peek_header(const void *in, size_t in_size, int *ndim, uint64_t *shape, int *dtype,
+                               int *ebtype, double *tol, double *s, double *norm, uint64_t *header_bytes) {
+  MGB_NOEXCEPT_CALL(peek_header_impl(in, in_size, ndim, shape, dtype, ebtype, tol, s, norm, header_bytes));
+}
+extern "C" int mgb_decompress(const void *in, size_t in_size, void **out, const mgb_config *cfg_in,
+                              int output_pre_allocated, int *ndim_out, uint64_t *shape_out, int *dtype_out) {
+  MGB_NOEXCEPT_CALL(
+      decompress_impl(in, in_size, out, cfg_in, output_pre_allocated, ndim_out, shape_out, dtype_out));
+}
+extern "C" int mgb_compress_subdomains(int ndim, int dtype, const uint64_t *shape, double tol, double s,
+                                       int ebtype, double norm, const void *d_in_first, uint64_t first,
+                                       uint64_t count, const mgb_config *cfg_in, uint8_t *d_out,
+                                       uint64_t cap, uint64_t *size) {
+  MGB_NOEXCEPT_CALL(compress_subdomains_impl(ndim, dtype, shape, tol, s, ebtype, norm, d_in_first, first,
+                                             count, cfg_in, d_out, cap, size));
+}
+extern "C" int mgb_write_header(int ndim, int dtype, const uint64_t *shape, double tol, double s,
+                                int ebtype, double norm, const void *const *coords,
+                                const mgb_config *cfg_in, uint8_t *out, uint64_t cap, uint64_t *size) {
+  MGB_NOEXCEPT_CALL(write_header_impl(ndim, dtype, shape, tol, s, ebtype, norm, coords, cfg_in, out, cap, size));
 }
 
 extern "C" uint64_t mgb_launch_count(void) { return g_mgb_launches; }

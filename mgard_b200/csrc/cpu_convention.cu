@@ -1537,6 +1537,44 @@ int mgb_cpu_compress(int ndim, int dtype, const uint64_t *shape, const void *con
   }
 }
 
+int mgb_cpu_write_header(int ndim, int dtype, const uint64_t *shape, const void *const *coords, double s,
+                         double tol, int compressor, uint8_t *out, uint64_t cap, uint64_t *size) {
+  if (!shape || !out || !size || ndim < 1 || ndim > MGB_MAX_DIMS || (dtype != MGB_F32 && dtype != MGB_F64) ||
+      (compressor != 1 && compressor != 2))
+    return MGB_BAD_ARGUMENT;
+  try {
+    mgb_header h;
+    h.convention = 1;
+    h.cpu_compressor = compressor;
+    h.ndim = ndim;
+    h.dtype = dtype;
+    h.ebtype = MGB_ABS;
+    h.s = dtype == MGB_F32 ? (double)(float)s : s;
+    h.tol = dtype == MGB_F32 ? (double)(float)tol : tol;
+    for (int d = 0; d < ndim; d++) {
+      if (shape[d] == 0 || shape[d] >= (1ull << 31))
+        return MGB_BAD_ARGUMENT;
+      h.shape[d] = shape[d];
+    }
+    if (coords) {
+      h.coords.resize(ndim);
+      for (int d = 0; d < ndim; d++) {
+        h.coords[d].resize(shape[d]);
+        for (uint64_t i = 0; i < shape[d]; i++)
+          h.coords[d][i] = dtype == MGB_F32 ? (double)((const float *)coords[d])[i] : ((const double *)coords[d])[i];
+      }
+    }
+    const std::vector<uint8_t> head = mgb_encode_stream_header(h);
+    *size = head.size();
+    if (head.size() > cap)
+      return MGB_OUTPUT_TOO_LARGE;
+    memcpy(out, head.data(), head.size());
+    return MGB_SUCCESS;
+  } catch (const std::exception &) {
+    return MGB_FAILURE;
+  }
+}
+
 int mgb_cpu_decompress(const void *in, size_t in_size, void **out, int *ndim, uint64_t *shape, int *dtype) {
   try {
     return cpu_decompress_impl(in, in_size, out, ndim, shape, dtype);

@@ -7,8 +7,11 @@
 // The header is the proto3 canonical serialisation of mgard.pb.Header (fields
 // in number order, default values omitted, repeated scalars packed) — written
 // by hand here (varint / fixed64 / length-delimited only) so that no protobuf
-// runtime is needed.  The preamble is "MGARD" | u64 LE header size | u32 LE
-// CRC32(header) (Metadata.cpp:441-459; little-endian, unlike the CPU API).
+// runtime is needed.  The preamble is "MGARD" | u64 header size | u32
+// CRC32(header): little-endian in MGARD-X streams (Metadata.cpp:441-459, native
+// byte order), BIG-endian in MGARD-CPU streams (serialize / deserialize of
+// include/format.tpp:11-41, used by write_metadata / read_metadata,
+// src/format.cpp:202-233).
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -18,21 +21,22 @@
 namespace {
 
 // CRC-32 (zlib polynomial 0xEDB88320), as crc32_z in Metadata.cpp:34-36
-uint32_t crc32_bytes(const uint8_t *p, size_t n) {
-  static uint32_t table[256];
-  static bool init = false;
-  if (!init) {
+struct Crc32Table {
+  uint32_t t[256];
+  Crc32Table() {
     for (uint32_t i = 0; i < 256; i++) {
       uint32_t c = i;
       for (int k = 0; k < 8; k++)
         c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
-      table[i] = c;
+      t[i] = c;
     }
-    init = true;
   }
+};
+uint32_t crc32_bytes(const uint8_t *p, size_t n) {
+  static const Crc32Table table; // thread-safe initialisation (C++11 magic static)
   uint32_t c = 0xFFFFFFFFu;
   for (size_t i = 0; i < n; i++)
-    c = table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+    c = table.t[(c ^ p[i]) & 0xFF] ^ (c >> 8);
   return c ^ 0xFFFFFFFFu;
 }
 
@@ -123,15 +127,15 @@ double as_double(uint64_t bits) {
 } // namespace
 
 namespace {
-std::vector<uint8_t> with_preamble(const std::string &hdr) {
+std::vector<uint8_t> with_preamble(const std::string &hdr, bool big_endian) {
   std::vector<uint8_t> out;
   out.insert(out.end(), {'M', 'G', 'A', 'R', 'D'});
   uint64_t hs = hdr.size();
   for (int i = 0; i < 8; i++)
-    out.push_back((uint8_t)(hs >> (8 * i)));
+    out.push_back((uint8_t)(hs >> (8 * (big_endian ? 7 - i : i))));
   uint32_t crc = crc32_bytes((const uint8_t *)hdr.data(), hdr.size());
   for (int i = 0; i < 4; i++)
-    out.push_back((uint8_t)(crc >> (8 * i)));
+    out.push_back((uint8_t)(crc >> (8 * (big_endian ? 3 - i : i))));
   out.insert(out.end(), hdr.begin(), hdr.end());
   return out;
 }
@@ -190,7 +194,7 @@ std::vector<uint8_t> encode_cpu_header(const mgb_header &h) {
   f_msg(hdr, 9, quant);
   f_msg(hdr, 11, enc);
   f_msg(hdr, 12, std::string()); // Device::CPU
-  return with_preamble(hdr);
+  return with_preamble(hdr, true); // format.tpp:27-41: big-endian
 }
 } // namespace
 
@@ -265,32 +269,53 @@ std::vector<uint8_t> mgb_encode_stream_header(const mgb_header &h) {
   f_msg(hdr, 11, enc);
   f_msg(hdr, 12, dev);
 
-  std::vector<uint8_t> out;
-  out.insert(out.end(), {'M', 'G', 'A', 'R', 'D'});
-  uint64_t hs = hdr.size();
-  for (int i = 0; i < 8; i++)
-    out.push_back((uint8_t)(hs >> (8 * i)));
-  uint32_t crc = crc32_bytes((const uint8_t *)hdr.data(), hdr.size());
-  for (int i = 0; i < 4; i++)
-    out.push_back((uint8_t)(crc >> (8 * i)));
-  out.insert(out.end(), hdr.begin(), hdr.end());
-  return out;
+  return with_preamble(hdr, false);
+}
+
+uint64_t mgb_preamble_header_size(const uint8_t *pre17, size_t stream_size) {
+  if (stream_size < 17 || memcmp(pre17, "MGARD", 5) != 0)
+    return UINT64_MAX;
+  uint64_t le = 0, be = 0;
+  for (int i = 0; i < 8; i++) {
+    le |= (uint64_t)pre17[5 + i] << (8 * i);
+    be |= (uint64_t)pre17[5 + i] << (8 * (7 - i));
+  }
+  // at most one reading of a non-empty header fits the stream (the other one is a
+  // byte-reversed, astronomically large number)
+  const uint64_t lim = stream_size - 17;
+  if (le <= lim && be <= lim)
+    return le > be ? le : be;
+  if (le <= lim)
+    return le;
+  if (be <= lim)
+    return be;
+  return UINT64_MAX;
 }
 
 int mgb_parse_stream_header(const uint8_t *data, size_t size, mgb_header &h,
                             uint64_t &total_bytes) {
   if (size < 17 || memcmp(data, "MGARD", 5) != 0)
     return MGB_BAD_STREAM;
+  // byte order of the preamble: little-endian (MGARD-X) or big-endian (MGARD-CPU);
+  // the reading whose size fits and whose CRC matches is taken and must agree with
+  // the convention the header body then declares
   uint64_t hs = 0;
-  for (int i = 0; i < 8; i++)
-    hs |= (uint64_t)data[5 + i] << (8 * i);
-  uint32_t crc = 0;
-  for (int i = 0; i < 4; i++)
-    crc |= (uint32_t)data[13 + i] << (8 * i);
-  if (hs > size - 17)
-    return MGB_BAD_STREAM;
+  bool big_endian = false, found = false;
   const uint8_t *hp = data + 17;
-  if (crc32_bytes(hp, hs) != crc)
+  for (int be = 0; be < 2 && !found; be++) {
+    uint64_t cand = 0;
+    uint32_t crc = 0;
+    for (int i = 0; i < 8; i++)
+      cand |= (uint64_t)data[5 + i] << (8 * (be ? 7 - i : i));
+    for (int i = 0; i < 4; i++)
+      crc |= (uint32_t)data[13 + i] << (8 * (be ? 3 - i : i));
+    if (cand <= size - 17 && crc32_bytes(hp, cand) == crc) {
+      hs = cand;
+      big_endian = be != 0;
+      found = true;
+    }
+  }
+  if (!found)
     return MGB_BAD_STREAM;
   total_bytes = 17 + hs;
 
@@ -424,6 +449,9 @@ int mgb_parse_stream_header(const uint8_t *data, size_t size, mgb_header &h,
     h.reorder = preprocessor; // Metadata.cpp:693-698
     h.decomposition = hierarchy == 2 ? 1 : 0; // Metadata.cpp:620-631
   }
+  // each reference reader accepts its own byte order only
+  if (big_endian != (h.convention == 1))
+    return MGB_BAD_STREAM;
   h.lossless = compressor == 5 ? 2 : 0;
   if (geometry == 1) {
     uint64_t tot = 0;

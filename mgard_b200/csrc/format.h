@@ -27,3 +27,6 @@ struct mgb_header {
 std::vector<uint8_t> mgb_encode_stream_header(const mgb_header &h);
 int mgb_parse_stream_header(const uint8_t *data, size_t size, mgb_header &h,
                             uint64_t &total_bytes);
+// header size announced by the 17-byte preamble in whichever byte order fits the
+// stream (UINT64_MAX: not an MGARD preamble / nothing fits)
+uint64_t mgb_preamble_header_size(const uint8_t *pre17, size_t stream_size);

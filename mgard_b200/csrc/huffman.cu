@@ -1546,8 +1546,11 @@ int mgb_huffman_decompress_impl(mgb_plan *p, const uint8_t *d_in, uint64_t size,
   const u64 *decodebook = (const u64 *)(d_in + off);
   off += dbsize + 8;
   const u64 *ddata = (const u64 *)(d_in + off);
+  // sizes come from the stream: no multiplication that could wrap
+  if (total_words > (size - off) / 8 || size - off - 8 * total_words < 8)
+    return MGB_BAD_STREAM;
   off += 8 * total_words + 8;
-  if (off + 16 * oc > size)
+  if (oc > n || oc > (size - off) / 16)
     return MGB_BAD_STREAM;
   if (ocount)
     *ocount = oc;

@@ -279,9 +279,9 @@ extern "C" void mgb_config_default(mgb_config *cfg) {
   cfg->decomposition = 0;
 }
 
-extern "C" int mgb_plan_create(int ndim, const uint64_t *shape, int dtype,
-                               const void *const *coords,
-                               const mgb_config *cfg, mgb_plan **out) {
+static int plan_create_impl(int ndim, const uint64_t *shape, int dtype,
+                            const void *const *coords,
+                            const mgb_config *cfg, mgb_plan **out) {
   if (!out || !shape)
     return MGB_BAD_ARGUMENT;
   *out = nullptr;
@@ -293,6 +293,9 @@ extern "C" int mgb_plan_create(int ndim, const uint64_t *shape, int dtype,
   for (int d = 0; d < ndim; d++)
     if (shape[d] < 3)
       return MGB_BAD_ARGUMENT;
+  uint64_t nelems = 0;
+  if (!mgb_checked_elems(ndim, shape, dtype == MGB_F32 ? 4 : 8, &nelems))
+    return MGB_BAD_ARGUMENT;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return MGB_BACKEND_NOT_AVAILABLE;
@@ -368,6 +371,12 @@ extern "C" int mgb_plan_create(int ndim, const uint64_t *shape, int dtype,
   }
   *out = p;
   return MGB_SUCCESS;
+}
+
+extern "C" int mgb_plan_create(int ndim, const uint64_t *shape, int dtype,
+                               const void *const *coords,
+                               const mgb_config *cfg, mgb_plan **out) {
+  MGB_NOEXCEPT_CALL(plan_create_impl(ndim, shape, dtype, coords, cfg, out));
 }
 
 extern "C" void mgb_plan_destroy(mgb_plan *p) {

@@ -105,6 +105,32 @@ struct mgb_plan {
   const unsigned char *dtab(uint64_t off) const { return d_tables + off * tsize; }
 };
 
+// Number of elements of a user / stream supplied shape with overflow checks: every
+// extent below 2^31 (the kernels keep per-dimension indices in 32 bits) and the byte
+// size below 2^62.  false: reject the shape.
+inline bool mgb_checked_elems(int ndim, const uint64_t *shape, size_t tsize, uint64_t *N) {
+  unsigned __int128 n = 1;
+  for (int d = 0; d < ndim; d++) {
+    if (shape[d] == 0 || shape[d] >= (1ull << 31))
+      return false;
+    n *= shape[d];
+    if (n * tsize >= ((unsigned __int128)1 << 62))
+      return false;
+  }
+  *N = (uint64_t)n;
+  return true;
+}
+
+// No exception crosses the C ABI (std::bad_alloc from a host table, ...).
+#define MGB_NOEXCEPT_CALL(expr)                                                \
+  do {                                                                         \
+    try {                                                                      \
+      return (expr);                                                           \
+    } catch (...) {                                                            \
+      return MGB_FAILURE;                                                      \
+    }                                                                          \
+  } while (0)
+
 // Function attributes (dynamic shared memory limits) are per device: true the
 // first time the calling site runs on the current device.
 inline bool mgb_first_use_on_device(bool (&seen)[64]) {

@@ -421,10 +421,27 @@ def header_bytes(h, s, tol, compressor=1):
 def stream(h, s, tol, payload, compressor=1):
     """CompressedDataset::write (reference include/CompressedDataset.tpp:26-29)
     with write_metadata (src/format.cpp:219-233): magic, u64 header size, u32
-    CRC32 of the header, header, payload."""
-    import struct
+    CRC32 of the header -- both BIG-endian (serialize<>, include/format.tpp:27-41;
+    known answers in tests/src/test_format.cpp:23-50) --, header, payload."""
     hdr = header_bytes(h, s, tol, compressor)
-    return b"MGARD" + struct.pack("<Q", len(hdr)) + struct.pack("<I", zlib.crc32(hdr)) + hdr + bytes(payload)
+    return preamble(hdr) + hdr + bytes(payload)
+
+
+def preamble(hdr):
+    import struct
+    return b"MGARD" + struct.pack(">Q", len(hdr)) + struct.pack(">I", zlib.crc32(hdr))
+
+
+def read_preamble(blob):
+    """read_metadata up to the header bytes (src/format.cpp:150-208): returns
+    (header_size, crc32); raises on a bad magic number or CRC."""
+    import struct
+    if blob[:5] != b"MGARD":
+        raise ValueError("bad magic number")
+    size, crc = struct.unpack(">QI", blob[5:17])
+    if size > len(blob) - 17 or zlib.crc32(blob[17:17 + size]) != crc:
+        raise ValueError("header CRC32 mismatch")
+    return size, crc
 
 
 def compress(h, u, s, tol, compressor=1):

@@ -109,6 +109,23 @@ def dequantize(q, shape, dtype, s, tol, coords=None):
     return _map(DEQUANTIZE, q, coords, out_dtype=dtype, shape=shape, real=dtype, s=s, tol=tol)
 
 
+def preamble(header):
+    """17 preamble bytes for `header` through the reference's SIGNATURE and
+    serialize<> templates (include/format.hpp:28, include/format.tpp:27-41)."""
+    out = (C.c_ubyte * 17)()
+    hb = bytes(header)
+    lib().refcpu_preamble(hb, C.c_uint64(len(hb)), out)
+    return bytes(out)
+
+
+def read_preamble(pre17):
+    size, crc = C.c_uint64(0), C.c_uint32(0)
+    rc = lib().refcpu_read_preamble(bytes(pre17[:17]), C.byref(size), C.byref(crc))
+    if rc:
+        raise ValueError("bad magic number")
+    return size.value, crc.value
+
+
 def zlib_compress(buf):
     buf = np.ascontiguousarray(buf).view(np.uint8).ravel()
     cap = buf.size + buf.size // 2 + 4096

@@ -14,6 +14,7 @@
 #include "TensorMultilevelCoefficientQuantizer.hpp"
 #include "compressors.hpp"
 #include "decompose.hpp"
+#include "format.hpp"
 #include "shuffle.hpp"
 
 namespace mgard {
@@ -159,4 +160,30 @@ extern "C" void refcpu_zlib_decompress(const void *src, uint64_t n, void *dst,
                                        uint64_t dst_bytes) {
   mgard::decompress_memory_z(const_cast<void *>(src), n,
                              static_cast<unsigned char *>(dst), dst_bytes);
+}
+
+// Preamble of an MGARD-CPU stream, byte order included, through the reference's own
+// templates: SIGNATURE (include/format.hpp:28) and serialize<> / deserialize<>
+// (include/format.tpp:11-41), combined as write_metadata / read_metadata do
+// (src/format.cpp:202-233; format.cpp itself needs libprotobuf and is not linked).
+#include <zlib.h>
+extern "C" void refcpu_preamble(const unsigned char *header, uint64_t n, unsigned char *out17) {
+  memcpy(out17, mgard::SIGNATURE.data(), mgard::SIGNATURE.size());
+  const auto sz = mgard::serialize<std::uint_least64_t, mgard::HEADER_SIZE_SIZE>(n);
+  uLong crc = crc32_z(0, Z_NULL, 0);
+  crc = crc32_z(crc, header, n); // compute_crc32, src/format.cpp:179-187
+  const auto cb = mgard::serialize<std::uint_least32_t, mgard::HEADER_CRC32_SIZE>((std::uint_least32_t)crc);
+  memcpy(out17 + 5, sz.data(), sz.size());
+  memcpy(out17 + 13, cb.data(), cb.size());
+}
+extern "C" int refcpu_read_preamble(const unsigned char *in17, uint64_t *size, uint32_t *crc) {
+  if (memcmp(in17, mgard::SIGNATURE.data(), mgard::SIGNATURE.size()) != 0)
+    return -1;
+  std::array<unsigned char, mgard::HEADER_SIZE_SIZE> sb;
+  std::array<unsigned char, mgard::HEADER_CRC32_SIZE> cb;
+  memcpy(sb.data(), in17 + 5, sb.size());
+  memcpy(cb.data(), in17 + 13, cb.size());
+  *size = mgard::deserialize<std::uint_least64_t, mgard::HEADER_SIZE_SIZE>(sb);
+  *crc = mgard::deserialize<std::uint_least32_t, mgard::HEADER_CRC32_SIZE>(cb);
+  return 0;
 }

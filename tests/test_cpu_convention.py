@@ -135,6 +135,79 @@ def test_oracle_header_matches_protobuf_golden():
         assert got == g[f"bytes{i}"].tobytes()
 
 
+def test_preamble_is_big_endian_known_answers():
+    """MGARD-CPU framing: header size and CRC32 are stored big-endian
+    (include/format.tpp:11-41).  Known answers of the reference's own test
+    (tests/src/test_format.cpp:23-50), checked on the oracle's packing and, when
+    built, on the reference's serialize<> / deserialize<> templates themselves."""
+    import struct
+    assert struct.pack(">Q", 144965140814303507) == bytes([0x02, 0x03, 0x05, 0x07, 0x0b, 0x0d, 0x11, 0x13])
+    assert struct.pack(">I", 2017) == bytes([0x00, 0x00, 0x07, 0xe1])
+    assert struct.pack(">I", 13117532) == bytes([0x00, 0xc8, 0x28, 0x5c])
+    assert struct.unpack(">Q", bytes([0xa1, 0xb2, 0xc3, 0xd4, 0xe5, 0xf6, 0x07, 0x18]))[0] == 11651590505119483672
+    hdr = bytes(range(247))
+    pre = mo.preamble(hdr)
+    assert pre[:5] == b"MGARD" and pre[5:13] == bytes([0, 0, 0, 0, 0, 0, 0, 0xf7])
+    assert pre[13:17] == struct.pack(">I", zlib.crc32(hdr))
+    assert mo.read_preamble(pre + hdr) == (247, zlib.crc32(hdr))
+    if ref_cpu.available():
+        rng = np.random.default_rng(3)
+        for n in (1, 20, 247, 300, 70000):
+            body = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+            assert ref_cpu.preamble(body) == mo.preamble(body)
+            assert ref_cpu.read_preamble(mo.preamble(body)) == (n, zlib.crc32(body))
+        assert ref_cpu.read_preamble(b"MGARD" + bytes([0xa1, 0xb2, 0xc3, 0xd4, 0xe5, 0xf6, 0x07, 0x18,
+                                                     0x00, 0xac, 0x00, 0x00])) == (11651590505119483672, 11272192)
+
+
+def test_library_writes_and_reads_the_cpu_framing():
+    """mgb_cpu_write_header (host only): bytes equal to the oracle's stream head --
+    big-endian preamble included -- for uniform and explicit grids; the parser takes
+    big-endian framing for MGARD-CPU headers and little-endian for MGARD-X headers
+    only (each reference reader accepts its own byte order, src/format.cpp:160-175 vs
+    src/mgard-x/Metadata/Metadata.cpp:475-500)."""
+    import ctypes as C
+    import struct
+    from mgard_b200 import _lib
+    import mgard_b200 as mg
+    L = _lib.lib()
+    rng = np.random.default_rng(11)
+    for shape, explicit, dt, s, tol, comp in (((17, 9), False, np.float32, math.inf, 1e-3, 1),
+                                               ((33, 20, 17), True, np.float64, 0.0, 1e-2, 2),
+                                               ((300,), True, np.float32, 1.0, 0.5, 2)):
+        coords = random_coords(rng, shape, dt) if explicit else None
+        h = mo.Hierarchy(shape, dt, coords)
+        want = mo.stream(h, s, tol, b"", comp)
+        carr = None
+        if coords is not None:
+            carr = (C.c_void_p * len(shape))(*[c.ctypes.data for c in coords])
+        out = np.zeros(1 << 16, dtype=np.uint8)
+        sz = C.c_uint64(0)
+        rc = L.mgb_cpu_write_header(len(shape), 0 if dt == np.float32 else 1, (C.c_uint64 * len(shape))(*shape),
+                                    carr, s, tol, comp, out.ctypes.data, out.size, C.byref(sz))
+        assert rc == 0
+        got = out[:sz.value].tobytes()
+        assert got == want
+        hs = len(got) - 17
+        assert got[5:13] == struct.pack(">Q", hs) and got[13:17] == struct.pack(">I", zlib.crc32(got[17:]))
+        if ref_cpu.available():
+            assert got[:17] == ref_cpu.preamble(got[17:])
+        info = mg.peek_header(np.frombuffer(got + b"\0" * 16, dtype=np.uint8))
+        assert list(info["shape"]) == list(shape) and info["header_bytes"] == len(got)
+        # the same header framed little-endian is not an MGARD-CPU stream
+        le = b"MGARD" + struct.pack("<Q", hs) + struct.pack("<I", zlib.crc32(got[17:])) + got[17:]
+        with pytest.raises(mg.MgardError):
+            mg.peek_header(np.frombuffer(le + b"\0" * 16, dtype=np.uint8))
+    # and an MGARD-X header framed big-endian is rejected as well
+    z = np.load(os.path.join(ROOT, "tests", "golden", "headers.npz"))
+    hdr = z["hdr0"].tobytes()
+    good = b"MGARD" + struct.pack("<Q", len(hdr)) + struct.pack("<I", zlib.crc32(hdr)) + hdr
+    assert mg.peek_header(np.frombuffer(good + b"\0" * 16, dtype=np.uint8))["header_bytes"] == len(good)
+    be = b"MGARD" + struct.pack(">Q", len(hdr)) + struct.pack(">I", zlib.crc32(hdr)) + hdr
+    with pytest.raises(mg.MgardError):
+        mg.peek_header(np.frombuffer(be + b"\0" * 16, dtype=np.uint8))
+
+
 @needs_ref
 @pytest.mark.parametrize("shape,explicit", SHAPES)
 @pytest.mark.parametrize("dt", [np.float32, np.float64])

@@ -263,6 +263,13 @@ int mgb_cpu_write_header(int ndim, int dtype, const uint64_t *shape,
 int mgb_cpu_decompress(const void *in, size_t in_size, void **out, int *ndim,
                        uint64_t *shape, int *dtype);
 
+/* Tuning knobs (tests and A/B measurements; results never depend on them).
+ * MGB_TUNE_SERIAL_MIN_CHUNKS: Huffman blocks with at least this many chunks are
+ * encoded / decoded by the thread-per-chunk kernels, smaller ones by the
+ * block-per-chunk kernels (0: always thread-per-chunk, negative: never). */
+enum { MGB_TUNE_SERIAL_MIN_CHUNKS = 0 };
+int mgb_tune(int key, long long value);
+
 /* kernel launch counter (bench.py's gpu_launches) */
 uint64_t mgb_launch_count(void);
 /* Per-kernel-family timing with CUDA events on the launching stream

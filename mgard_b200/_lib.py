@@ -80,6 +80,7 @@ SIGNATURES = {
     "mgb_cpu_compress": (_i32, [_i32, _i32, _pu64, C.POINTER(_vp), _dbl, _dbl, _i32, _vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "mgb_cpu_write_header": (_i32, [_i32, _i32, _pu64, C.POINTER(_vp), _dbl, _dbl, _i32, _vp, _u64, _pu64]),
     "mgb_cpu_decompress": (_i32, [_vp, C.c_size_t, C.POINTER(_vp), C.POINTER(_i32), _pu64, C.POINTER(_i32)]),
+    "mgb_tune": (_i32, [_i32, C.c_longlong]),
     "mgb_launch_count": (_u64, []),
     "mgb_profile_enable": (None, [_i32]),
     "mgb_profile_report": (_i32, [_i32, C.POINTER(C.c_char_p), C.POINTER(C.c_ulonglong), C.POINTER(_dbl), C.POINTER(_dbl)]),

@@ -132,6 +132,14 @@ def unpin_memory(array):
     check(_lib.lib().mgb_unpin_memory(array.ctypes.data), "unpin_memory")
 
 
+TUNE_SERIAL_MIN_CHUNKS = 0
+
+
+def tune(key, value):
+    """mgb_tune: A/B knobs (results never depend on them)."""
+    check(_lib.lib().mgb_tune(int(key), int(value)), "tune")
+
+
 def launch_count():
     """Number of kernels this library has launched so far (bench.py gpu_launches)."""
     return int(_lib.lib().mgb_launch_count())

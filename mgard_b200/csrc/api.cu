@@ -40,7 +40,11 @@ int mgb_quantize_range(mgb_plan *plan, const void *d_coef, int ebtype, double to
                        double norm, uint16_t *d_sym, uint32_t *d_hist,
                        unsigned long long *d_ocount, uint64_t *d_oidx, int64_t *d_oval,
                        uint64_t outlier_cap, uint64_t first, uint64_t count, int zero,
-                       unsigned max_blocks, cudaStream_t st);
+                       unsigned max_blocks, cudaStream_t st, const void *d_qtab);
+int mgb_prepare_quantizers(mgb_plan *plan, int ebtype, double tol, double s, int src, const void *d_src,
+                           uint64_t n_total, uint64_t nsub, void *d_qtab, double *d_norm_out,
+                           cudaStream_t st);
+int mgb_norm_async(mgb_plan *plan, const void *d_in, uint64_t n, double *d_red, cudaStream_t st);
 int mgb_linearize_symbols(mgb_plan *p, const uint16_t *d_dense, uint16_t *d_linear, const unsigned long long *d_ocount,
                           uint64_t *d_oidx, uint64_t ocap, cudaStream_t st);
 int mgb_delinearize_symbols(mgb_plan *p, const uint16_t *d_linear, uint16_t *d_dense, uint32_t *d_inverse,
@@ -69,6 +73,8 @@ int ensure_lowlevel_workspace(mgb_plan *p) {
     MGB_CUDA_CHECK(cudaMalloc(&p->d_sym, p->N * sizeof(uint16_t) + 64));
   if (!p->d_hist)
     MGB_CUDA_CHECK(cudaMalloc(&p->d_hist, p->cfg.huff_dict_size * sizeof(uint32_t)));
+  if (!p->d_qtab)
+    MGB_CUDA_CHECK(cudaMalloc(&p->d_qtab, MGB_MAX_LEVELS * sizeof(double)));
   if (!p->d_oidx) {
     // a power of two, so that the list can always be padded for the index sort
     p->outlier_cap = 4096;
@@ -84,37 +90,45 @@ bool is_inf(double s) { return std::isinf(s) && s > 0; }
 
 } // namespace
 
-static int compress_lowlevel_impl(mgb_plan *p, const void *d_in, int ebtype,
-                                     double tol, double s, double *norm,
-                                     uint8_t *d_out, uint64_t cap, uint64_t *size,
-                                     void *stream) {
-  if (!p || !d_in || !d_out || !size || !norm)
-    return MGB_BAD_ARGUMENT;
-  cudaStream_t st = (cudaStream_t)stream;
+// Everything of Compressor::Compress up to (not including) the final read-back of
+// the block size: norm (relative bounds), decomposition, quantization + histogram,
+// Huffman.  Nothing here waits for the device.
+//   d_qtab_ext != nullptr  reciprocal quantizers already in device memory (global norm
+//                          of a domain-decomposed run, mgb_prepare_quantizers)
+//   otherwise REL          the norm is reduced on the device - by-product of the finest
+//                          level's coefficient kernel (L-inf, fp32, tiled 3-D path) or
+//                          the norm kernels - and turned into the table there
+//   otherwise ABS          the table is computed on the host and passed by value
+static int compress_lowlevel_async(mgb_plan *p, const void *d_in, int ebtype, double tol, double s,
+                                   const void *d_qtab_ext, uint8_t *d_out, uint64_t cap,
+                                   cudaStream_t st) {
   int rc = ensure_lowlevel_workspace(p);
   if (rc)
     return rc;
-  // Compressor.hpp:121-129: the norm is only computed for relative bounds.  For the
-  // L-infinity norm of fp32 data on the tiled 3-D path it is a by-product of the
-  // finest level's coefficient kernel (no separate pass, no synchronisation up front)
-  const bool fuse_norm = ebtype == MGB_REL && is_inf(s) && p->dtype == MGB_F32 && p->D == 3 &&
-                         !p->force_generic && p->shape[1] * p->shape[2] < (1ull << 31) && p->L >= 1 &&
-                         p->cfg.decomposition == 0 && getenv("MGB_NO_FUSED_NORM") == nullptr;
+  double *d_normout = (double *)(p->d_scalars + 9), *d_red = (double *)(p->d_scalars + 10);
+  const void *qtab = d_qtab_ext;
   p->fused_norm.armed = false;
-  if (fuse_norm) {
-    if (!p->d_absmax) {
-      MGB_CUDA_CHECK(cudaMalloc(&p->d_absmax, 8));
-      MGB_CUDA_CHECK(cudaMallocHost(&p->h_absmax, 8));
-      MGB_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_norm, cudaEventDisableTiming));
+  if (!qtab && ebtype == MGB_REL) {
+    // Compressor.hpp:121-129: the norm is only computed for relative bounds
+    const bool fuse_norm = is_inf(s) && p->dtype == MGB_F32 && p->D == 3 && !p->force_generic &&
+                           p->shape[1] * p->shape[2] < (1ull << 31) && p->L >= 1 &&
+                           p->cfg.decomposition == 0 && getenv("MGB_NO_FUSED_NORM") == nullptr;
+    if (fuse_norm) {
+      if (!p->d_absmax)
+        MGB_CUDA_CHECK(cudaMalloc(&p->d_absmax, 8));
+      MGB_CUDA_CHECK(cudaMemsetAsync(p->d_absmax, 0, 8, st));
+      // decompose_t turns max |x| into the table right behind the coefficient kernel
+      p->fused_norm.armed = true;
+      p->fused_norm.tol = tol;
+      p->fused_norm.s = s;
+    } else {
+      rc = mgb_norm_async(p, d_in, p->N, d_red, st);
+      if (!rc)
+        rc = mgb_prepare_quantizers(p, MGB_REL, tol, s, 1, d_red, p->N, 0, p->d_qtab, d_normout, st);
+      if (rc)
+        return rc;
     }
-    MGB_CUDA_CHECK(cudaMemsetAsync(p->d_absmax, 0, 8, st));
-    p->fused_norm.armed = true;
-    p->fused_norm.collected = false;
-  } else if (ebtype == MGB_REL) {
-    MGB_CUDA_CHECK(cudaStreamSynchronize(st));
-    rc = mgb_norm(p, d_in, s, norm);
-    if (rc)
-      return rc;
+    qtab = p->d_qtab;
   }
   // s = inf, 3-D: the upper half of the coefficients is quantized while the coarse
   // levels are still being decomposed (refactor.cu: decompose_t)
@@ -124,70 +138,90 @@ static int compress_lowlevel_impl(mgb_plan *p, const void *d_in, int ebtype,
   p->early_q.ebtype = ebtype;
   p->early_q.tol = tol;
   p->early_q.s = s;
-  p->early_q.norm = *norm;
+  p->early_q.norm = 1.0;
+  p->early_q.d_qtab = qtab;
   rc = mgb_decompose_impl(p, d_in, p->d_coef, st);
   p->early_q.armed = false;
-  if (rc == MGB_SUCCESS && fuse_norm) {
-    rc = mgb_fused_norm_collect(p);
-    *norm = p->fused_norm.value;
-  }
   p->fused_norm.armed = false;
   if (rc)
     return rc;
+  if (p->early_q.done) {
+    MGB_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_qjoin, 0));
+    rc = mgb_quantize_range(p, p->d_coef, ebtype, tol, s, 1.0, p->d_sym, p->d_hist, p->d_scalars,
+                            p->d_oidx, p->d_oval, p->outlier_cap, 0, p->early_q.first, 0, 148 * 4, st,
+                            qtab);
+  } else {
+    rc = mgb_quantize_range(p, p->d_coef, ebtype, tol, s, 1.0, p->d_sym, p->d_hist, p->d_scalars,
+                            p->d_oidx, p->d_oval, p->outlier_cap, 0, ~0ull, 1, 148 * 4, st, qtab);
+  }
+  if (rc)
+    return rc;
+  const uint16_t *sym = p->d_sym;
+  if (p->cfg.reorder) {
+    // Config::reorder: symbols and outlier positions in level-linearised order
+    // (LinearQuantization.hpp:46-146,232-248); the work buffer is free by now
+    rc = mgb_linearize_symbols(p, p->d_sym, (uint16_t *)p->d_wA, p->d_scalars, p->d_oidx,
+                               p->outlier_cap, st);
+    if (rc)
+      return rc;
+    sym = (const uint16_t *)p->d_wA;
+  }
+  // index order: deterministic stream
+  rc = mgb_sort_outliers(p->d_scalars, p->d_oidx, p->d_oval, p->outlier_cap, st);
+  if (rc)
+    return rc;
+  // speculative: encode assuming the outlier buffer was large enough (checked by the caller
+  // after mgb_huffman_finish)
+  return mgb_huffman_compress_async(p, sym, p->N, p->d_hist, p->d_scalars, 0, p->d_oidx, p->d_oval,
+                                    d_out, cap, st);
+}
+
+// After mgb_huffman_finish: the outlier list did not fit (LinearQuantization.hpp:661-675)
+// -> grow the buffers; the caller runs the sub-domain again.
+static int grow_outlier_buffers(mgb_plan *p, uint64_t oc) {
+  cudaFree(p->d_oidx);
+  cudaFree(p->d_oval);
+  p->d_oidx = nullptr;
+  p->d_oval = nullptr;
+  while (p->outlier_cap < oc)
+    p->outlier_cap <<= 1;
+  MGB_CUDA_CHECK(cudaMalloc(&p->d_oidx, p->outlier_cap * 8));
+  MGB_CUDA_CHECK(cudaMalloc(&p->d_oval, p->outlier_cap * 8));
+  return MGB_SUCCESS;
+}
+
+// compress_lowlevel_async + size read-back (one synchronisation), repeated once
+// with larger outlier buffers if the list overflowed.  *norm: in (ABS: unused), out
+// (REL: the norm the device computed, or the value behind d_qtab_ext's table).
+static int compress_lowlevel_sync(mgb_plan *p, const void *d_in, int ebtype, double tol, double s,
+                                  const void *d_qtab_ext, double *norm, uint8_t *d_out, uint64_t cap,
+                                  uint64_t *size, cudaStream_t st) {
   for (int attempt = 0; attempt < 2; attempt++) {
-    if (attempt == 0 && p->early_q.done) {
-      MGB_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_qjoin, 0));
-      rc = mgb_quantize_range(p, p->d_coef, ebtype, tol, s, *norm, p->d_sym, p->d_hist,
-                              p->d_scalars, p->d_oidx, p->d_oval, p->outlier_cap, 0,
-                              p->early_q.first, 0, 148 * 4, st);
-    } else {
-      rc = mgb_quantize(p, p->d_coef, ebtype, tol, s, *norm, p->d_sym, p->d_hist,
-                        p->d_scalars, p->d_oidx, p->d_oval, p->outlier_cap, st);
-    }
+    int rc = compress_lowlevel_async(p, d_in, ebtype, tol, s, d_qtab_ext, d_out, cap, st);
     if (rc)
       return rc;
-    const uint16_t *sym = p->d_sym;
-    if (p->cfg.reorder) {
-      // Config::reorder: symbols and outlier positions in level-linearised order
-      // (LinearQuantization.hpp:46-146,232-248); the work buffer is free by now
-      rc = mgb_linearize_symbols(p, p->d_sym, (uint16_t *)p->d_wA, p->d_scalars, p->d_oidx,
-                                 p->outlier_cap, st);
-      if (rc)
-        return rc;
-      sym = (const uint16_t *)p->d_wA;
+    rc = mgb_huffman_finish(p, size, st);
+    const uint64_t oc = p->h_pinned[0];
+    if (oc <= p->outlier_cap) {
+      if (!d_qtab_ext && ebtype == MGB_REL && norm)
+        memcpy(norm, &p->h_pinned[9], sizeof(double));
+      return rc;
     }
-    // index order: deterministic stream
-    rc = mgb_sort_outliers(p->d_scalars, p->d_oidx, p->d_oval, p->outlier_cap, st);
+    rc = grow_outlier_buffers(p, oc);
     if (rc)
       return rc;
-    if (attempt == 0) {
-      // speculative: encode assuming the outlier buffer was large enough
-      rc = mgb_huffman_compress_async(p, sym, p->N, p->d_hist, p->d_scalars, 0,
-                                      p->d_oidx, p->d_oval, d_out, cap, st);
-      if (rc)
-        return rc;
-      rc = mgb_huffman_finish(p, size, st);
-      uint64_t oc = p->h_pinned[0];
-      if (oc <= p->outlier_cap)
-        return rc;
-      // LinearQuantization.hpp:661-675: grow the outlier buffers and redo
-      cudaFree(p->d_oidx);
-      cudaFree(p->d_oval);
-      p->d_oidx = nullptr;
-      p->d_oval = nullptr;
-      while (p->outlier_cap < oc)
-        p->outlier_cap <<= 1;
-      MGB_CUDA_CHECK(cudaMalloc(&p->d_oidx, p->outlier_cap * 8));
-      MGB_CUDA_CHECK(cudaMalloc(&p->d_oval, p->outlier_cap * 8));
-    } else {
-      rc = mgb_huffman_compress_async(p, sym, p->N, p->d_hist, p->d_scalars, 0,
-                                      p->d_oidx, p->d_oval, d_out, cap, st);
-      if (rc)
-        return rc;
-      return mgb_huffman_finish(p, size, st);
-    }
   }
   return MGB_FAILURE;
+}
+
+static int compress_lowlevel_impl(mgb_plan *p, const void *d_in, int ebtype,
+                                  double tol, double s, double *norm,
+                                  uint8_t *d_out, uint64_t cap, uint64_t *size,
+                                  void *stream) {
+  if (!p || !d_in || !d_out || !size || !norm)
+    return MGB_BAD_ARGUMENT;
+  return compress_lowlevel_sync(p, d_in, ebtype, tol, s, nullptr, norm, d_out, cap, size,
+                                (cudaStream_t)stream);
 }
 
 static int decompress_lowlevel_impl(mgb_plan *p, const uint8_t *d_in, uint64_t size,

@@ -1245,12 +1245,48 @@ __global__ void parse_sizes_kernel(const unsigned char *__restrict__ p, u64 off,
   dst[2] = *(const u64 *)(p + o2 + 8 + 8 * tw);
 }
 
+} // namespace
+#include "huffman_serial.cuh"
+namespace {
+
+// inputs with at least this many chunks take the chunk-serial kernels
+// (huffman_serial.cuh); MGB_SERIAL_MIN_CHUNKS overrides (0: always, huge: never)
+u64 g_serial_min_chunks = getenv("MGB_SERIAL_MIN_CHUNKS") ? strtoull(getenv("MGB_SERIAL_MIN_CHUNKS"), nullptr, 10)
+                                                          : 16384ull;
+u64 serial_min_chunks() { return g_serial_min_chunks; }
+
 // Launches the decoders for one serialised block.  OUT = uint16_t: symbols;
 // OUT = float / double: values dequantized with `scale` while a chunk is flushed.
 template <typename OUT>
 int launch_decoders(mgb_plan *p, const u64 *ddata, u64 total_words, const u64 *bits,
                     const u64 *woff, u64 nchunk, int chunk, u64 n, const u64 *decodebook, int dict,
                     OUT *out, OUT scale, cudaStream_t st) {
+  if (nchunk >= serial_min_chunks() && serial::tab_bytes(dict) <= 200 * 1024) {
+    // thread per chunk (huffman_serial.cuh)
+    const size_t tabb = serial::tab_bytes(dict);
+    if (!p->d_declut)
+      MGB_CUDA_CHECK(cudaMalloc(&p->d_declut, tabb));
+    static bool configured[64] = {};
+    if (mgb_first_use_on_device(configured)) {
+      cudaFuncSetAttribute(serial::decode_serial_kernel<OUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(serial::decode_serial_kernel<OUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    }
+    MGB_LAUNCH(MGB_K_PARSE, st, (serial::build_lut_kernel<<<1, 1024, 0, st>>>(decodebook, dict, (unsigned char *)p->d_declut)));
+    const unsigned blocks = (unsigned)((nchunk + serial::DS_T - 1) / serial::DS_T);
+    const bool vec = ((uintptr_t)out & 31) == 0 && ((size_t)chunk * sizeof(OUT)) % 32 == 0;
+    if (vec)
+      MGB_LAUNCH(MGB_K_DECODE, st,
+                 (serial::decode_serial_kernel<OUT, true><<<blocks, serial::DS_T, tabb, st>>>(
+                     ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict,
+                     (const unsigned char *)p->d_declut, out, scale)));
+    else
+      MGB_LAUNCH(MGB_K_DECODE, st,
+                 (serial::decode_serial_kernel<OUT, false><<<blocks, serial::DS_T, tabb, st>>>(
+                     ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict,
+                     (const unsigned char *)p->d_declut, out, scale)));
+    MGB_CUDA_CHECK(cudaGetLastError());
+    return MGB_SUCCESS;
+  }
   unsigned *sub = p->d_dec_sub;
   const u64 subn = p->dec_sub_cap;
   // fast path: chunks staged in shared memory.  First launch: 2 blocks of 512
@@ -1369,6 +1405,16 @@ int ensure_huff_workspace(mgb_plan *p) {
 
 int mgb_huff_workspace(mgb_plan *p) { return ensure_huff_workspace(p); }
 
+extern "C" int mgb_tune(int key, long long value) {
+  switch (key) {
+  case MGB_TUNE_SERIAL_MIN_CHUNKS:
+    g_serial_min_chunks = value < 0 ? ~0ull : (u64)value;
+    return MGB_SUCCESS;
+  default:
+    return MGB_BAD_ARGUMENT;
+  }
+}
+
 extern "C" int mgb_codebook(mgb_plan *p, const uint32_t *d_hist, uint64_t *d_codebook,
                             uint64_t *d_decodebook, void *stream) {
   if (!p || !d_hist || !d_codebook || !d_decodebook)
@@ -1444,7 +1490,36 @@ int mgb_huffman_compress_async(mgb_plan *p, const uint16_t *d_sym, uint64_t n,
   // the codebook is read through L1 (measured faster than a shared-memory copy,
   // which limits the kernel to two blocks per SM); MGB_ENC_SHARED_CB=1 for A/B runs
   static const bool enc_shared = getenv("MGB_ENC_SHARED_CB") != nullptr;
-  if (dict <= 16384 && enc_shared) {
+  if (nchunk >= serial_min_chunks()) {
+    // thread per chunk (huffman_serial.cuh); codebook in shared memory when it fits
+    const unsigned blocks = (unsigned)((nchunk + serial::ES_T - 1) / serial::ES_T);
+    const bool vec = ((uintptr_t)d_sym & 31) == 0 && ((size_t)chunk * 2) % 32 == 0;
+    const size_t smem = (size_t)dict * 8;
+    static const bool cb_global = getenv("MGB_ENC_SERIAL_GLOBAL_CB") != nullptr;
+    if (smem <= 72 * 1024 && !cb_global) {
+      static bool configured[64] = {};
+      if (mgb_first_use_on_device(configured)) {
+        cudaFuncSetAttribute(serial::encode_serial_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+        cudaFuncSetAttribute(serial::encode_serial_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+      }
+      if (vec)
+        MGB_LAUNCH(MGB_K_ENCODE, st,
+                   (serial::encode_serial_kernel<true, true><<<blocks, serial::ES_T, smem, st>>>(
+                       d_sym, n, chunk, p->d_codebook, dict, (u64 *)p->d_chunk_woff, scal, ddata)));
+      else
+        MGB_LAUNCH(MGB_K_ENCODE, st,
+                   (serial::encode_serial_kernel<true, false><<<blocks, serial::ES_T, smem, st>>>(
+                       d_sym, n, chunk, p->d_codebook, dict, (u64 *)p->d_chunk_woff, scal, ddata)));
+    } else if (vec) {
+      MGB_LAUNCH(MGB_K_ENCODE, st,
+                 (serial::encode_serial_kernel<false, true><<<blocks, serial::ES_T, 0, st>>>(
+                     d_sym, n, chunk, p->d_codebook, dict, (u64 *)p->d_chunk_woff, scal, ddata)));
+    } else {
+      MGB_LAUNCH(MGB_K_ENCODE, st,
+                 (serial::encode_serial_kernel<false, false><<<blocks, serial::ES_T, 0, st>>>(
+                     d_sym, n, chunk, p->d_codebook, dict, (u64 *)p->d_chunk_woff, scal, ddata)));
+    }
+  } else if (dict <= 16384 && enc_shared) {
     size_t smem = ((size_t)dict + TILE_WORDS) * 8;
     cudaFuncSetAttribute(encode_kernel<true>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1558,8 +1633,9 @@ int mgb_huffman_decompress_impl(mgb_plan *p, const uint8_t *d_in, uint64_t size,
     *d_oidx = (const uint64_t *)(d_in + off);
   if (d_oval)
     *d_oval = (const int64_t *)(d_in + off + 8 * oc);
-  // scratch for the sub-sequence bookkeeping (3 x u32 per 128 stream bits)
-  {
+  // scratch for the sub-sequence bookkeeping (3 x u32 per 128 stream bits) of the
+  // block-per-chunk decoders
+  if (nchunk < serial_min_chunks()) {
     u64 need = (total_words * 64) / DEC_SB + nchunk + 8;
     if (p->dec_sub_cap < need) {
       cudaFree(p->d_dec_sub);

@@ -389,10 +389,7 @@ extern "C" void mgb_plan_destroy(mgb_plan *p) {
   cudaFree(p->d_wA);
   cudaFree(p->d_sd);
   cudaFree(p->d_absmax);
-  if (p->h_absmax)
-    cudaFreeHost(p->h_absmax);
-  if (p->ev_norm)
-    cudaEventDestroy(p->ev_norm);
+  cudaFree(p->d_qtab);
   cudaFree(p->d_wB);
   if (p->side)
     cudaStreamDestroy(p->side);
@@ -418,6 +415,7 @@ extern "C" void mgb_plan_destroy(mgb_plan *p) {
   cudaFree(p->d_norm_tmp);
   cudaFree(p->d_cbwork);
   cudaFree(p->d_dec_sub);
+  cudaFree(p->d_declut);
   if (p->h_pinned)
     cudaFreeHost(p->h_pinned);
   delete p;

@@ -71,6 +71,7 @@ struct mgb_plan {
   uint64_t outlier_cap = 0;
   unsigned char *d_norm_tmp = nullptr; // reduction partials (doubles)
   unsigned char *d_cbwork = nullptr;   // codebook kernel scratch
+  unsigned *d_declut = nullptr;        // chunk-serial decoder tables (huffman_serial.cuh)
   unsigned *d_dec_sub = nullptr;       // decoder sub-sequence bookkeeping
   uint64_t dec_sub_cap = 0;
   unsigned long long *h_pinned = nullptr; // pinned host scalars
@@ -88,6 +89,7 @@ struct mgb_plan {
     bool armed = false, done = false;
     int ebtype = 0;
     double tol = 0, s = 0, norm = 0;
+    const void *d_qtab = nullptr; // quantizer table in device memory (else tol / norm above)
     uint64_t first = 0; // elements [first, N) were quantized early
   } early_q;
 
@@ -95,12 +97,13 @@ struct mgb_plan {
   // level's coefficient kernel instead of a separate pass (armed by
   // mgb_compress_lowlevel, produced and collected in refactor.cu)
   unsigned *d_absmax = nullptr;
-  float *h_absmax = nullptr; // pinned
-  cudaEvent_t ev_norm = nullptr;
   struct {
-    bool armed = false, collected = false;
-    double value = 0;
+    bool armed = false;
+    double tol = 0, s = 0;
   } fused_norm;
+  // reciprocal quantizers per level, computed on the device from a norm that never
+  // visits the host (quantize.cu: prepare_q_kernel)
+  void *d_qtab = nullptr;
 
   const unsigned char *dtab(uint64_t off) const { return d_tables + off * tsize; }
 };
@@ -158,7 +161,6 @@ int mgb_plan_ensure_workspace(mgb_plan *p);
 uint64_t mgb_level_elems(const mgb_plan *p, int l);
 
 // refactor.cu
-int mgb_fused_norm_collect(mgb_plan *p);
 int mgb_decompose_impl(mgb_plan *p, const void *d_in, void *d_out,
                        cudaStream_t st);
 int mgb_recompose_impl(mgb_plan *p, const void *d_in, void *d_out,

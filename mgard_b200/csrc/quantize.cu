@@ -101,9 +101,13 @@ quantize_linear_kernel(const T *__restrict__ v, i64 N, T q, T vol, int dict,
                        uint16_t *__restrict__ sym, unsigned *__restrict__ ghist,
                        unsigned long long *__restrict__ ocount,
                        uint64_t *__restrict__ oidx, i64 *__restrict__ oval,
-                       unsigned long long ocap, unsigned long long base) {
+                       unsigned long long ocap, unsigned long long base,
+                       const T *__restrict__ qdev) {
   // v / sym point at element `base` of the array (outlier indices are global)
+  // qdev: the quantizer table lives in device memory (prepare_q_kernel)
   extern __shared__ unsigned sh[];
+  if (qdev)
+    q = qdev[0];
   typedef typename Vec16<T>::type V;
   constexpr int VN = Vec16<T>::n, PER = 8, NV = PER / VN;
   for (int i = threadIdx.x; i < dict; i += blockDim.x)
@@ -208,9 +212,12 @@ quantize_level_kernel(const QParams p, const Tables<T> tb, const T *__restrict__
                       uint16_t *__restrict__ sym, unsigned *__restrict__ ghist,
                       unsigned long long *__restrict__ ocount,
                       uint64_t *__restrict__ oidx, i64 *__restrict__ oval,
-                      unsigned long long ocap) {
+                      unsigned long long ocap, const T *__restrict__ qdev) {
   extern __shared__ unsigned sh[];
+  __shared__ T s_q[MGB_MAX_LEVELS];
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = tid; i <= p.L; i += blockDim.x * blockDim.y)
+    s_q[i] = qdev ? qdev[i] : tb.q[i];
   for (int i = tid; i < p.dict; i += blockDim.x * blockDim.y)
     sh[i] = 0;
   __syncthreads();
@@ -236,7 +243,7 @@ quantize_level_kernel(const QParams p, const Tables<T> tb, const T *__restrict__
       bool is_out = false;
       if (valid) {
         int l = max(lvl, p.marks[(size_t)(D - 1) * p.marks_width + f]);
-        qi = quantize_one<T>(v[base + f], tb.q[l], tb.vol[l], p.dict);
+        qi = quantize_one<T>(v[base + f], s_q[l], tb.vol[l], p.dict);
         if (qi >= 0 && qi < p.dict)
           s = (unsigned)qi;
         else
@@ -451,31 +458,110 @@ __global__ void norm_final_kernel(const double *__restrict__ part, int nblocks,
 
 // LinearQuantizer::CalcQuantizers (LinearQuantization.hpp:495-545), evaluated
 // with the reference's types: tol/s/norm are T, abs_tol is double.
+// denominators of CalcQuantizers, evaluated with the reference's types (s is T, the
+// products are double): quantizer[l] = abs_tol / denom[l]
+template <typename T> void calc_denoms(const mgb_plan *p, double s_, double *denom) {
+  const T s = (T)s_;
+  const uint64_t l_target = (uint64_t)p->L;
+  const size_t dof = p->N;
+  for (int l = 0; l < p->L + 1; l++) {
+    if (s == std::numeric_limits<T>::infinity()) {
+      if (p->cfg.decomposition == 1) // SingleDim (LinearQuantization.hpp:516-520)
+        denom[l] = ((l_target + 1) * (uint8_t)p->D * (1 + std::pow(3, 1)));
+      else
+        denom[l] = ((l_target + 1) * (1 + std::pow(3, p->D)));
+    } else {
+      denom[l] = (std::exp2(s * l) * std::sqrt(dof));
+    }
+  }
+}
+
 template <typename T>
 void calc_quantizers(const mgb_plan *p, int ebtype, double tol_, double s_,
                      double norm_, bool reciprocal, T *out) {
-  T tol = (T)tol_, s = (T)s_, norm = (T)norm_;
+  T tol = (T)tol_, norm = (T)norm_;
   double abs_tol = tol;
   if (ebtype == MGB_REL)
     abs_tol *= norm;
   abs_tol *= 2;
-  const uint64_t l_target = (uint64_t)p->L;
-  const size_t dof = p->N;
-  if (s == std::numeric_limits<T>::infinity()) {
-    for (int l = 0; l < p->L + 1; l++) {
-      if (p->cfg.decomposition == 1) // SingleDim (LinearQuantization.hpp:516-520)
-        out[l] = (abs_tol) / ((l_target + 1) * (uint8_t)p->D * (1 + std::pow(3, 1)));
+  double denom[MGB_MAX_LEVELS];
+  calc_denoms<T>(p, s_, denom);
+  for (int l = 0; l < p->L + 1; l++) {
+    out[l] = (abs_tol) / denom[l];
+    if (reciprocal)
+      out[l] = 1.0f / out[l];
+  }
+}
+
+// The same bookkeeping on the device, for bounds that depend on a norm which is only
+// known in device memory (no host round trip between the norm and the quantizer):
+//   norm      norm_calculator's last step (NormCalculator.hpp:44-71) or, decomposed,
+//             calc_norm_decomposed (ErrorToleranceCalculator.hpp:91-132), in T, 0 -> epsilon
+//   local tol calc_local_abs_tol (ErrorToleranceCalculator.hpp:134-155) when decomposed
+//   table     CalcQuantizers (LinearQuantization.hpp:495-545), reciprocals
+// IEEE division and square root are correctly rounded on both sides and nothing is
+// contracted (-fmad=false), so the table equals the host's bit for bit.
+struct QPrep {
+  int nlevels;       // L + 1
+  int rel;           // error_bound_type::REL
+  int s_inf;
+  int src;           // 0: fp32 max |x| bit pattern; 1: double {max |x|, sum x^2}
+  unsigned long long n_total; // elements of the whole domain (s-norm)
+  unsigned long long nsub;    // > 0: domain-decomposed into nsub sub-domains
+  double tol;
+  double denom[MGB_MAX_LEVELS];
+};
+template <typename T>
+__global__ void prepare_q_kernel(const QPrep p, const unsigned *__restrict__ absmax_bits,
+                                 const double *__restrict__ red, T *__restrict__ qtab,
+                                 double *__restrict__ norm_out) {
+  if (threadIdx.x || blockIdx.x)
+    return;
+  T norm = (T)1;
+  if (p.rel) {
+    if (p.src == 0) {
+      norm = (T)__uint_as_float(*absmax_bits);
+    } else if (p.s_inf) {
+      norm = (T)red[0];
+    } else if (sizeof(T) == 4) {
+      norm = (T)sqrtf((float)red[1] / (float)p.n_total);
+    } else {
+      norm = (T)sqrt(red[1] / (double)p.n_total);
+    }
+    if (norm == (T)0)
+      norm = std::numeric_limits<T>::epsilon();
+  }
+  *norm_out = (double)norm;
+  T tol = (T)p.tol;
+  int rel = p.rel;
+  if (p.nsub) {
+    // sub-domains are compressed with an absolute bound
+    if (sizeof(T) == 4) {
+      const float t = (float)p.tol, n = (float)norm;
+      float lt;
+      if (p.rel)
+        lt = p.s_inf ? t * n : sqrtf((t * n) * (t * n) / (float)p.nsub);
       else
-        out[l] = (abs_tol) / ((l_target + 1) * (1 + std::pow(3, p->D)));
-      if (reciprocal)
-        out[l] = 1.0f / out[l];
+        lt = p.s_inf ? t : sqrtf((t * t) / (float)p.nsub);
+      tol = (T)lt;
+    } else {
+      const double t = p.tol, n = (double)norm;
+      double lt;
+      if (p.rel)
+        lt = p.s_inf ? t * n : sqrt((t * n) * (t * n) / (double)p.nsub);
+      else
+        lt = p.s_inf ? t : sqrt((t * t) / (double)p.nsub);
+      tol = (T)lt;
     }
-  } else {
-    for (int l = 0; l < p->L + 1; l++) {
-      out[l] = (abs_tol) / (std::exp2(s * l) * std::sqrt(dof));
-      if (reciprocal)
-        out[l] = 1.0f / out[l];
-    }
+    rel = 0;
+  }
+  double abs_tol = (double)tol;
+  if (rel)
+    abs_tol *= (double)norm;
+  abs_tol *= 2;
+  for (int l = 0; l < p.nlevels; l++) {
+    T q = (T)(abs_tol / p.denom[l]);
+    qtab[l] = (T)(1.0f / q);
   }
 }
 
@@ -531,7 +617,7 @@ int quantize_t(mgb_plan *p, const T *d_coef, int ebtype, double tol, double s,
                double norm, uint16_t *d_sym, uint32_t *d_hist,
                unsigned long long *d_ocount, uint64_t *d_oidx, int64_t *d_oval,
                uint64_t ocap, cudaStream_t st, uint64_t first = 0, uint64_t count = ~0ull,
-               bool zero = true, unsigned max_blocks = 148 * 4) {
+               bool zero = true, unsigned max_blocks = 148 * 4, const T *qdev = nullptr) {
   // [first, first + count): part of the array (s = inf only); zero: clear the
   // histogram and the outlier counter first
   QParams qp;
@@ -555,7 +641,7 @@ int quantize_t(mgb_plan *p, const T *d_coef, int ebtype, double tol, double s,
     MGB_LAUNCH(MGB_K_QUANTIZE, st,
                (quantize_linear_kernel<T><<<blocks, 256, smem, st>>>(
                    d_coef + first, (i64)count, tb.q[0], tb.vol[0], dict, d_sym + first, d_hist,
-                   d_ocount, d_oidx, (i64 *)d_oval, ocap, (unsigned long long)first)));
+                   d_ocount, d_oidx, (i64 *)d_oval, ocap, (unsigned long long)first, qdev)));
   } else {
     if (first != 0 || count != p->N)
       return MGB_BAD_ARGUMENT;
@@ -569,7 +655,7 @@ int quantize_t(mgb_plan *p, const T *d_coef, int ebtype, double tol, double s,
     unsigned blocks = std::min<unsigned>((qp.rows + block.y - 1) / block.y, 148 * 6);
     MGB_LAUNCH(MGB_K_QUANTIZE, st,
                (quantize_level_kernel<T><<<blocks, block, smem, st>>>(
-                   qp, tb, d_coef, d_sym, d_hist, d_ocount, d_oidx, (i64 *)d_oval, ocap)));
+                   qp, tb, d_coef, d_sym, d_hist, d_ocount, d_oidx, (i64 *)d_oval, ocap, qdev)));
   }
   MGB_CUDA_CHECK(cudaGetLastError());
   return MGB_SUCCESS;
@@ -733,14 +819,67 @@ int mgb_quantize_range(mgb_plan *plan, const void *d_coef, int ebtype, double to
                        double norm, uint16_t *d_sym, uint32_t *d_hist,
                        unsigned long long *d_ocount, uint64_t *d_oidx, int64_t *d_oval,
                        uint64_t outlier_cap, uint64_t first, uint64_t count, int zero,
-                       unsigned max_blocks, cudaStream_t st) {
+                       unsigned max_blocks, cudaStream_t st, const void *d_qtab) {
+  // d_qtab != nullptr: reciprocal quantizers in device memory (mgb_prepare_quantizers);
+  // ebtype / tol / norm are not used then
+  if (count == ~0ull)
+    count = plan->N - first;
   if (plan->dtype == MGB_F32)
     return quantize_t<float>(plan, (const float *)d_coef, ebtype, tol, s, norm, d_sym, d_hist,
                              d_ocount, d_oidx, d_oval, outlier_cap, st, first, count, zero != 0,
-                             max_blocks);
+                             max_blocks, (const float *)d_qtab);
   return quantize_t<double>(plan, (const double *)d_coef, ebtype, tol, s, norm, d_sym, d_hist,
                             d_ocount, d_oidx, d_oval, outlier_cap, st, first, count, zero != 0,
-                            max_blocks);
+                            max_blocks, (const double *)d_qtab);
+}
+
+// Quantizer table of `plan` from a norm that lives in device memory (see
+// prepare_q_kernel).  src 0: d_src = fp32 bit pattern of max |x| (coef3d by-product);
+// src 1: d_src = double {max |x|, sum x^2} (norm kernels, possibly all-reduced).
+// n_total: elements the s-norm is taken over; nsub > 0: domain-decomposed run.
+int mgb_prepare_quantizers(mgb_plan *plan, int ebtype, double tol, double s, int src, const void *d_src,
+                           uint64_t n_total, uint64_t nsub, void *d_qtab, double *d_norm_out,
+                           cudaStream_t st) {
+  QPrep q;
+  memset(&q, 0, sizeof(q));
+  q.nlevels = plan->L + 1;
+  q.rel = ebtype == MGB_REL;
+  q.s_inf = std::isinf(s) && s > 0;
+  q.src = src;
+  q.n_total = n_total;
+  q.nsub = nsub;
+  q.tol = tol;
+  if (plan->dtype == MGB_F32) {
+    calc_denoms<float>(plan, s, q.denom);
+    MGB_LAUNCH(MGB_K_NORM, st,
+               (prepare_q_kernel<float><<<1, 32, 0, st>>>(q, (const unsigned *)d_src, (const double *)d_src,
+                                                          (float *)d_qtab, d_norm_out)));
+  } else {
+    calc_denoms<double>(plan, s, q.denom);
+    MGB_LAUNCH(MGB_K_NORM, st,
+               (prepare_q_kernel<double><<<1, 32, 0, st>>>(q, (const unsigned *)d_src, (const double *)d_src,
+                                                           (double *)d_qtab, d_norm_out)));
+  }
+  MGB_CUDA_CHECK(cudaGetLastError());
+  return MGB_SUCCESS;
+}
+
+// max |x| and sum x^2 of n elements into d_red[0..1] (doubles), asynchronously:
+// two-stage deterministic reduction (norm_partial_kernel / norm_final_kernel)
+int mgb_norm_async(mgb_plan *plan, const void *d_in, uint64_t n, double *d_red, cudaStream_t st) {
+  const int nblocks = 148 * 8;
+  if (!plan->d_norm_tmp)
+    MGB_CUDA_CHECK(cudaMalloc(&plan->d_norm_tmp, (2 * nblocks + 2) * sizeof(double)));
+  double *part = (double *)plan->d_norm_tmp;
+  if (plan->dtype == MGB_F32)
+    MGB_LAUNCH(MGB_K_NORM, st,
+               (norm_partial_kernel<float><<<nblocks, 256, 0, st>>>((const float *)d_in, (i64)n, part)));
+  else
+    MGB_LAUNCH(MGB_K_NORM, st,
+               (norm_partial_kernel<double><<<nblocks, 256, 0, st>>>((const double *)d_in, (i64)n, part)));
+  MGB_LAUNCH(MGB_K_NORM, st, (norm_final_kernel<<<1, 32, 0, st>>>(part, nblocks, d_red)));
+  MGB_CUDA_CHECK(cudaGetLastError());
+  return MGB_SUCCESS;
 }
 
 // Outliers are appended with atomics, so their order depends on scheduling.

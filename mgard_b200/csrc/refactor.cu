@@ -35,7 +35,10 @@ int mgb_quantize_range(mgb_plan *plan, const void *d_coef, int ebtype, double to
                        double norm, uint16_t *d_sym, uint32_t *d_hist,
                        unsigned long long *d_ocount, uint64_t *d_oidx, int64_t *d_oval,
                        uint64_t outlier_cap, uint64_t first, uint64_t count, int zero,
-                       unsigned max_blocks, cudaStream_t st);
+                       unsigned max_blocks, cudaStream_t st, const void *d_qtab);
+int mgb_prepare_quantizers(mgb_plan *plan, int ebtype, double tol, double s, int src, const void *d_src,
+                           uint64_t n_total, uint64_t nsub, void *d_qtab, double *d_norm_out,
+                           cudaStream_t st);
 
 namespace {
 
@@ -1155,19 +1158,15 @@ int decompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
       const bool with_norm = l == p->L && p->fused_norm.armed && sizeof(T) == 4;
       launch_coef3d<T>(p, l, cur, d_out, coarse, st, with_norm ? p->d_absmax : nullptr);
       if (with_norm) {
-        MGB_CUDA_CHECK(cudaMemcpyAsync(p->h_absmax, p->d_absmax, sizeof(float), cudaMemcpyDeviceToHost, st));
-        MGB_CUDA_CHECK(cudaEventRecord(p->ev_norm, st));
+        // max |x| -> norm -> quantizer table, all in device memory (read by both
+        // quantizer launches; the host sees the norm with the block size at the end)
+        rc = mgb_prepare_quantizers(p, MGB_REL, p->fused_norm.tol, p->fused_norm.s, 0, p->d_absmax, p->N, 0,
+                                    p->d_qtab, (double *)(p->d_scalars + 9), st);
+        if (rc)
+          return rc;
       }
       launch_masstrans3d<T>(p, l, d_out, w, st);
       thomas_all<T>(p, l, w, coarse, 1, st);
-      if (with_norm && p->early_q.armed) {
-        // the quantizer launched below needs the norm on the host: wait for the
-        // coefficient kernel only (the load vector and the solves are already queued)
-        rc = mgb_fused_norm_collect(p);
-        if (rc)
-          return rc;
-        p->early_q.norm = p->fused_norm.value;
-      }
       if (l == p->L && p->early_q.armed && (void *)d_out == (void *)p->d_coef) {
         // planes r >= coarse size hold level-L coefficients only (final).  Quantize
         // them now, two blocks per SM, while the coarse levels - a chain of small
@@ -1186,7 +1185,7 @@ int decompose_t(mgb_plan *p, const T *d_in, T *d_out, cudaStream_t st) {
           rc = mgb_quantize_range(p, p->d_coef, p->early_q.ebtype, p->early_q.tol, p->early_q.s,
                                   p->early_q.norm, p->d_sym, p->d_hist, p->d_scalars, p->d_oidx,
                                   p->d_oval, p->outlier_cap, first, p->N - first, 1, 148 * 2,
-                                  p->side_q);
+                                  p->side_q, p->early_q.d_qtab);
           if (rc)
             return rc;
           MGB_CUDA_CHECK(cudaEventRecord(p->ev_qjoin, p->side_q));
@@ -1669,20 +1668,6 @@ template <typename T> int recompose_single_t(mgb_plan *p, const T *d_in, T *d_ou
 }
 
 } // namespace
-
-// max |x| produced by the finest level's coefficient kernel -> norm in T
-// (zero replaced by epsilon, NormCalculator.hpp:72-80)
-int mgb_fused_norm_collect(mgb_plan *p) {
-  if (!p->fused_norm.armed || p->fused_norm.collected)
-    return MGB_SUCCESS;
-  MGB_CUDA_CHECK(cudaEventSynchronize(p->ev_norm));
-  float f = *p->h_absmax;
-  if (f == 0)
-    f = std::numeric_limits<float>::epsilon();
-  p->fused_norm.value = f;
-  p->fused_norm.collected = true;
-  return MGB_SUCCESS;
-}
 
 int mgb_decompose_impl(mgb_plan *p, const void *d_in, void *d_out, cudaStream_t st) {
   if (p->cfg.decomposition == 1) {

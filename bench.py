@@ -1,22 +1,27 @@
 #!/usr/bin/env python
 """bench.py — MGARD-X hot path on B200: compress + decompress throughput.
 
-Workload (BASELINE.json configs[1], SURVEY.md §8d "C2"): 3-D fp32 513^3
-synthetic field, relative L-inf bound 1e-3 (s = inf), Huffman lossless, dict
-8192, block 20480.  One "step" = one compress + one decompress of the field.
+Workload at every N (BASELINE.json configs[4], SURVEY.md 8d/8e "C5"): 3-D fp32
+2049^3 synthetic field (34.4 GB), relative L-inf bound 1e-3 (s = inf), Huffman
+lossless, dict 8192, block 20480, MaxDim-decomposed along dim 0 in 8 sub-domains of
+257 planes (7 x 257 + 250, DomainDecomposer.hpp:124-169).  GPU g of N owns the
+sub-domains [g*8/N, (g+1)*8/N): STRONG scaling, the stream does not depend on N.
+One "step" = one compress + one decompress of the whole domain through
+mgb_compress_sharded / mgb_decompress_sharded (global norm all-reduce + size
+all-gather over NCCL inside the timed region).
 
-  value  (device resident)  original bytes moved through the codec per second:
-         2 * N * 4 B / (t_compress + t_decompress); inputs already in HBM.
-  e2e    same metric through the public host API mgard_b200.compress /
-         decompress with pinned HOST buffers (H2D of the field, D2H of the
-         stream, and back) inside the timed region.
-  N > 1  weak scaling: the domain is (N*513) x 513 x 513, MaxDim-decomposed
-         along dim 0 with 513 planes per sub-domain, one sub-domain per rank,
-         global norm all-reduce + size all-gather (mgard_b200/sharded.py).
+  value  (device resident)  original bytes through the codec per second:
+         2 * 34.4 GB / (t_compress + t_decompress), max over ranks; inputs in HBM.
+  e2e    the same calls with pinned HOST buffers (H2D of the field, D2H of the
+         records, and back, inside the timed region; three-stream pipeline).
+  c2     (N = 1 only) BASELINE configs[1]: 513^3 fp32, same bound, one sub-domain,
+         through Compressor::Compress / Decompress (mgb_*_lowlevel), with the
+         per-kernel roofline table.
 
-`--impl reference` times the UNMODIFIED reference (MGARD-X SERIAL adapter built
-from /root/reference as oracle/_ref) on the host, on a bounded 129^3 / 257^3
-sample of the same field.
+`--impl reference` times the UNMODIFIED reference (MGARD-X SERIAL adapter built from
+/root/reference as oracle/_ref) on the host: one 257^3 block of the same field per
+host core, all cores at once (what the reference's CPU pipeline does with one
+sub-domain per thread, CPUPipelines.hpp:88-135).
 """
 import argparse
 import json
@@ -31,10 +36,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "compress/decompress GB/s at 1/2/4/8 B200 vs HBM roofline; ratio at bound"
-SHAPE = (513, 513, 513)
+GSHAPE = (2049, 2049, 2049)
+DD_SIZE = 257
+SHAPE = (513, 513, 513)  # C2
 TOL, S = 1e-3, float("inf")
 SEED = 2049
 _REAL_STDOUT = None  # saved stdout fd when N > 1 (see main)
+WORKLOAD = ("3D fp32 2049x2049x2049 synthetic field (34.4 GB), relative L-inf 1e-3 (s=inf), Huffman lossless, "
+            "dict 8192, block 20480, MaxDim sub-domains of 257 planes (7x257+250) spread over the GPUs")
 
 
 def measured_peaks():
@@ -65,12 +74,13 @@ def field_numpy(shape, lo=0, seed=SEED, full_shape=None):
     return (u + 1e-3 * xi.reshape(shape)).astype(np.float32)
 
 
-def field_torch(shape, device, seed=SEED, plane0=0):
-    """Same field generated on the device (planes plane0.. of a taller domain
-    share the noise stream by linear index)."""
+def field_torch(shape, device, seed=SEED, plane0=0, full_n0=None):
+    """Same field generated on the device: planes [plane0, plane0 + shape[0]) of a
+    domain with full_n0 planes (coordinates and noise index of the full domain)."""
     import torch
     n0, n1, n2 = shape
-    x0 = (torch.arange(n0, device=device, dtype=torch.float64) / (n0 - 1)).view(-1, 1, 1)
+    full_n0 = full_n0 or n0
+    x0 = ((torch.arange(n0, device=device, dtype=torch.float64) + plane0) / (full_n0 - 1)).view(-1, 1, 1)
     x1 = (torch.arange(n1, device=device, dtype=torch.float64) / (n1 - 1)).view(1, -1, 1)
     x2 = (torch.arange(n2, device=device, dtype=torch.float64) / (n2 - 1)).view(1, 1, -1)
     out = torch.empty(shape, dtype=torch.float32, device=device)
@@ -83,7 +93,7 @@ def field_torch(shape, device, seed=SEED, plane0=0):
         v &= M
         return v - (1 << 64) if v >= (1 << 63) else v
 
-    step = 64
+    step = max(1, min(64, (1 << 26) // (n1 * n2)))
     for a in range(0, n0, step):
         b = min(n0, a + step)
         u = (torch.sin(6 * math.pi * x0[a:b]) * torch.cos(4 * math.pi * x1) * torch.sin(2 * math.pi * x2)
@@ -149,69 +159,256 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def reference_arm(args):
-    """Times the reference's own CPU implementation (oracle/_ref, SERIAL adapter,
-    1 core) on a bounded sample of the workload."""
+def _ref_block(arg):
+    """One worker of the reference arm: MGARD-X SERIAL compress + decompress of one
+    n^3 block of the workload field (planes from `plane0` of the 2049^3 domain)."""
+    n, plane0, reps = arg
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import baseline_fields as bf
     import ref_x
-    n = args.ref_size
-    shape = (n, n, n)
-    u = field_numpy(shape)
-    times_c, times_d = [], []
-    cr = None
-    for it in range(args.warmup + args.steps):
+    u = bf.c2_like(GSHAPE, plane0, n, crop=(n, n))
+    tc = td = 0.0
+    size = 0
+    err = 0.0
+    for _ in range(reps):
         t0 = time.perf_counter()
         r = ref_x.compress(u, ref_x.REL, TOL, S)
         t1 = time.perf_counter()
-        back = ref_x.decompress(r["payload"], shape, u.dtype, ref_x.REL, TOL, S, r["norm"])
+        back = ref_x.decompress(r["payload"], u.shape, u.dtype, ref_x.REL, TOL, S, r["norm"])
         t2 = time.perf_counter()
-        if it >= args.warmup:
-            times_c.append(t1 - t0)
-            times_d.append(t2 - t1)
-        cr = u.nbytes / r["payload"].size
-    tc, td = sum(times_c) / len(times_c), sum(times_d) / len(times_d)
-    value = 2 * u.nbytes / (tc + td) / 1e9
+        tc += t1 - t0
+        td += t2 - t1
+        size = int(r["payload"].size)
+        err = float(np.abs(back - u).max() / np.abs(u).max())
+    return u.nbytes, tc / reps, td / reps, size, err
+
+
+def reference_cpu(n, cores, steps=1):
+    """All host cores at once, one n^3 block per core (the reference's own CPU
+    pipeline runs one sub-domain per thread, CPUPipelines.hpp:88-135).  Returns the
+    aggregate rate of (compress + decompress)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_ref_block, [(n, (37 * k) % (GSHAPE[0] - n), steps) for k in range(cores)])
+        wall = time.perf_counter() - t0
+    nbytes = sum(r[0] for r in res)
+    # blocks run concurrently: the step takes as long as the slowest worker
+    tc, td = max(r[1] for r in res), max(r[2] for r in res)
+    return {"bytes": nbytes, "tc": tc, "td": td, "wall": wall, "ratio": nbytes / sum(r[3] for r in res),
+            "rel_err": max(r[4] for r in res)}
+
+
+def reference_arm(args):
+    """Times the reference's own CPU implementation (oracle/_ref, MGARD-X SERIAL
+    adapter) on a bounded sample of the workload: one 257^3 block per host core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n = args.ref_size
+    r = reference_cpu(n, cores, steps=max(1, min(args.steps, 3)))
+    value = 2 * r["bytes"] / (r["tc"] + r["td"]) / 1e9
+    sample = (f"{cores} blocks of {n}^3 fp32 of the 2049^3 workload field, one per host core, MGARD-X SERIAL "
+              f"Compressor::Compress+Decompress, REL 1e-3 s=inf")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": (tc + td) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": (r["tc"] + r["td"]) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "3D fp32 513x513x513 synthetic field, relative L-inf 1e-3, Huffman lossless",
-                   "sample": f"{n}^3 sample of the same field"},
-        "compress_gbs": u.nbytes / tc / 1e9, "decompress_gbs": u.nbytes / td / 1e9,
-        "ratio": cr,
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": 1, "kind": "reference",
-                         "sample": f"MGARD-X SERIAL Compressor::Compress+Decompress on a {n}^3 fp32 sample, REL 1e-3 s=inf"},
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "compress_gbs": r["bytes"] / r["tc"] / 1e9, "decompress_gbs": r["bytes"] / r["td"] / 1e9,
+        "ratio": r["ratio"],
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
 
 
-def cpu_baseline(n=129):
+def cpu_baseline(n=257):
+    """Reference arms on the box's host cores: (i) MGARD-X SERIAL, one n^3 block of
+    the workload field per core; (ii) MGARD-CPU mgard::compress / decompress stages
+    (OpenMP, all cores) on BASELINE config 1."""
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    cores = os.cpu_count() or 1
     try:
         import ref_x
         if not ref_x.available():
             raise RuntimeError("oracle/_ref not built")
-        u = field_numpy((n, n, n))
-        t0 = time.perf_counter()
-        r = ref_x.compress(u, ref_x.REL, TOL, S)
-        t1 = time.perf_counter()
-        ref_x.decompress(r["payload"], u.shape, u.dtype, ref_x.REL, TOL, S, r["norm"])
-        t2 = time.perf_counter()
-        return {"value": 2 * u.nbytes / (t2 - t0) / 1e9, "unit": "GB/s", "cores": 1,
-                "kind": "reference",
-                "sample": f"MGARD-X SERIAL (oracle/_ref) compress+decompress of a {n}^3 fp32 sample of the workload field, {t2 - t0:.1f} s",
-                "compress_gbs": u.nbytes / (t1 - t0) / 1e9, "decompress_gbs": u.nbytes / (t2 - t1) / 1e9,
-                "ratio": u.nbytes / r["payload"].size}
+        r = reference_cpu(n, cores)
+        out = {"value": 2 * r["bytes"] / (r["tc"] + r["td"]) / 1e9, "unit": "GB/s", "cores": cores,
+               "kind": "reference",
+               "sample": f"MGARD-X SERIAL (oracle/_ref) compress+decompress, {cores} blocks of {n}^3 fp32 of the "
+                         f"workload field, one per host core at once, {r['wall']:.1f} s",
+               "compress_gbs": r["bytes"] / r["tc"] / 1e9, "decompress_gbs": r["bytes"] / r["td"] / 1e9,
+               "ratio": r["ratio"]}
     except Exception as e:  # the oracle always exists; report why it could not run
-        return {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+        out = {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import baseline_fields as bf
+        import ref_cpu
+        u = bf.c1()
+        t0 = time.perf_counter()
+        c = ref_cpu.decompose(u)
+        q = ref_cpu.quantize(c, u.shape, float("inf"), 1e-4)
+        blob = ref_cpu.huffman_zstd_compress(q) if ref_cpu.zstd_available() else ref_cpu.zlib_compress(q)
+        t1 = time.perf_counter()
+        q2 = (ref_cpu.huffman_zstd_decompress(blob, q.size) if ref_cpu.zstd_available()
+              else ref_cpu.zlib_decompress(blob, q.nbytes))
+        back = ref_cpu.recompose(ref_cpu.dequantize(np.asarray(q2).reshape(-1), u.shape, u.dtype, float("inf"), 1e-4),
+                                 u.shape)
+        t2 = time.perf_counter()
+        out["mgard_cpu"] = {"value": 2 * u.nbytes / (t2 - t0) / 1e9, "unit": "GB/s",
+                            "cores": int(os.environ.get("OMP_NUM_THREADS", cores)), "kind": "reference",
+                            "sample": "MGARD-CPU mgard::compress + decompress stages (reference templates, OpenMP) on "
+                                      "BASELINE config 1, 129^3 fp64 ABS 1e-4 s=inf, Huffman+zstd payload",
+                            "compress_gbs": u.nbytes / (t1 - t0) / 1e9, "decompress_gbs": u.nbytes / (t2 - t1) / 1e9,
+                            "ratio": u.nbytes / len(blob),
+                            "max_abs_error": float(np.abs(np.asarray(back).reshape(u.shape) - u).max())}
+    except Exception as e:
+        out["mgard_cpu"] = {"value": None, "sample": f"unavailable: {e}"}
+    return out
+
+
+def kernel_table(L, reps):
+    import ctypes as C
+    fam = []
+    k = 0
+    while True:
+        name, n_l, tot, mx = C.c_char_p(), C.c_ulonglong(0), C.c_double(0), C.c_double(0)
+        if L.mgb_profile_report(k, C.byref(name), C.byref(n_l), C.byref(tot), C.byref(mx)) != 0:
+            break
+        if n_l.value:
+            fam.append({"kernel": name.value.decode(), "launches_per_step": n_l.value / reps,
+                        "ms_per_step": tot.value / reps, "max_launch_ms": mx.value})
+        k += 1
+    fam.sort(key=lambda f: -f["ms_per_step"])
+    return fam
+
+
+def algorithmic_bytes(shape, stream_bytes):
+    """Per kernel family: algorithmic bytes of its largest (finest-level) launch on one
+    sub-domain of `shape`, fp32."""
+    nl = shape[0] * shape[1] * shape[2]
+    cs = (shape[0] // 2 + 1) * (shape[1] // 2 + 1) * (shape[2] // 2 + 1)
+    return {
+        "coef": 2 * nl * 4,                    # read the level box, write coefficients + coarse
+        "restore": 2 * nl * 4 + cs * 4,        # read coefficients + coarse, write the level box
+        "mass_trans": (nl + cs) * 4,           # fused f/c/r pass: read n, write n/8
+        "quantize_hist": nl * 4 + nl * 2,      # read T, write u16 symbols
+        "encode": nl * 2 + stream_bytes,
+        "chunk_bits": nl * 2,
+        "decode": stream_bytes + nl * 4,       # s=inf: dequantized while flushing
+        "thomas_contig": 2 * cs * 4, "thomas_strided": 2 * cs * 4,
+        "norm": nl * 4,
+    }
+
+
+def roofline_tables(fam, shape, stream_bytes, peak, peak_src, ncu_file):
+    """roofline (dominant kernel) + per-kernel list from a kernel_table."""
+    alg = algorithmic_bytes(shape, stream_bytes)
+    ncu = {}
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", ncu_file)))
+    except Exception:
+        pass
+
+    def traffic_of(k):
+        t = ncu.get(k)
+        return (t["dram_read_bytes"] + t["dram_write_bytes"]) if t else None
+
+    # the quantizer runs as two launches when the upper half of the coefficients is
+    # quantized early (api.cu): its largest launch covers that share of the array
+    N = shape[0] * shape[1] * shape[2]
+    qshare = 1.0
+    for f in fam:
+        if f["kernel"] == "quantize_hist" and f["launches_per_step"] > 1.5:
+            first = -(-(shape[0] // 2 + 1) * shape[1] * shape[2] // 8) * 8
+            qshare = max(first, N - first) / N
+    alg["quantize_hist"] *= qshare
+    per_kernel = []
+    for f in fam:
+        a = alg.get(f["kernel"])
+        if a:
+            ach = a / (f["max_launch_ms"] * 1e-3) / 1e9
+            per_kernel.append({"kernel": f["kernel"], "achieved": ach, "frac": ach / peak,
+                               "algorithmic_bytes": a, "traffic": traffic_of(f["kernel"]),
+                               "launch_ms": f["max_launch_ms"]})
+    roof = None
+    if fam:
+        top = fam[0]
+        a = alg.get(top["kernel"])
+        if a:
+            achieved = a / (top["max_launch_ms"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic_of(top["kernel"]), "peak_source": peak_src,
+                    "note": "largest (finest-level) launch of the dominant family on one sub-domain: algorithmic "
+                            "bytes / CUDA-event duration measured in this run; traffic = dram read+write bytes of "
+                            f"that launch from ncu --set full (profiles/{ncu_file}), null if not captured"}
+            tb = sum(k["traffic"] for k in per_kernel if k["traffic"])
+            tt = sum(k["launch_ms"] for k in per_kernel if k["traffic"]) * 1e-3
+            if tt > 0:
+                roof["dram_efficiency"] = tb / tt / 1e9 / peak
+    return roof, per_kernel
+
+
+def bench_c2(mg, L, dev, cfg, W, K, peak, peak_src):
+    """BASELINE configs[1] on one GPU: 513^3 fp32, one sub-domain, device resident."""
+    import numpy as np
+    import torch
+    N = int(np.prod(SHAPE))
+    nbytes = N * 4
+    u = field_torch(SHAPE, dev)
+    plan = mg.Plan(SHAPE, np.float32, config=cfg)
+    out = torch.empty(nbytes + 8 * (128 + cfg.huff_dict_size) + (1 << 20), dtype=torch.uint8, device=dev)
+    back = torch.empty(SHAPE, dtype=torch.float32, device=dev)
+    for _ in range(W):
+        payload, norm = plan.compress(u, mg.error_bound_type.REL, TOL, S, out=out)
+        plan.decompress(payload, mg.error_bound_type.REL, TOL, S, norm, out=back)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    tc = td = 0.0
+    for _ in range(K):
+        ev[0].record()
+        payload, norm = plan.compress(u, mg.error_bound_type.REL, TOL, S, out=out)
+        ev[1].record()
+        plan.decompress(payload, mg.error_bound_type.REL, TOL, S, norm, out=back)
+        ev[2].record()
+        torch.cuda.synchronize()
+        tc += ev[0].elapsed_time(ev[1])
+        td += ev[1].elapsed_time(ev[2])
+    tc /= K
+    td /= K
+    err = float((back - u).abs().max())
+    bound = TOL * float(u.abs().max())
+    stream = int(payload.numel())
+    L.mgb_profile_enable(1)
+    reps = 3
+    for _ in range(reps):
+        payload1, norm1 = plan.compress(u, mg.error_bound_type.REL, TOL, S, out=out)
+        plan.decompress(payload1, mg.error_bound_type.REL, TOL, S, norm1, out=back)
+    torch.cuda.synchronize()
+    L.mgb_profile_enable(0)
+    fam = kernel_table(L, reps)
+    roof, per_kernel = roofline_tables(fam, SHAPE, stream, peak, peak_src, "r2_ncu_traffic.json")
+    res = {"workload": "3D fp32 513x513x513 synthetic field, relative L-inf 1e-3 (s=inf), Huffman lossless, one "
+                       "sub-domain, Compressor::Compress / Decompress device resident",
+           "value": 2 * nbytes / ((tc + td) * 1e-3) / 1e9, "unit": "GB/s", "compress_ms": tc, "decompress_ms": td,
+           "compress_gbs": nbytes / (tc * 1e-3) / 1e9, "decompress_gbs": nbytes / (td * 1e-3) / 1e9,
+           "ratio": nbytes / stream, "max_abs_error": err, "error_bound": bound, "bound_ok": bool(err <= bound),
+           "steps": K, "warmup": W, "roofline": roof, "roofline_kernels": per_kernel, "kernel_breakdown": fam,
+           "roofline_codec": {"compress_frac": (nbytes + stream) / (tc * 1e-3) / 1e9 / peak,
+                              "decompress_frac": (nbytes + stream) / (td * 1e-3) / 1e9 / peak,
+                              "basis": "B_alg = N*4 + stream bytes per direction"}}
+    del plan, u, out, back
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -220,10 +417,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-size", type=int, default=129)
-    ap.add_argument("--cpu-size", type=int, default=193)
+    ap.add_argument("--ref-size", type=int, default=257)
+    ap.add_argument("--cpu-size", type=int, default=257)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c2", action="store_true")
+    ap.add_argument("--domain", type=int, default=GSHAPE[0], help="edge of the cubic domain (default 2049)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -254,42 +453,42 @@ def main():
     W = max(args.warmup, 3)
     K = args.steps
     L = _lib.lib()
+    peak, peak_src = measured_peaks()
 
-    N = int(np.prod(SHAPE))
-    nbytes = N * 4
-    gshape = (SHAPE[0] * world,) + SHAPE[1:]
-    u = field_torch(SHAPE, dev, plane0=rank * SHAPE[0])
+    gshape = (args.domain,) * 3
+    ext = sharded.partition(gshape[0], DD_SIZE)
+    comm = sharded.Comm(dist if world > 1 else None)
+    first, count = comm.owned(len(ext))
+    plane0, planes = sum(ext[:first]), sum(ext[first:first + count])
+    lshape = (planes,) + gshape[1:]
+    n_total = int(np.prod(gshape))
+    total_bytes = n_total * 4
+    local_bytes = int(np.prod(lshape)) * 4
+    B = {"u": field_torch(lshape, dev, plane0=plane0, full_n0=gshape[0])}  # device buffers (freed before e2e)
     cfg = mg.Config()
     cfg.dev_id = local_rank
-    plan = mg.Plan(SHAPE, np.float32, config=cfg)
-    cap = nbytes + 8 * (128 + cfg.huff_dict_size) + (1 << 20)
-    out = torch.empty(cap, dtype=torch.uint8, device=dev)
-    back = torch.empty(SHAPE, dtype=torch.float32, device=dev)
+    cap = int(local_bytes * 0.4) + count * (8 * (128 + cfg.huff_dict_size) + (1 << 20))
+    B["out"] = torch.empty(cap, dtype=torch.uint8, device=dev)
+    B["back"] = torch.empty(lshape, dtype=torch.float32, device=dev)
+    REL = mg.error_bound_type.REL
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_compress():
-        if world == 1:
-            payload, norm = plan.compress(u, mg.error_bound_type.REL, TOL, S, out=out)
-            return payload, norm, 0.0
-        r = sharded.compress_sharded(u, gshape, TOL, S, mg.error_bound_type.REL, SHAPE[0],
-                                     config=cfg, dist=dist)
-        return r["records"], r["norm"], r
+    def one_compress(src=None, dst=None):
+        return sharded.compress_sharded_native(B["u"] if src is None else src, gshape, TOL, S, REL, DD_SIZE,
+                                               config=cfg, comm=comm, out=B["out"] if dst is None else dst)
 
-    def one_decompress(payload, norm):
-        if world == 1:
-            return plan.decompress(payload, mg.error_bound_type.REL, TOL, S, norm, out=back)
-        # sharded: the rank's own record `u64 size | payload`, ABS with tol*norm
-        return plan.decompress(payload[8:], mg.error_bound_type.ABS,
-                               float(np.float32(TOL) * np.float32(norm)), S, norm, out=back)
+    def one_decompress(r, dst=None):
+        return sharded.decompress_sharded_native(r["header"], r["records"], B["back"] if dst is None else dst,
+                                                 config=cfg, comm=comm)
 
     # ---- warm-up (also builds workspaces) ----
     for _ in range(W):
-        payload, norm, _r = one_compress()
-        one_decompress(payload, norm)
+        r = one_compress()
+        one_decompress(r)
     barrier()
     launches0 = mg.launch_count()
     sampler = ClockSampler(local_rank)
@@ -299,9 +498,9 @@ def main():
     barrier()
     for _ in range(K):
         ev[0].record()
-        payload, norm, _r = one_compress()
+        r = one_compress()
         ev[1].record()
-        one_decompress(payload, norm)
+        one_decompress(r)
         ev[2].record()
         torch.cuda.synchronize()
         tc += ev[0].elapsed_time(ev[1])
@@ -311,207 +510,106 @@ def main():
     launches = mg.launch_count() - launches0
     tc /= K
     td /= K
+    err = 0.0
+    for a in range(0, planes, 64):
+        err = max(err, float((B["back"][a:a + 64] - B["u"][a:a + 64]).abs().max()))
+    norm = r["norm"]
     if world > 1:
-        t = torch.tensor([tc, td], dtype=torch.float64, device=dev)
+        t = torch.tensor([tc, td, err], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tc, td = float(t[0]), float(t[1])
-    stream_bytes = int(payload.numel())
-    err = float((back - u).abs().max())
-    bound = TOL * float(u.abs().max()) if world == 1 else TOL * norm
-    if world > 1:
-        t = torch.tensor([stream_bytes], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        total_stream = float(t[0])
-        e = torch.tensor([err], dtype=torch.float64, device=dev)
-        dist.all_reduce(e, op=dist.ReduceOp.MAX)
-        err = float(e[0])
-    else:
-        total_stream = stream_bytes
-    value = 2 * nbytes * world / ((tc + td) * 1e-3) / 1e9
+        tc, td, err = float(t[0]), float(t[1]), float(t[2])
+    total_stream = int(r["total"])
+    bound = TOL * norm
+    value = 2 * total_bytes / ((tc + td) * 1e-3) / 1e9
 
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": K,
-        "warmup": W, "ms_per_step": tc + td, "higher_is_better": True, "scaling": "weak",
+        "warmup": W, "ms_per_step": tc + td, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "3D fp32 513x513x513 synthetic field per GPU, relative L-inf 1e-3 (s=inf), Huffman lossless, dict 8192, block 20480",
-                   "step": "compress + decompress of the field (device resident)",
-                   "l2": "input (540 MB) and coefficient/symbol arrays exceed the 126 MB L2; no explicit flush",
-                   "multi_gpu": "MaxDim slabs of 513 planes along dim 0, one per rank; norm all-reduce + size all-gather" if world > 1 else "single GPU"},
-        "compress_gbs": nbytes * world / (tc * 1e-3) / 1e9,
-        "decompress_gbs": nbytes * world / (td * 1e-3) / 1e9,
+        "config": {"workload": WORKLOAD if args.domain == GSHAPE[0] else f"{args.domain}^3 variant of: " + WORKLOAD,
+                   "step": "compress + decompress of the whole domain (device resident), mgb_compress_sharded / "
+                           "mgb_decompress_sharded",
+                   "l2": "every sub-domain (4.3 GB) and its coefficient / symbol arrays exceed the 126 MB L2; no "
+                         "explicit flush",
+                   "multi_gpu": f"GPU g owns sub-domains [g*8/N, (g+1)*8/N) ({count} here); NCCL all-reduce of the "
+                                "per-sub-domain {max|u|, sum u^2} pairs (device-ordered) + all-gather of container "
+                                "sizes" if world > 1 else "single GPU: all 8 sub-domains"},
+        "compress_gbs": total_bytes / (tc * 1e-3) / 1e9,
+        "decompress_gbs": total_bytes / (td * 1e-3) / 1e9,
         "compress_ms": tc, "decompress_ms": td,
-        "ratio": nbytes * world / total_stream,
+        "ratio": total_bytes / total_stream, "stream_bytes": total_stream,
         "max_abs_error": err, "error_bound": bound, "bound_ok": bool(err <= bound),
         "gpu_launches": int(launches), "clocks": clocks,
+        "roofline_codec": {
+            "compress_frac": (total_bytes + total_stream) / (tc * 1e-3) / 1e9 / (peak * world),
+            "decompress_frac": (total_bytes + total_stream) / (td * 1e-3) / 1e9 / (peak * world),
+            "basis": "B_alg = N*4 + stream bytes per direction, against n_gpus x the measured copy bandwidth"},
     }
 
+    # ---- roofline of the dominant kernel: per-kernel CUDA events, one more pass ----
+    L.mgb_profile_enable(1)
+    r1 = one_compress()
+    one_decompress(r1)
+    torch.cuda.synchronize()
+    L.mgb_profile_enable(0)
     if rank == 0:
-        # ---- roofline of the dominant kernel (separate profiled pass) ----
-        peak, peak_src = measured_peaks()
-        L.mgb_profile_enable(1)
-        reps = 3
-        for _ in range(reps):
-            payload1, norm1 = plan.compress(u, mg.error_bound_type.REL, TOL, S, out=out)
-            plan.decompress(payload1, mg.error_bound_type.REL, TOL, S, norm1, out=back)
-        torch.cuda.synchronize()
-        L.mgb_profile_enable(0)
-        import ctypes as C
-        fam = []
-        k = 0
-        while True:
-            name, n_l, tot, mx = C.c_char_p(), C.c_ulonglong(0), C.c_double(0), C.c_double(0)
-            if L.mgb_profile_report(k, C.byref(name), C.byref(n_l), C.byref(tot), C.byref(mx)) != 0:
-                break
-            if n_l.value:
-                fam.append({"kernel": name.value.decode(), "launches_per_step": n_l.value / reps,
-                            "ms_per_step": tot.value / reps, "max_launch_ms": mx.value})
-            k += 1
-        fam.sort(key=lambda f: -f["ms_per_step"])
+        fam = kernel_table(L, 1)
         line["kernel_breakdown"] = fam
-        # algorithmic bytes of the largest launch of each family (finest level), fp32
-        # (DESIGN.md section 4):
-        nl = N
-        cs = (SHAPE[0] // 2 + 1) * (SHAPE[1] // 2 + 1) * (SHAPE[2] // 2 + 1)
-        alg = {
-            "coef": 2 * nl * 4,                    # read the level box, write coefficients + coarse
-            "restore": 2 * nl * 4 + cs * 4,        # read coefficients + coarse, write the level box
-            "mass_trans": (nl + cs) * 4,           # fused f/c/r pass: read n, write n/8
-            "quantize_hist": nl * 4 + nl * 2,      # read T, write u16 symbols
-            "encode": nl * 2 + total_stream / world,
-            "chunk_bits": nl * 2,
-            "decode": total_stream / world + nl * 4,   # s=inf: dequantized while flushing
-            "thomas_contig": 2 * cs * 4, "thomas_strided": 2 * cs * 4,
-            "norm": nl * 4,
-        }
-        # DRAM bytes per launch measured by ncu --set full on the same workload
-        # (profiles/r1_ncu_traffic.json, produced by scripts/make_profiles.py)
-        ncu = {}
-        try:
-            ncu = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
-        except Exception:
-            pass
-
-        def traffic_of(k):
-            t = ncu.get(k)
-            return (t["dram_read_bytes"] + t["dram_write_bytes"]) if t else None
-
-        # the quantizer runs as two launches when the upper half of the coefficients is
-        # quantized early (api.cu): its largest launch covers that share of the array
-        qshare = 1.0
-        for f in fam:
-            if f["kernel"] == "quantize_hist" and f["launches_per_step"] > 1.5:
-                first = -(-(SHAPE[0] // 2 + 1) * SHAPE[1] * SHAPE[2] // 8) * 8
-                qshare = max(first, N - first) / N
-        alg["quantize_hist"] *= qshare
-        if "quantize_hist" in ncu and qshare < 1.0:
-            ncu["quantize_hist"] = dict(ncu["quantize_hist"])
-            for key in ("dram_read_bytes", "dram_write_bytes"):
-                ncu["quantize_hist"][key] *= qshare
-
-        per_kernel = []
-        for f in fam:
-            a = alg.get(f["kernel"])
-            if a:
-                ach = a / (f["max_launch_ms"] * 1e-3) / 1e9
-                per_kernel.append({"kernel": f["kernel"], "achieved": ach, "frac": ach / peak,
-                                   "algorithmic_bytes": a, "traffic": traffic_of(f["kernel"]),
-                                   "launch_ms": f["max_launch_ms"]})
+        sub_stream = int(r1["records"].numel()) / max(count, 1)
+        roof, per_kernel = roofline_tables(fam, (ext[first],) + gshape[1:], sub_stream, peak, peak_src,
+                                           "r2_ncu_traffic_c5.json")
+        if roof:
+            line["roofline"] = roof
         line["roofline_kernels"] = per_kernel
-        if fam:
-            top = fam[0]
-            a = alg.get(top["kernel"])
-            if a:
-                achieved = a / (top["max_launch_ms"] * 1e-3) / 1e9
-                line["roofline"] = {"bound": "hbm", "kernel": top["kernel"], "achieved": achieved,
-                                    "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                                    "traffic": traffic_of(top["kernel"]), "peak_source": peak_src,
-                                    "note": "largest (finest-level) launch of the dominant family: algorithmic bytes / "
-                                            "CUDA-event duration; traffic = dram read+write bytes of that launch from "
-                                            "ncu --set full (profiles/r1_ncu_traffic.json)"}
-        # time-weighted DRAM efficiency over the finest-level launches:
-        # sum of ncu DRAM bytes / sum of live launch durations / peak
-        tb = sum(k["traffic"] for k in per_kernel if k["traffic"])
-        tt = sum(k["launch_ms"] for k in per_kernel if k["traffic"]) * 1e-3
-        if tt > 0:
-            line["roofline"]["dram_efficiency"] = tb / tt / 1e9 / peak
-        # whole-codec view on the B_alg basis of SURVEY §8d
-        line["roofline_codec"] = {
-            "compress_frac": (nbytes + total_stream / world) / (tc * 1e-3) / 1e9 / peak,
-            "decompress_frac": (nbytes + total_stream / world) / (td * 1e-3) / 1e9 / peak,
-            "basis": "B_alg = N*4 + stream bytes per direction"}
 
-    # ---- e2e through the public host API with pinned host buffers ----
-    if not args.no_e2e and world == 1:
-        hin = torch.empty(SHAPE, dtype=torch.float32, pin_memory=True)
-        hin.copy_(u)
-        hout = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
-        hback = torch.empty(SHAPE, dtype=torch.float32, pin_memory=True)
-        hin_np, hout_np, hback_np = hin.numpy(), hout.numpy(), hback.numpy()
-        ek = max(3, min(K, 5))
-        for _ in range(2):
-            s_ = mg.compress(hin_np, TOL, S, mg.error_bound_type.REL, config=cfg, out=hout_np)
-            mg.decompress(s_, config=cfg, out=hback_np)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(ek):
-            s_ = mg.compress(hin_np, TOL, S, mg.error_bound_type.REL, config=cfg, out=hout_np)
-            mg.decompress(s_, config=cfg, out=hback_np)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        et = (t1 - t0) / ek
-        e2e_err = float(np.abs(hback_np - hin_np).max())
-        line["e2e"] = {"value": 2 * nbytes / et / 1e9, "unit": "GB/s",
-                       "h2d_bytes_per_step": int(nbytes + s_.size),
-                       "d2h_bytes_per_step": int(s_.size + nbytes),
-                       "ms_per_step": et * 1e3, "max_abs_error": e2e_err,
-                       "api": "mgard_b200.compress / decompress (mgard_x::compress mirror), pinned host buffers"}
-    elif not args.no_e2e and world > 1:
-        # sharded API with HOST buffers: every rank copies its slab in from pinned
-        # memory, compresses it (norm all-reduce + size all-gather inside), copies its
-        # records out; then the way back.  Copies are inside the timed region.
-        hin = torch.empty(SHAPE, dtype=torch.float32, pin_memory=True)
-        hin.copy_(u)
+    # ---- e2e: the same calls with pinned HOST buffers ----
+    if not args.no_e2e:
+        hin = torch.empty(lshape, dtype=torch.float32, pin_memory=True)
+        hin.copy_(B["u"])
         hrec = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
-        hback = torch.empty(SHAPE, dtype=torch.float32, pin_memory=True)
-        du = torch.empty_like(u)
-        drec = torch.empty(cap, dtype=torch.uint8, device=dev)
-        ek = max(3, min(K, 5))
-        rec_bytes = 0
+        hback = torch.empty(lshape, dtype=torch.float32, pin_memory=True)
+        hin_np, hrec_np, hback_np = hin.numpy(), hrec.numpy(), hback.numpy()
+        del r, r1
+        B.clear()
+        torch.cuda.empty_cache()
+        ek = 2 if total_bytes > (8 << 30) else max(3, min(K, 5))
 
         def e2e_step():
-            du.copy_(hin, non_blocking=True)
-            r = sharded.compress_sharded(du, gshape, TOL, S, mg.error_bound_type.REL, SHAPE[0],
-                                         config=cfg, dist=dist)
-            n = int(r["records"].numel())
-            hrec[:n].copy_(r["records"], non_blocking=True)
-            torch.cuda.synchronize()
-            drec[:n].copy_(hrec[:n], non_blocking=True)
-            b = plan.decompress(drec[8:n], mg.error_bound_type.ABS,
-                                float(np.float32(TOL) * np.float32(r["norm"])), S, r["norm"], out=back)
-            hback.copy_(b, non_blocking=True)
-            torch.cuda.synchronize()
-            return n
+            rr = one_compress(hin_np, hrec_np)
+            one_decompress(rr, hback_np)
+            return rr
 
-        for _ in range(2):
-            rec_bytes = e2e_step()
+        e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(ek):
-            rec_bytes = e2e_step()
+            rr = e2e_step()
         barrier()
         et = (time.perf_counter() - t0) / ek
-        tt = torch.tensor([et, float(rec_bytes)], dtype=torch.float64, device=dev)
-        tmax = tt.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
-        e2e_err = float((hback - hin).abs().max())
-        line["e2e"] = {"value": 2 * nbytes * world / float(tmax[0]) / 1e9, "unit": "GB/s",
-                       "h2d_bytes_per_step": int(nbytes * world + float(tt[1])),
-                       "d2h_bytes_per_step": int(nbytes * world + float(tt[1])),
-                       "ms_per_step": float(tmax[0]) * 1e3, "max_abs_error": e2e_err,
-                       "api": "mgard_b200.sharded.compress_sharded / Plan.decompress per rank, pinned host "
-                              "buffers, H2D + D2H inside the timed region; max over ranks"}
+        rec_bytes = float(len(rr["records"]))
+        e2e_err = 0.0  # every 16th plane and the last one (the host pass over 2 x 34 GB is the slow part)
+        for a in list(range(0, planes, 16)) + [planes - 1]:
+            e2e_err = max(e2e_err, float(np.abs(hback_np[a] - hin_np[a]).max()))
+        if world > 1:
+            tt = torch.tensor([et, e2e_err], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            et, e2e_err = float(tt[0]), float(tt[1])
+            tb = torch.tensor([rec_bytes], dtype=torch.float64, device=dev)
+            dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+            rec_bytes = float(tb[0])
+        line["e2e"] = {"value": 2 * total_bytes / et / 1e9, "unit": "GB/s",
+                       "h2d_bytes_per_step": int(total_bytes + rec_bytes),
+                       "d2h_bytes_per_step": int(rec_bytes + total_bytes),
+                       "ms_per_step": et * 1e3, "max_abs_error": e2e_err, "steps": ek,
+                       "api": "mgb_compress_sharded / mgb_decompress_sharded with pinned host buffers: H2D of "
+                              "sub-domain k+1, compute of k and D2H of k-1 overlap on three streams; max over ranks"}
+        del hin, hrec, hback
 
+    if rank == 0 and world == 1 and not args.no_c2:
+        B.clear()
+        torch.cuda.empty_cache()
+        mg.release_cache()
+        line["c2"] = bench_c2(mg, L, dev, cfg, W, K, peak, peak_src)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_size)
     if rank == 0:
@@ -520,6 +618,7 @@ def main():
             os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
         else:
             print(json.dumps(line))
+    comm.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -182,6 +182,55 @@ int mgb_compress_subdomains(int ndim, int dtype, const uint64_t *shape,
                             const void *d_in_first, uint64_t first,
                             uint64_t count, const mgb_config *cfg,
                             uint8_t *d_out, uint64_t cap, uint64_t *size);
+/* ---- one process per GPU: slab-sharded compress / decompress -----------------
+ * (no reference counterpart - the reference walks the sub-domains
+ * of DomainDecomposer.hpp:124-169 serially on one device, GPUPipelines.hpp:88-207, and
+ * its published multi-GPU runs use one MPI rank per GPU outside the library).
+ * The domain `shape` is MaxDim-decomposed along dim 0 in sub-domains of
+ * cfg->domain_decomposition_size planes; process `rank` of `nranks` owns the
+ * contiguous block of sub-domains mgb_owned_subdomains reports and passes them back to
+ * back in `local` (host or device).  Collectives (NCCL, resolved with dlopen - the
+ * library does not link it): one all-reduce of the per-sub-domain {max|u|, sum u^2}
+ * pairs behind relative bounds, stream-ordered on the device, and one all-gather of
+ * the container sizes.  The records written are those mgb_compress writes for the same
+ * domain on one GPU, for any number of processes. */
+typedef struct mgb_comm mgb_comm;
+/* ncclGetUniqueId -> 128 bytes (rank 0; ship them to the other ranks), then
+ * ncclCommInitRank on every rank.  nranks == 1 needs neither NCCL nor an id. */
+int mgb_comm_unique_id(uint8_t *id128);
+int mgb_comm_init_rank(const uint8_t *id128, int nranks, int rank, mgb_comm **comm);
+/* wrap a communicator the caller already has (ncclComm_t passed as void*) */
+int mgb_comm_from_nccl(void *nccl_comm, int nranks, int rank, mgb_comm **comm);
+void mgb_comm_destroy(mgb_comm *comm);
+int mgb_comm_rank(const mgb_comm *comm);
+int mgb_comm_size(const mgb_comm *comm);
+/* sub-domains [first, first + count) of `num_subdomains` owned by this process */
+int mgb_owned_subdomains(const mgb_comm *comm, uint64_t num_subdomains,
+                         uint64_t *first, uint64_t *count);
+/* comm == NULL: single process.  out (host or device, capacity cap) receives this
+ * process's `u64 size | payload` records; *local_size their bytes, *offset where they
+ * start in the assembled stream (header + records of lower ranks), *total_size the
+ * stream's size, all_sizes[nranks] every container's size, *norm the norm of the whole
+ * domain (relative bounds), header[0..*header_size) the preamble + metadata (every
+ * rank gets the same bytes; rank 0 writes them).  Optional outputs may be NULL.
+ * Synchronous at return. */
+int mgb_compress_sharded(mgb_comm *comm, int ndim, int dtype, const uint64_t *shape,
+                         double tol, double s, int ebtype, const void *local,
+                         const mgb_config *cfg, void *out, uint64_t cap,
+                         uint64_t *local_size, uint64_t *offset, uint64_t *total_size,
+                         uint64_t *all_sizes, double *norm, uint8_t *header,
+                         uint64_t header_cap, uint64_t *header_size);
+/* header: the stream's preamble + metadata (host); records: this process's records
+ * (host or device); local_out: its sub-domains back to back (host or device).  No
+ * exchange: every process decodes what it owns. */
+int mgb_decompress_sharded(mgb_comm *comm, const uint8_t *header, uint64_t header_size,
+                           const void *records, uint64_t records_size, void *local_out,
+                           const mgb_config *cfg);
+/* byte offset and size (8 + payload) of each record of an assembled stream: walks the
+ * u64 chain (CompressionHighLevel.hpp:485-520); *count = number of sub-domains */
+int mgb_stream_records(const void *stream, uint64_t size, uint64_t *offsets,
+                       uint64_t *sizes, uint64_t cap, uint64_t *count);
+
 /* Serialised metadata for the whole (decomposed) domain, host buffer. */
 int mgb_write_header(int ndim, int dtype, const uint64_t *shape, double tol,
                      double s, int ebtype, double norm,

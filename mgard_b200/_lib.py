@@ -62,6 +62,17 @@ SIGNATURES = {
     "mgb_peek_header": (_i32, [_vp, C.c_size_t, C.POINTER(_i32), _pu64, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_dbl), _pu64]),
     "mgb_release_cache": (None, []),
     "mgb_compress_subdomains": (_i32, [_i32, _i32, _pu64, _dbl, _dbl, _i32, _dbl, _vp, _u64, _u64, C.POINTER(MgbConfig), _vp, _u64, _pu64]),
+    "mgb_comm_unique_id": (_i32, [_vp]),
+    "mgb_comm_init_rank": (_i32, [_vp, _i32, _i32, C.POINTER(_vp)]),
+    "mgb_comm_from_nccl": (_i32, [_vp, _i32, _i32, C.POINTER(_vp)]),
+    "mgb_comm_destroy": (None, [_vp]),
+    "mgb_comm_rank": (_i32, [_vp]),
+    "mgb_comm_size": (_i32, [_vp]),
+    "mgb_owned_subdomains": (_i32, [_vp, _u64, _pu64, _pu64]),
+    "mgb_compress_sharded": (_i32, [_vp, _i32, _i32, _pu64, _dbl, _dbl, _i32, _vp, C.POINTER(MgbConfig), _vp, _u64,
+                                    _pu64, _pu64, _pu64, _pu64, C.POINTER(_dbl), _vp, _u64, _pu64]),
+    "mgb_decompress_sharded": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, C.POINTER(MgbConfig)]),
+    "mgb_stream_records": (_i32, [_vp, _u64, _pu64, _pu64, _u64, _pu64]),
     "mgb_write_header": (_i32, [_i32, _i32, _pu64, _dbl, _dbl, _i32, _dbl, C.POINTER(_vp), C.POINTER(MgbConfig), _vp, _u64, _pu64]),
     "mgb_pin_memory": (_i32, [_vp, _u64]),
     "mgb_check_memory_pinned": (_i32, [_vp]),

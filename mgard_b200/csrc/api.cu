@@ -45,6 +45,8 @@ int mgb_prepare_quantizers(mgb_plan *plan, int ebtype, double tol, double s, int
                            uint64_t n_total, uint64_t nsub, void *d_qtab, double *d_norm_out,
                            cudaStream_t st);
 int mgb_norm_async(mgb_plan *plan, const void *d_in, uint64_t n, double *d_red, cudaStream_t st);
+int mgb_norm_raw(int dtype, const void *d_in, uint64_t n, double *d_part, double *d_red, cudaStream_t st);
+int mgb_norm_combine(const double *d_pairs, int count, double *d_red, cudaStream_t st);
 int mgb_linearize_symbols(mgb_plan *p, const uint16_t *d_dense, uint16_t *d_linear, const unsigned long long *d_ocount,
                           uint64_t *d_oidx, uint64_t ocap, cudaStream_t st);
 int mgb_delinearize_symbols(mgb_plan *p, const uint16_t *d_linear, uint16_t *d_dense, uint32_t *d_inverse,
@@ -99,9 +101,10 @@ bool is_inf(double s) { return std::isinf(s) && s > 0; }
 //                          level's coefficient kernel (L-inf, fp32, tiled 3-D path) or
 //                          the norm kernels - and turned into the table there
 //   otherwise ABS          the table is computed on the host and passed by value
-static int compress_lowlevel_async(mgb_plan *p, const void *d_in, int ebtype, double tol, double s,
-                                   const void *d_qtab_ext, uint8_t *d_out, uint64_t cap,
-                                   cudaStream_t st) {
+// front: norm, decomposition, quantization + histogram, outlier order (the block's
+// destination is not needed yet); back: Huffman into d_out.
+static int compress_lowlevel_front(mgb_plan *p, const void *d_in, int ebtype, double tol, double s,
+                                   const void *d_qtab_ext, cudaStream_t st) {
   int rc = ensure_lowlevel_workspace(p);
   if (rc)
     return rc;
@@ -156,7 +159,6 @@ static int compress_lowlevel_async(mgb_plan *p, const void *d_in, int ebtype, do
   }
   if (rc)
     return rc;
-  const uint16_t *sym = p->d_sym;
   if (p->cfg.reorder) {
     // Config::reorder: symbols and outlier positions in level-linearised order
     // (LinearQuantization.hpp:46-146,232-248); the work buffer is free by now
@@ -164,16 +166,26 @@ static int compress_lowlevel_async(mgb_plan *p, const void *d_in, int ebtype, do
                                p->outlier_cap, st);
     if (rc)
       return rc;
-    sym = (const uint16_t *)p->d_wA;
   }
   // index order: deterministic stream
-  rc = mgb_sort_outliers(p->d_scalars, p->d_oidx, p->d_oval, p->outlier_cap, st);
-  if (rc)
-    return rc;
-  // speculative: encode assuming the outlier buffer was large enough (checked by the caller
-  // after mgb_huffman_finish)
+  return mgb_sort_outliers(p->d_scalars, p->d_oidx, p->d_oval, p->outlier_cap, st);
+}
+
+// speculative: encodes assuming the outlier buffer was large enough (the flag read back
+// with the block size tells)
+static int compress_lowlevel_back(mgb_plan *p, uint8_t *d_out, uint64_t cap, cudaStream_t st) {
+  const uint16_t *sym = p->cfg.reorder ? (const uint16_t *)p->d_wA : p->d_sym;
   return mgb_huffman_compress_async(p, sym, p->N, p->d_hist, p->d_scalars, 0, p->d_oidx, p->d_oval,
                                     d_out, cap, st);
+}
+
+static int compress_lowlevel_async(mgb_plan *p, const void *d_in, int ebtype, double tol, double s,
+                                   const void *d_qtab_ext, uint8_t *d_out, uint64_t cap,
+                                   cudaStream_t st) {
+  int rc = compress_lowlevel_front(p, d_in, ebtype, tol, s, d_qtab_ext, st);
+  if (rc)
+    return rc;
+  return compress_lowlevel_back(p, d_out, cap, st);
 }
 
 // After mgb_huffman_finish: the outlier list did not fit (LinearQuantization.hpp:661-675)
@@ -224,9 +236,11 @@ static int compress_lowlevel_impl(mgb_plan *p, const void *d_in, int ebtype,
                                 (cudaStream_t)stream);
 }
 
-static int decompress_lowlevel_impl(mgb_plan *p, const uint8_t *d_in, uint64_t size,
-                                       int ebtype, double tol, double s, double norm,
-                                       void *d_out, void *stream) {
+// Compressor::Decompress without the final synchronisation (the Huffman header is
+// still read back to size the views, Huffman.hpp:264-320)
+static int decompress_lowlevel_async(mgb_plan *p, const uint8_t *d_in, uint64_t size,
+                                     int ebtype, double tol, double s, double norm,
+                                     void *d_out, void *stream) {
   if (!p || !d_in || !d_out)
     return MGB_BAD_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
@@ -273,10 +287,15 @@ static int decompress_lowlevel_impl(mgb_plan *p, const uint8_t *d_in, uint64_t s
     rc = mgb_dequantize(p, p->d_sym, oc, oidx, oval, ebtype, tol, s, norm, p->d_coef, st);
   if (rc)
     return rc;
-  rc = mgb_recompose_impl(p, p->d_coef, d_out, st);
+  return mgb_recompose_impl(p, p->d_coef, d_out, st);
+}
+
+static int decompress_lowlevel_impl(mgb_plan *p, const uint8_t *d_in, uint64_t size, int ebtype,
+                                    double tol, double s, double norm, void *d_out, void *stream) {
+  int rc = decompress_lowlevel_async(p, d_in, size, ebtype, tol, s, norm, d_out, stream);
   if (rc)
     return rc;
-  MGB_CUDA_CHECK(cudaStreamSynchronize(st));
+  MGB_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
   return MGB_SUCCESS;
 }
 
@@ -294,10 +313,6 @@ struct CacheKey {
 
 struct HighLevelCache {
   std::map<CacheKey, mgb_plan *> plans;
-  unsigned char *d_stage = nullptr; // sub-domain input / output staging
-  uint64_t stage_bytes = 0;
-  unsigned char *d_payload = nullptr; // aligned compressed sub-domain
-  uint64_t payload_bytes = 0;
   std::mutex mu;
 };
 HighLevelCache g_cache;
@@ -523,100 +538,398 @@ void header_from(int ndim, int dtype, const uint64_t *shape, double tol, double 
   }
 }
 
-// compress sub-domains [first, first+count) into records `u64 size | payload`
-// appended to `out` (host or device) starting at *offset.
-int compress_records(int ndim, int dtype, const uint64_t *shape, const Partition &pt,
-                     double local_tol, double s, int local_eb, double *norm,
-                     const void *in_full_or_first, bool in_is_first_subdomain,
-                     uint64_t first, uint64_t count, const void *const *coords,
-                     const mgb_config *cfg, unsigned char *out, bool out_on_device,
-                     uint64_t cap, uint64_t *offset, cudaStream_t st) {
-  const size_t tsize = dtype == MGB_F32 ? 4 : 8;
-  for (uint64_t id = first; id < first + count; id++) {
-    uint64_t sub[MGB_MAX_DIMS];
-    subdomain_shape(pt, ndim, shape, id, sub);
-    uint64_t nsub = 1;
-    for (int d = 0; d < ndim; d++)
-      nsub *= sub[d];
-    // coordinates of the sub-domain (DomainDecomposer.hpp:283-300)
-    const void *subcoords[MGB_MAX_DIMS];
-    if (coords) {
-      for (int d = 0; d < ndim; d++)
-        subcoords[d] = coords[d];
-      if (pt.decomposed)
-        subcoords[pt.dim] =
-            (const unsigned char *)coords[pt.dim] + id * pt.size * tsize;
+// ---- NCCL, resolved at run time ---------------------------------------------------
+// The library does not link NCCL: one-process-per-GPU callers (torch.distributed,
+// MPI + NCCL) already have libnccl.so.2 in the process; it is looked up with dlopen.
+struct mgb_nccl_uid {
+  char internal[128];
+};
+struct NcclApi {
+  int (*GetUniqueId)(mgb_nccl_uid *) = nullptr;
+  int (*CommInitRank)(void **, int, mgb_nccl_uid, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+const NcclApi &nccl_api() {
+  static NcclApi api = [] {
+    NcclApi a;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h)
+      h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h)
+      h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+      a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+      a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+      a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
+      a.AllGather = (decltype(a.AllGather))dlsym(h, "ncclAllGather");
+      a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+      a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.AllGather;
     }
-    mgb_plan *plan = nullptr;
-    bool owned = false;
-    int rc = get_plan(ndim, dtype, sub, coords ? subcoords : nullptr, cfg, &plan, &owned);
-    if (rc)
-      return rc;
-    const uint64_t raw_bytes = nsub * tsize;
-    // dense device copy of the sub-domain
-    const void *d_in;
-    const bool in_dev = is_device_pointer(in_full_or_first);
-    const bool contiguous = !pt.decomposed || pt.dim == 0;
-    if (in_is_first_subdomain && !contiguous)
-      return MGB_BAD_ARGUMENT;
-    uint64_t plane = tsize; // bytes of one index along dim 0
-    for (int d = 1; d < ndim; d++)
-      plane *= shape[d];
-    const unsigned char *sp = nullptr;
-    if (contiguous) {
-      uint64_t rel = in_is_first_subdomain ? id - first : id;
-      sp = (const unsigned char *)in_full_or_first +
-           (pt.decomposed ? rel * pt.size * plane : 0);
+    return a;
+  }();
+  return api;
+}
+enum { NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+#define MGB_NCCL_CHECK(x)                                                                \
+  do {                                                                                   \
+    int e_ = (x);                                                                        \
+    if (e_ != 0) {                                                                       \
+      const NcclApi &a_ = nccl_api();                                                    \
+      fprintf(stderr, "mgard_b200: NCCL error %s at %s:%d\n",                            \
+              a_.GetErrorString ? a_.GetErrorString(e_) : "?", __FILE__, __LINE__);      \
+      return MGB_FAILURE;                                                                \
+    }                                                                                    \
+  } while (0)
+
+} // namespace
+
+struct mgb_comm {
+  void *nccl = nullptr; // ncclComm_t
+  int rank = 0, nranks = 1;
+  bool owned = false;
+};
+
+namespace {
+
+// ---- per-device resources of the high-level calls -----------------------------------
+// Three non-blocking streams as the reference's pipeline has three queues per device
+// (GPUPipelines.hpp:88-207): host-to-device staging, compute, device-to-host drain;
+// two staging slots each way.
+struct DevRes {
+  cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr};
+  cudaEvent_t ev_entry = nullptr;
+  unsigned char *stage[2] = {nullptr, nullptr};
+  uint64_t stage_bytes[2] = {0, 0};
+  unsigned char *payload[2] = {nullptr, nullptr};
+  uint64_t payload_bytes[2] = {0, 0};
+  unsigned char *d_full = nullptr; // whole local block staged once (relative bounds, host input)
+  uint64_t full_bytes = 0;
+  double *d_red = nullptr;   // [0..1] {max |x|, sum x^2} of the domain, [2] norm, [4..] reduction scratch
+  double *d_pairs = nullptr; // {max, sum} per sub-domain
+  uint64_t pairs_cap = 0;
+  unsigned long long *d_sizes = nullptr; // size exchange: [0] mine, [8..8+nranks) all
+  uint64_t sizes_cap = 0;
+  unsigned long long *h_pin = nullptr; // pinned scratch
+};
+std::map<int, DevRes> g_devres;
+
+int dev_res(DevRes **out) {
+  int dev = 0;
+  MGB_CUDA_CHECK(cudaGetDevice(&dev));
+  DevRes &r = g_devres[dev];
+  if (!r.s_comp) {
+    MGB_CUDA_CHECK(cudaStreamCreateWithFlags(&r.s_in, cudaStreamNonBlocking));
+    MGB_CUDA_CHECK(cudaStreamCreateWithFlags(&r.s_comp, cudaStreamNonBlocking));
+    MGB_CUDA_CHECK(cudaStreamCreateWithFlags(&r.s_out, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+      MGB_CUDA_CHECK(cudaEventCreateWithFlags(&r.ev_in[k], cudaEventDisableTiming));
+      MGB_CUDA_CHECK(cudaEventCreateWithFlags(&r.ev_out[k], cudaEventDisableTiming));
+      MGB_CUDA_CHECK(cudaEventCreateWithFlags(&r.ev_comp[k], cudaEventDisableTiming));
     }
-    if (in_dev && contiguous) {
-      d_in = sp;
-    } else {
-      rc = ensure_bytes(&g_cache.d_stage, &g_cache.stage_bytes, raw_bytes);
-      if (rc)
-        return rc;
-      if (contiguous) {
-        MGB_CUDA_CHECK(cudaMemcpyAsync(g_cache.d_stage, sp, raw_bytes,
-                                       cudaMemcpyDefault, st));
-      } else {
-        rc = copy_subdomain(pt, ndim, shape, tsize, id, in_full_or_first,
-                            g_cache.d_stage, true, st);
+    MGB_CUDA_CHECK(cudaEventCreateWithFlags(&r.ev_entry, cudaEventDisableTiming));
+    MGB_CUDA_CHECK(cudaMalloc(&r.d_red, (4 + MGB_NORM_PART_DOUBLES) * sizeof(double)));
+    MGB_CUDA_CHECK(cudaMallocHost(&r.h_pin, 64 * sizeof(unsigned long long)));
+  }
+  *out = &r;
+  return MGB_SUCCESS;
+}
+
+// Work issued before the call on the legacy default stream (and streams that
+// synchronise with it) is ordered before ours: the caller's buffers are ready.
+int join_caller(DevRes *r) {
+  MGB_CUDA_CHECK(cudaEventRecord(r->ev_entry, cudaStreamLegacy));
+  MGB_CUDA_CHECK(cudaStreamWaitEvent(r->s_in, r->ev_entry, 0));
+  MGB_CUDA_CHECK(cudaStreamWaitEvent(r->s_comp, r->ev_entry, 0));
+  MGB_CUDA_CHECK(cudaStreamWaitEvent(r->s_out, r->ev_entry, 0));
+  return MGB_SUCCESS;
+}
+
+// owned (non-uniform) plans are destroyed on every path
+struct PlanGuard {
+  mgb_plan *p = nullptr;
+  bool owned = false;
+  ~PlanGuard() {
+    if (owned && p)
+      mgb_plan_destroy(p);
+  }
+};
+
+uint64_t subdomain_elems(const Partition &pt, int ndim, const uint64_t *shape, uint64_t id) {
+  uint64_t sub[MGB_MAX_DIMS];
+  subdomain_shape(pt, ndim, shape, id, sub);
+  uint64_t n = 1;
+  for (int d = 0; d < ndim; d++)
+    n *= sub[d];
+  return n;
+}
+
+// One call of the high-level compressor on this process: sub-domains
+// [first, first + count) of the partition `pt` of the domain `shape`.
+struct CompressJob {
+  int ndim = 0, dtype = 0;
+  const uint64_t *shape = nullptr; // whole domain
+  Partition pt;
+  uint64_t first = 0, count = 1;
+  // input: the whole array (local == false; any partition, single process) or this
+  // process's sub-domains back to back (local == true; partition along dim 0)
+  const void *in = nullptr;
+  bool local = false;
+  const void *const *coords = nullptr;
+  const mgb_config *cfg = nullptr;
+  double tol = 0, s = 0;
+  int ebtype = MGB_ABS;
+  bool norm_given = false; // norm holds the global norm (mgb_compress_subdomains)
+  double norm = 1;         // out: norm of the original data (relative bounds)
+  unsigned char *out = nullptr;
+  bool out_dev = false;
+  uint64_t cap = 0;
+  uint64_t offset = 0; // in: where the first record goes; out: end of the last one
+  mgb_comm *comm = nullptr;
+};
+
+// plan of sub-domain `id` (coordinates cut as DomainDecomposer.hpp:283-300 does)
+int subdomain_plan(const CompressJob &j, uint64_t id, PlanGuard &g, uint64_t *sub) {
+  subdomain_shape(j.pt, j.ndim, j.shape, id, sub);
+  const size_t tsize = j.dtype == MGB_F32 ? 4 : 8;
+  const void *subcoords[MGB_MAX_DIMS];
+  if (j.coords) {
+    for (int d = 0; d < j.ndim; d++)
+      subcoords[d] = j.coords[d];
+    if (j.pt.decomposed)
+      subcoords[j.pt.dim] = (const unsigned char *)j.coords[j.pt.dim] + id * j.pt.size * tsize;
+  }
+  return get_plan(j.ndim, j.dtype, sub, j.coords ? subcoords : nullptr, j.cfg, &g.p, &g.owned);
+}
+
+// where sub-domain `id` starts in the input when it is contiguous there
+const unsigned char *subdomain_ptr(const CompressJob &j, uint64_t id, uint64_t plane) {
+  if (!j.pt.decomposed)
+    return (const unsigned char *)j.in;
+  const uint64_t rel = j.local ? id - j.first : id;
+  return (const unsigned char *)j.in + rel * j.pt.size * plane;
+}
+
+// dense copy of sub-domain `id` into device memory `dst` on stream st
+int fetch_subdomain(const CompressJob &j, uint64_t id, uint64_t plane, bool contiguous, uint64_t raw_bytes,
+                    unsigned char *dst, cudaStream_t st) {
+  const size_t tsize = j.dtype == MGB_F32 ? 4 : 8;
+  if (contiguous) {
+    MGB_CUDA_CHECK(cudaMemcpyAsync(dst, subdomain_ptr(j, id, plane), raw_bytes, cudaMemcpyDefault, st));
+    return MGB_SUCCESS;
+  }
+  return copy_subdomain(j.pt, j.ndim, j.shape, tsize, id, j.in, dst, true, st);
+}
+
+int compress_core(CompressJob &j) {
+  DevRes *r = nullptr;
+  int rc = dev_res(&r);
+  if (rc)
+    return rc;
+  rc = join_caller(r);
+  if (rc)
+    return rc;
+  const mgb_config *cfg = j.cfg;
+  const size_t tsize = j.dtype == MGB_F32 ? 4 : 8;
+  const bool in_dev = is_device_pointer(j.in);
+  const bool contiguous = !j.pt.decomposed || j.pt.dim == 0;
+  if (j.local && !contiguous)
+    return MGB_BAD_ARGUMENT;
+  uint64_t plane = tsize; // bytes of one index along dim 0
+  for (int d = 1; d < j.ndim; d++)
+    plane *= j.shape[d];
+  uint64_t n_total = 1;
+  for (int d = 0; d < j.ndim; d++)
+    n_total *= j.shape[d];
+  const bool direct_in = in_dev && contiguous; // sub-domains are read where they lie
+  cudaStream_t sc = r->s_comp;
+
+  // ---- error control of a decomposed domain (CompressionHighLevel.hpp:128-139) -------
+  // relative bounds need the norm of the WHOLE domain before any sub-domain is
+  // quantized: {max |x|, sum x^2} per sub-domain (two-stage reduction each), summed
+  // across processes (x + 0 is exact, so every process ends up with every pair), then
+  // combined in sub-domain order - the result does not depend on the number of
+  // processes.  Nothing of this visits the host; the quantizer tables are made on the
+  // device from the reduced pair (quantize.cu: prepare_q_kernel).
+  const bool device_norm = j.pt.decomposed && j.ebtype == MGB_REL && !j.norm_given;
+  double ltol = j.tol;
+  int leb = j.ebtype;
+  if (j.pt.decomposed && !device_norm) {
+    ltol = local_abs_tol(j.dtype, j.ebtype, j.norm, j.tol, j.s, j.pt.count);
+    leb = MGB_ABS;
+  }
+  uint64_t local_bytes = 0, max_raw = 0;
+  for (uint64_t id = j.first; id < j.first + j.count; id++) {
+    const uint64_t b = subdomain_elems(j.pt, j.ndim, j.shape, id) * tsize;
+    local_bytes += b;
+    max_raw = std::max(max_raw, b);
+  }
+  bool staged_full = false; // the local block sits dense in r->d_full
+  if (device_norm) {
+    if (r->pairs_cap < j.pt.count) {
+      cudaFree(r->d_pairs);
+      r->d_pairs = nullptr;
+      r->pairs_cap = 0;
+      MGB_CUDA_CHECK(cudaMalloc(&r->d_pairs, 2 * j.pt.count * sizeof(double)));
+      r->pairs_cap = j.pt.count;
+    }
+    MGB_CUDA_CHECK(cudaMemsetAsync(r->d_pairs, 0, 2 * j.pt.count * sizeof(double), sc));
+    double *d_part = r->d_red + 4;
+    if (direct_in) {
+      for (uint64_t id = j.first; id < j.first + j.count; id++) {
+        rc = mgb_norm_raw(j.dtype, subdomain_ptr(j, id, plane), subdomain_elems(j.pt, j.ndim, j.shape, id), d_part,
+                          r->d_pairs + 2 * id, sc);
         if (rc)
           return rc;
       }
-      d_in = g_cache.d_stage;
+    } else {
+      // host (or strided) input: one pass over the link if the block fits next to the
+      // workspaces, else the norm pass re-reads it as the reference's
+      // calc_norm_decomposed_w_prefetch does (ErrorToleranceCalculator.hpp:91-132)
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      staged_full = local_bytes <= r->full_bytes ||
+                    (double)local_bytes + 8.0 * (double)max_raw + (double)(1ull << 30) < (double)(free_b + r->full_bytes);
+      if (staged_full) {
+        rc = ensure_bytes(&r->d_full, &r->full_bytes, local_bytes);
+        if (rc)
+          return rc;
+      } else {
+        for (int k = 0; k < 2; k++) {
+          rc = ensure_bytes(&r->stage[k], &r->stage_bytes[k], max_raw);
+          if (rc)
+            return rc;
+        }
+      }
+      uint64_t off = 0, k = 0;
+      for (uint64_t id = j.first; id < j.first + j.count; id++, k++) {
+        const uint64_t nsub = subdomain_elems(j.pt, j.ndim, j.shape, id);
+        unsigned char *dst = staged_full ? r->d_full + off : r->stage[k & 1];
+        if (!staged_full && k >= 2)
+          MGB_CUDA_CHECK(cudaStreamWaitEvent(r->s_in, r->ev_comp[k & 1], 0));
+        rc = fetch_subdomain(j, id, plane, contiguous, nsub * tsize, dst, r->s_in);
+        if (rc)
+          return rc;
+        MGB_CUDA_CHECK(cudaEventRecord(r->ev_in[k & 1], r->s_in));
+        MGB_CUDA_CHECK(cudaStreamWaitEvent(sc, r->ev_in[k & 1], 0));
+        rc = mgb_norm_raw(j.dtype, dst, nsub, d_part, r->d_pairs + 2 * id, sc);
+        if (rc)
+          return rc;
+        MGB_CUDA_CHECK(cudaEventRecord(r->ev_comp[k & 1], sc));
+        off += nsub * tsize;
+      }
+      if (!staged_full) { // the slots are reused by the compression pass below
+        MGB_CUDA_CHECK(cudaStreamWaitEvent(r->s_in, r->ev_comp[0], 0));
+        MGB_CUDA_CHECK(cudaStreamWaitEvent(r->s_in, r->ev_comp[1], 0));
+      }
     }
-    uint64_t pcap = raw_bytes + 2 * (1024 + 8ull * cfg->huff_dict_size) +
-                    32 * ((nsub - 1) / cfg->huff_block_size + 1) + 4096;
-    // device output whose payload position is 8-byte aligned: compress straight
-    // into the record (no staging copy); otherwise through an aligned buffer
-    unsigned char *direct = nullptr;
-    if (cfg->lossless != 2 && out_on_device && *offset + 8 <= cap &&
-        (((uintptr_t)(out + *offset + 8)) & 7) == 0)
-      direct = out + *offset + 8;
-    if (!direct) {
-      rc = ensure_bytes(&g_cache.d_payload, &g_cache.payload_bytes, pcap);
+    if (j.comm && j.comm->nranks > 1) {
+      const NcclApi &nc = nccl_api();
+      if (!nc.ok || !j.comm->nccl)
+        return MGB_FAILURE;
+      MGB_NCCL_CHECK(nc.AllReduce(r->d_pairs, r->d_pairs, 2 * j.pt.count, NCCL_FLOAT64, NCCL_SUM, j.comm->nccl, sc));
+    }
+    rc = mgb_norm_combine(r->d_pairs, (int)j.pt.count, r->d_red, sc);
+    if (rc)
+      return rc;
+  }
+
+  // ---- records: H2D of k+1 | compute of k | D2H of k-1 ------------------------------
+  const bool stage_in = !(direct_in || staged_full);
+  if (stage_in)
+    for (int k = 0; k < 2; k++) {
+      rc = ensure_bytes(&r->stage[k], &r->stage_bytes[k], max_raw);
       if (rc)
         return rc;
     }
+  auto issue_fetch = [&](uint64_t k) -> int {
+    const uint64_t id = j.first + k;
+    const uint64_t nsub = subdomain_elems(j.pt, j.ndim, j.shape, id);
+    int e = fetch_subdomain(j, id, plane, contiguous, nsub * tsize, r->stage[k & 1], r->s_in);
+    if (e)
+      return e;
+    MGB_CUDA_CHECK(cudaEventRecord(r->ev_in[k & 1], r->s_in));
+    return MGB_SUCCESS;
+  };
+  if (stage_in) {
+    rc = issue_fetch(0);
+    if (rc)
+      return rc;
+  }
+  uint64_t full_off = 0;
+  for (uint64_t k = 0; k < j.count; k++) {
+    const uint64_t id = j.first + k;
+    uint64_t sub[MGB_MAX_DIMS];
+    PlanGuard g;
+    rc = subdomain_plan(j, id, g, sub);
+    if (rc)
+      return rc;
+    mgb_plan *plan = g.p;
+    const uint64_t nsub = plan->N, raw_bytes = nsub * tsize;
+    const int slot = (int)(k & 1);
+    // slot (k+1)&1 was last read by the compression of k-1, which the host has waited for
+    if (stage_in && k + 1 < j.count) {
+      rc = issue_fetch(k + 1);
+      if (rc)
+        return rc;
+    }
+    const void *d_in;
+    if (direct_in)
+      d_in = subdomain_ptr(j, id, plane);
+    else if (staged_full)
+      d_in = r->d_full + full_off;
+    else {
+      d_in = r->stage[slot];
+      MGB_CUDA_CHECK(cudaStreamWaitEvent(sc, r->ev_in[slot], 0));
+    }
+    full_off += raw_bytes;
+    const void *qtab = nullptr;
+    if (device_norm) {
+      rc = ensure_lowlevel_workspace(plan);
+      if (rc)
+        return rc;
+      rc = mgb_prepare_quantizers(plan, MGB_REL, j.tol, j.s, 1, r->d_red, n_total, j.pt.count, plan->d_qtab,
+                                  r->d_red + 2, sc);
+      if (rc)
+        return rc;
+      qtab = plan->d_qtab;
+    }
+    uint64_t pcap = raw_bytes + 2 * (1024 + 8ull * cfg->huff_dict_size) +
+                    32 * ((nsub - 1) / cfg->huff_block_size + 1) + 4096;
+    // device output whose payload position is 8-byte aligned: compress straight into
+    // the record; otherwise into a slot that the drain stream copies out
+    unsigned char *direct = nullptr;
+    if (cfg->lossless != 2 && j.out_dev && j.offset + 8 <= j.cap && (((uintptr_t)(j.out + j.offset + 8)) & 7) == 0)
+      direct = j.out + j.offset + 8;
+    if (!direct) {
+      rc = ensure_bytes(&r->payload[slot], &r->payload_bytes[slot], pcap);
+      if (rc)
+        return rc;
+      MGB_CUDA_CHECK(cudaStreamWaitEvent(sc, r->ev_out[slot], 0)); // drained (record k-2)
+    }
     uint64_t psize = 0;
-    rc = mgb_compress_lowlevel(plan, d_in, local_eb, local_tol, s, norm,
-                               direct ? direct : g_cache.d_payload,
-                               direct ? std::min<uint64_t>(pcap, cap - *offset - 8) : pcap, &psize,
-                               st);
-    if (owned)
-      mgb_plan_destroy(plan);
-    const void *payload = direct ? direct : g_cache.d_payload;
+    double nrm = j.norm;
+    rc = compress_lowlevel_sync(plan, d_in, leb, ltol, j.s, qtab, &nrm, direct ? direct : r->payload[slot],
+                                direct ? std::min<uint64_t>(pcap, j.cap - j.offset - 8) : pcap, &psize, sc);
+    if (!j.pt.decomposed && j.ebtype == MGB_REL)
+      j.norm = nrm;
+    const void *payload = direct ? direct : r->payload[slot];
     std::vector<unsigned char> zbuf; // host: size_t count | zstd frame
     if (rc == MGB_SUCCESS && cfg->lossless == 2) {
       const ZstdApi &z = zstd_api();
       if (!z.ok)
         return MGB_FAILURE;
       std::vector<unsigned char> hpay(psize);
-      MGB_CUDA_CHECK(cudaMemcpyAsync(hpay.data(), payload, psize, cudaMemcpyDeviceToHost, st));
-      MGB_CUDA_CHECK(cudaStreamSynchronize(st));
+      MGB_CUDA_CHECK(cudaMemcpyAsync(hpay.data(), payload, psize, cudaMemcpyDeviceToHost, sc));
+      MGB_CUDA_CHECK(cudaStreamSynchronize(sc));
       zbuf.resize(sizeof(size_t) + z.bound(psize));
-      const size_t zs = z.compress(zbuf.data() + sizeof(size_t), zbuf.size() - sizeof(size_t),
-                                   hpay.data(), psize, cfg->zstd_compress_level);
+      const size_t zs = z.compress(zbuf.data() + sizeof(size_t), zbuf.size() - sizeof(size_t), hpay.data(), psize,
+                                   cfg->zstd_compress_level);
       if (z.is_error(zs))
         return MGB_FAILURE;
       const size_t count = psize;
@@ -634,23 +947,40 @@ int compress_records(int ndim, int dtype, const uint64_t *shape, const Partition
     if (rc)
       return rc;
     // GPUPipelines.hpp:157-193
-    if (*offset + 8 + psize > cap)
+    if (j.offset + 8 + psize > j.cap)
       return MGB_OUTPUT_TOO_LARGE;
-    uint64_t sz = psize;
-    if (out_on_device) {
-      MGB_CUDA_CHECK(cudaMemcpyAsync(out + *offset, &sz, 8, cudaMemcpyHostToDevice, st));
-      MGB_CUDA_CHECK(cudaStreamSynchronize(st));
+    const bool host_payload = payload == (const void *)zbuf.data() && !zbuf.empty();
+    if (j.out_dev) {
+      // pageable source: staged by the runtime before the call returns
+      const uint64_t sz = psize;
+      MGB_CUDA_CHECK(cudaMemcpyAsync(j.out + j.offset, &sz, 8, cudaMemcpyHostToDevice, r->s_out));
     } else {
-      memcpy(out + *offset, &sz, 8);
+      memcpy(j.out + j.offset, &psize, 8);
     }
-    if (payload != (const void *)(out + *offset + 8)) {
-      MGB_CUDA_CHECK(cudaMemcpyAsync(out + *offset + 8, payload, psize, cudaMemcpyDefault, st));
-      MGB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (payload != (const void *)(j.out + j.offset + 8)) {
+      if (host_payload || payload == d_in) {
+        // small or rare: host-resident zstd frame / raw fallback, waited for right away
+        // (the source is a local buffer or a staging slot about to be reused)
+        MGB_CUDA_CHECK(cudaMemcpyAsync(j.out + j.offset + 8, payload, psize, cudaMemcpyDefault, r->s_out));
+        MGB_CUDA_CHECK(cudaStreamSynchronize(r->s_out));
+      } else {
+        // the compression of k is complete (its size was read back): drain it while
+        // the next sub-domain is compressed
+        MGB_CUDA_CHECK(cudaMemcpyAsync(j.out + j.offset + 8, payload, psize, cudaMemcpyDefault, r->s_out));
+      }
     }
-    *offset += 8 + psize;
+    MGB_CUDA_CHECK(cudaEventRecord(r->ev_out[slot], r->s_out));
+    j.offset += 8 + psize;
   }
+  if (device_norm) {
+    MGB_CUDA_CHECK(cudaMemcpyAsync(&r->h_pin[40], r->d_red + 2, sizeof(double), cudaMemcpyDeviceToHost, sc));
+    MGB_CUDA_CHECK(cudaStreamSynchronize(sc));
+    memcpy(&j.norm, &r->h_pin[40], sizeof(double));
+  }
+  MGB_CUDA_CHECK(cudaStreamSynchronize(r->s_out));
   return MGB_SUCCESS;
 }
+
 
 int check_args(int ndim, int dtype, const uint64_t *shape) {
   if (!shape)
@@ -665,6 +995,13 @@ int check_args(int ndim, int dtype, const uint64_t *shape) {
     return MGB_BACKEND_NOT_AVAILABLE;
   }
   return MGB_SUCCESS;
+}
+
+// contiguous block of sub-domains per process (balanced, rank-major)
+void owned_range(uint64_t nsub, int rank, int nranks, uint64_t *first, uint64_t *count) {
+  const uint64_t base = nsub / nranks, rem = nsub % nranks;
+  *first = rank * base + std::min<uint64_t>(rank, rem);
+  *count = base + ((uint64_t)rank < rem ? 1 : 0);
 }
 
 } // namespace
@@ -698,60 +1035,30 @@ static int compress_impl(int ndim, int dtype, const uint64_t *shape, double tol,
   uint64_t N = 0;
   if (!mgb_checked_elems(ndim, shape, tsize, &N))
     return MGB_BAD_ARGUMENT;
-  Partition pt;
-  rc = make_partition(ndim, shape, tsize, &cfg, pt);
+  CompressJob j;
+  rc = make_partition(ndim, shape, tsize, &cfg, j.pt);
   if (rc)
     return rc;
-  cudaStream_t st = 0;
-  double norm = 1;
-  double ltol = tol;
-  int leb = ebtype;
-  if (pt.decomposed) {
-    // CompressionHighLevel.hpp:128-139 + ErrorToleranceCalculator.hpp:70-155
-    if (ebtype == MGB_REL) {
-      double mx = 0, ss = 0;
-      for (uint64_t id = 0; id < pt.count; id++) {
-        uint64_t sub[MGB_MAX_DIMS];
-        subdomain_shape(pt, ndim, shape, id, sub);
-        mgb_plan *plan = nullptr;
-        bool owned = false;
-        mgb_config c2 = cfg;
-        rc = get_plan(ndim, dtype, sub, nullptr, &c2, &plan, &owned);
-        if (rc)
-          return rc;
-        uint64_t nsub = plan->N;
-        rc = ensure_bytes(&g_cache.d_stage, &g_cache.stage_bytes, nsub * tsize);
-        if (rc)
-          return rc;
-        rc = copy_subdomain(pt, ndim, shape, tsize, id, in, g_cache.d_stage, true, st);
-        if (rc)
-          return rc;
-        MGB_CUDA_CHECK(cudaStreamSynchronize(st));
-        double m1, s1;
-        rc = mgb_norm_partials(plan, g_cache.d_stage, &m1, &s1);
-        if (rc)
-          return rc;
-        mx = std::max(mx, m1);
-        ss += s1;
-      }
-      if (is_inf(s))
-        norm = mx;
-      else
-        norm = dtype == MGB_F32 ? (double)std::sqrt((float)ss / N) : std::sqrt(ss / N);
-      if (dtype == MGB_F32)
-        norm = (double)(float)norm;
-    }
-    ltol = local_abs_tol(dtype, ebtype, norm, tol, s, pt.count);
-    leb = MGB_ABS;
-  }
+  j.ndim = ndim;
+  j.dtype = dtype;
+  j.shape = shape;
+  j.first = 0;
+  j.count = j.pt.count;
+  j.in = in;
+  j.local = false;
+  j.coords = coords;
+  j.cfg = &cfg;
+  j.tol = tol;
+  j.s = s;
+  j.ebtype = ebtype;
   mgb_header h;
-  header_from(ndim, dtype, shape, tol, s, ebtype, norm, coords, &cfg, pt, h);
+  header_from(ndim, dtype, shape, tol, s, ebtype, 1.0, coords, &cfg, j.pt, h);
   std::vector<uint8_t> hdr = mgb_encode_stream_header(h);
   uint64_t cap;
   unsigned char *obuf;
   if (!output_pre_allocated) {
     // CompressionHighLevel.hpp:149-158 (OUTPUT_SAFTY_OVERHEAD = 1e6)
-    cap = N * tsize + 1000000 + hdr.size() + 8 * pt.count;
+    cap = N * tsize + 1000000 + hdr.size() + 8 * j.pt.count;
     if (in_dev) {
       void *p = nullptr;
       MGB_CUDA_CHECK(cudaMalloc(&p, cap));
@@ -765,21 +1072,22 @@ static int compress_impl(int ndim, int dtype, const uint64_t *shape, double tol,
     cap = *out_size;
     obuf = (unsigned char *)*out;
   }
-  const bool out_dev = is_device_pointer(obuf);
-  uint64_t offset = hdr.size();
-  if (offset > cap)
+  j.out = obuf;
+  j.out_dev = is_device_pointer(obuf);
+  j.cap = cap;
+  j.offset = hdr.size();
+  if (j.offset > cap)
     rc = MGB_OUTPUT_TOO_LARGE;
   if (!rc)
-    rc = compress_records(ndim, dtype, shape, pt, ltol, s, leb, &norm, in, false, 0,
-                          pt.count, coords, &cfg, obuf, out_dev, cap, &offset, st);
+    rc = compress_core(j);
   if (!rc) {
-    // the norm of a non-decomposed REL run is known only now
+    // the norm of a relative bound is known only now
     // (CompressionHighLevel.hpp:253-279 serialises the metadata again)
-    header_from(ndim, dtype, shape, tol, s, ebtype, norm, coords, &cfg, pt, h);
+    header_from(ndim, dtype, shape, tol, s, ebtype, j.norm, coords, &cfg, j.pt, h);
     std::vector<uint8_t> hdr2 = mgb_encode_stream_header(h);
     if (hdr2.size() != hdr.size())
       rc = MGB_FAILURE;
-    else if (out_dev)
+    else if (j.out_dev)
       rc = cudaMemcpy(obuf, hdr2.data(), hdr2.size(), cudaMemcpyHostToDevice) == cudaSuccess
                ? MGB_SUCCESS
                : MGB_CUDA_ERROR;
@@ -796,9 +1104,10 @@ static int compress_impl(int ndim, int dtype, const uint64_t *shape, double tol,
     return rc;
   }
   *out = obuf;
-  *out_size = offset;
+  *out_size = j.offset;
   return MGB_SUCCESS;
 }
+
 
 static int peek_header_impl(const void *in, size_t in_size, int *ndim, uint64_t *shape,
                                int *dtype, int *ebtype, double *tol, double *s,
@@ -838,6 +1147,263 @@ static int peek_header_impl(const void *in, size_t in_size, int *ndim, uint64_t 
   return MGB_SUCCESS;
 }
 
+namespace {
+
+// One call of the high-level decompressor on this process: records of sub-domains
+// [first, first + count), the first one starting at in + offset.
+struct DecompressJob {
+  const mgb_header *h = nullptr;
+  Partition pt;
+  uint64_t first = 0, count = 1;
+  const unsigned char *in = nullptr;
+  uint64_t in_size = 0, offset = 0;
+  // output: the whole array (local == false) or this process's sub-domains back to
+  // back (local == true; partition along dim 0)
+  unsigned char *out = nullptr;
+  bool local = false;
+  const mgb_config *cfg = nullptr;
+  const void *const *coords = nullptr; // whole-domain coordinates (T) or nullptr
+};
+
+int decompress_core(DecompressJob &j) {
+  DevRes *r = nullptr;
+  int rc = dev_res(&r);
+  if (rc)
+    return rc;
+  rc = join_caller(r);
+  if (rc)
+    return rc;
+  const mgb_header &h = *j.h;
+  const int ndim = h.ndim, dtype = h.dtype;
+  const size_t tsize = dtype == MGB_F32 ? 4 : 8;
+  const bool in_dev = is_device_pointer(j.in), out_dev = is_device_pointer(j.out);
+  const bool contiguous = !j.pt.decomposed || j.pt.dim == 0;
+  if (j.local && !contiguous)
+    return MGB_BAD_ARGUMENT;
+  double ltol = h.tol;
+  int leb = h.ebtype;
+  if (j.pt.decomposed) {
+    ltol = local_abs_tol(dtype, h.ebtype, h.norm, h.tol, h.s, j.pt.count);
+    leb = MGB_ABS;
+  }
+  uint64_t plane = tsize;
+  for (int d = 1; d < ndim; d++)
+    plane *= h.shape[d];
+  cudaStream_t sc = r->s_comp;
+  // record sizes: the u64 chain is walked up front (8 bytes per record)
+  std::vector<uint64_t> rec_off(j.count), rec_size(j.count);
+  uint64_t offset = j.offset;
+  for (uint64_t k = 0; k < j.count; k++) {
+    if (offset + 8 > j.in_size)
+      return MGB_BAD_STREAM;
+    uint64_t psize = 0;
+    if (in_dev)
+      MGB_CUDA_CHECK(cudaMemcpy(&psize, j.in + offset, 8, cudaMemcpyDeviceToHost));
+    else
+      memcpy(&psize, j.in + offset, 8);
+    offset += 8;
+    if (psize > j.in_size - offset)
+      return MGB_BAD_STREAM;
+    rec_off[k] = offset;
+    rec_size[k] = psize;
+    offset += psize;
+  }
+  // a record is decoded where it lies when it is in device memory and 8-byte aligned
+  auto in_place = [&](uint64_t k) { return in_dev && ((uintptr_t)(j.in + rec_off[k]) & 7) == 0 && h.lossless != 2; };
+  auto raw_of = [&](uint64_t k) { return subdomain_elems(j.pt, ndim, h.shape, j.first + k) * tsize; };
+  auto issue_fetch = [&](uint64_t k) -> int {
+    if (in_place(k) || h.lossless == 2 || rec_size[k] >= raw_of(k))
+      return MGB_SUCCESS;
+    const int slot = (int)(k & 1);
+    int e = ensure_bytes(&r->payload[slot], &r->payload_bytes[slot], rec_size[k] + 64);
+    if (e)
+      return e;
+    MGB_CUDA_CHECK(cudaStreamWaitEvent(r->s_in, r->ev_comp[slot], 0)); // decode of k-2 has read the slot
+    MGB_CUDA_CHECK(cudaMemcpyAsync(r->payload[slot], j.in + rec_off[k], rec_size[k], cudaMemcpyDefault, r->s_in));
+    MGB_CUDA_CHECK(cudaEventRecord(r->ev_in[slot], r->s_in));
+    return MGB_SUCCESS;
+  };
+  if (j.count) {
+    rc = issue_fetch(0);
+    if (rc)
+      return rc;
+  }
+  for (uint64_t k = 0; k < j.count; k++) {
+    const uint64_t id = j.first + k;
+    const int slot = (int)(k & 1);
+    uint64_t sub[MGB_MAX_DIMS];
+    subdomain_shape(j.pt, ndim, h.shape, id, sub);
+    const uint64_t raw_bytes = raw_of(k), psize = rec_size[k];
+    if (k + 1 < j.count) {
+      rc = issue_fetch(k + 1);
+      if (rc)
+        return rc;
+    }
+    // dense device destination of this sub-domain
+    const uint64_t rel = j.local ? k : id;
+    unsigned char *final_dst = j.out + (j.pt.decomposed && contiguous ? rel * j.pt.size * plane : 0);
+    unsigned char *d_dst;
+    const bool direct_out = out_dev && contiguous;
+    if (direct_out) {
+      d_dst = final_dst;
+    } else {
+      rc = ensure_bytes(&r->stage[slot], &r->stage_bytes[slot], raw_bytes);
+      if (rc)
+        return rc;
+      d_dst = r->stage[slot];
+      MGB_CUDA_CHECK(cudaStreamWaitEvent(sc, r->ev_out[slot], 0)); // drained (sub-domain k-2)
+    }
+    if (psize >= raw_bytes) {
+      // raw sub-domain (GPUPipelines.hpp:417,458-466)
+      MGB_CUDA_CHECK(cudaMemcpyAsync(d_dst, j.in + rec_off[k], raw_bytes, cudaMemcpyDefault, sc));
+    } else {
+      PlanGuard g;
+      const void *subcoords[MGB_MAX_DIMS];
+      if (j.coords) {
+        for (int d = 0; d < ndim; d++)
+          subcoords[d] = j.coords[d];
+        if (j.pt.decomposed)
+          subcoords[j.pt.dim] = (const unsigned char *)j.coords[j.pt.dim] + id * j.pt.size * tsize;
+      }
+      rc = get_plan(ndim, dtype, sub, j.coords ? subcoords : nullptr, j.cfg, &g.p, &g.owned);
+      if (rc)
+        return rc;
+      const unsigned char *d_pay;
+      uint64_t hsize = psize; // size of the Huffman block
+      if (h.lossless == 2) {
+        // Zstd.hpp:100-125: `size_t count | zstd frame` -> Huffman block, on the host
+        const ZstdApi &z = zstd_api();
+        if (!z.ok)
+          return MGB_FAILURE;
+        if (psize < sizeof(size_t))
+          return MGB_BAD_STREAM;
+        std::vector<unsigned char> rec(psize), hpay;
+        MGB_CUDA_CHECK(cudaMemcpy(rec.data(), j.in + rec_off[k], psize, cudaMemcpyDefault));
+        size_t count = 0;
+        memcpy(&count, rec.data(), sizeof(size_t));
+        if (count > (size_t)raw_bytes * 2 + (1u << 24))
+          return MGB_BAD_STREAM;
+        hpay.resize(count);
+        const size_t got = z.decompress(hpay.data(), count, rec.data() + sizeof(size_t), psize - sizeof(size_t));
+        if (z.is_error(got) || got != count)
+          return MGB_BAD_STREAM;
+        hsize = count;
+        MGB_CUDA_CHECK(cudaStreamSynchronize(sc)); // the slot may still be read by the previous decode
+        rc = ensure_bytes(&r->payload[slot], &r->payload_bytes[slot], hsize + 64);
+        if (rc)
+          return rc;
+        MGB_CUDA_CHECK(cudaMemcpy(r->payload[slot], hpay.data(), hsize, cudaMemcpyHostToDevice));
+        d_pay = r->payload[slot];
+      } else if (in_place(k)) {
+        d_pay = j.in + rec_off[k];
+      } else {
+        MGB_CUDA_CHECK(cudaStreamWaitEvent(sc, r->ev_in[slot], 0));
+        d_pay = r->payload[slot];
+      }
+      rc = decompress_lowlevel_async(g.p, d_pay, hsize, leb, ltol, h.s, h.norm, d_dst, sc);
+      if (rc)
+        return rc;
+      if (g.owned) // its workspaces go away with the guard
+        MGB_CUDA_CHECK(cudaStreamSynchronize(sc));
+    }
+    MGB_CUDA_CHECK(cudaEventRecord(r->ev_comp[slot], sc));
+    if (!direct_out) {
+      MGB_CUDA_CHECK(cudaStreamWaitEvent(r->s_out, r->ev_comp[slot], 0));
+      if (contiguous)
+        MGB_CUDA_CHECK(cudaMemcpyAsync(final_dst, d_dst, raw_bytes, cudaMemcpyDefault, r->s_out));
+      else {
+        rc = copy_subdomain(j.pt, ndim, h.shape, tsize, id, j.out, d_dst, false, r->s_out);
+        if (rc)
+          return rc;
+      }
+      MGB_CUDA_CHECK(cudaEventRecord(r->ev_out[slot], r->s_out));
+    }
+  }
+  MGB_CUDA_CHECK(cudaStreamSynchronize(sc));
+  MGB_CUDA_CHECK(cudaStreamSynchronize(r->s_out));
+  return MGB_SUCCESS;
+}
+
+// header of a stream in host or device memory
+int read_header(const void *in, size_t in_size, mgb_header &h, uint64_t &hb) {
+  std::vector<uint8_t> head;
+  const uint8_t *hp = (const uint8_t *)in;
+  size_t hsize = in_size;
+  if (is_device_pointer(in)) {
+    if (in_size < 17)
+      return MGB_BAD_STREAM;
+    uint8_t pre[17];
+    MGB_CUDA_CHECK(cudaMemcpy(pre, in, 17, cudaMemcpyDeviceToHost));
+    const uint64_t hs = mgb_preamble_header_size(pre, in_size);
+    if (hs == UINT64_MAX)
+      return MGB_BAD_STREAM;
+    head.resize(17 + hs);
+    MGB_CUDA_CHECK(cudaMemcpy(head.data(), in, 17 + hs, cudaMemcpyDeviceToHost));
+    hp = head.data();
+    hsize = head.size();
+  }
+  return mgb_parse_stream_header(hp, hsize, h, hb);
+}
+
+// what the header fixes for the decoder: configuration, partition, coordinates
+struct DecodeSetup {
+  mgb_config cfg;
+  Partition pt;
+  std::vector<std::vector<unsigned char>> cbytes;
+  const void *cptr[MGB_MAX_DIMS];
+  bool nonuniform = false;
+  uint64_t N = 0;
+};
+int decode_setup(const mgb_header &h, const mgb_config *cfg_in, DecodeSetup &d) {
+  if (h.convention != 0)
+    return MGB_BAD_STREAM; // MGARD-CPU stream: mgb_cpu_decompress reads those
+  mgb_config_default(&d.cfg);
+  if (cfg_in)
+    d.cfg.dev_id = cfg_in->dev_id;
+  // Metadata.cpp:129-136: the header overrides the configuration
+  d.cfg.huff_dict_size = h.dict_size;
+  d.cfg.huff_block_size = h.block_size;
+  d.cfg.lossless = h.lossless;
+  d.cfg.reorder = h.reorder;
+  d.cfg.decomposition = h.decomposition;
+  const int ndim = h.ndim;
+  const size_t tsize = h.dtype == MGB_F32 ? 4 : 8;
+  for (int k = 0; k < ndim; k++)
+    if (h.shape[k] < 3)
+      return MGB_BAD_STREAM;
+  // a header that passes its CRC can still announce an absurd shape
+  if (!mgb_checked_elems(ndim, h.shape, tsize, &d.N))
+    return MGB_BAD_STREAM;
+  d.pt.decomposed = h.decomposed;
+  d.pt.dim = (int)h.dd_dim;
+  d.pt.size = h.dd_size;
+  d.pt.count = 1;
+  if (d.pt.decomposed) {
+    if (d.pt.dim >= ndim || d.pt.size < 3 || d.pt.size >= h.shape[d.pt.dim])
+      return MGB_BAD_STREAM;
+    d.pt.count = (h.shape[d.pt.dim] - 1) / d.pt.size + 1;
+  }
+  // CompressionHighLevel.hpp:456-464: coordinates go through float
+  d.nonuniform = !h.coords.empty();
+  if (d.nonuniform) {
+    d.cbytes.resize(ndim);
+    for (int k = 0; k < ndim; k++) {
+      d.cbytes[k].resize(h.shape[k] * tsize);
+      for (uint64_t i = 0; i < h.shape[k]; i++) {
+        float f = (float)h.coords[k][i];
+        if (h.dtype == MGB_F32)
+          ((float *)d.cbytes[k].data())[i] = f;
+        else
+          ((double *)d.cbytes[k].data())[i] = f;
+      }
+      d.cptr[k] = d.cbytes[k].data();
+    }
+  }
+  return MGB_SUCCESS;
+}
+
+} // namespace
+
 static int decompress_impl(const void *in, size_t in_size, void **out,
                               const mgb_config *cfg_in, int output_pre_allocated,
                               int *ndim_out, uint64_t *shape_out, int *dtype_out) {
@@ -857,207 +1423,45 @@ static int decompress_impl(const void *in, size_t in_size, void **out,
   } else if (cfg_in && cfg_in->dev_id >= 0) {
     cudaSetDevice(cfg_in->dev_id);
   }
-  // header
-  std::vector<uint8_t> head;
-  const uint8_t *hp = (const uint8_t *)in;
-  size_t hsize = in_size;
-  if (in_dev) {
-    if (in_size < 17)
-      return MGB_BAD_STREAM;
-    uint8_t pre[17];
-    MGB_CUDA_CHECK(cudaMemcpy(pre, in, 17, cudaMemcpyDeviceToHost));
-    const uint64_t hs = mgb_preamble_header_size(pre, in_size);
-    if (hs == UINT64_MAX)
-      return MGB_BAD_STREAM;
-    head.resize(17 + hs);
-    MGB_CUDA_CHECK(cudaMemcpy(head.data(), in, 17 + hs, cudaMemcpyDeviceToHost));
-    hp = head.data();
-    hsize = head.size();
-  }
   mgb_header h;
   uint64_t hb = 0;
-  int rc = mgb_parse_stream_header(hp, hsize, h, hb);
+  int rc = read_header(in, in_size, h, hb);
   if (rc)
     return rc;
-  if (h.convention != 0)
-    return MGB_BAD_STREAM; // MGARD-CPU stream: mgb_cpu_decompress reads those
-  mgb_config cfg;
-  mgb_config_default(&cfg);
-  if (cfg_in)
-    cfg.dev_id = cfg_in->dev_id;
-  // Metadata.cpp:129-136: the header overrides the configuration
-  cfg.huff_dict_size = h.dict_size;
-  cfg.huff_block_size = h.block_size;
-  cfg.lossless = h.lossless;
-  cfg.reorder = h.reorder;
-  cfg.decomposition = h.decomposition;
-  const int ndim = h.ndim, dtype = h.dtype;
-  const size_t tsize = dtype == MGB_F32 ? 4 : 8;
-  uint64_t N = 0;
-  for (int d = 0; d < ndim; d++)
-    if (h.shape[d] < 3)
-      return MGB_BAD_STREAM;
-  // a header that passes its CRC can still announce an absurd shape
-  if (!mgb_checked_elems(ndim, h.shape, tsize, &N))
-    return MGB_BAD_STREAM;
-  Partition pt;
-  pt.decomposed = h.decomposed;
-  pt.dim = (int)h.dd_dim;
-  pt.size = h.dd_size;
-  pt.count = 1;
-  if (pt.decomposed) {
-    if (pt.dim >= ndim || pt.size < 3 || pt.size >= h.shape[pt.dim])
-      return MGB_BAD_STREAM;
-    pt.count = (h.shape[pt.dim] - 1) / pt.size + 1;
-  }
-  // CompressionHighLevel.hpp:456-464: coordinates go through float
-  std::vector<std::vector<unsigned char>> cbytes;
-  const void *cptr[MGB_MAX_DIMS];
-  const bool nonuniform = !h.coords.empty();
-  if (nonuniform) {
-    cbytes.resize(ndim);
-    for (int d = 0; d < ndim; d++) {
-      cbytes[d].resize(h.shape[d] * tsize);
-      for (uint64_t i = 0; i < h.shape[d]; i++) {
-        float f = (float)h.coords[d][i];
-        if (dtype == MGB_F32)
-          ((float *)cbytes[d].data())[i] = f;
-        else
-          ((double *)cbytes[d].data())[i] = f;
-      }
-      cptr[d] = cbytes[d].data();
-    }
-  }
-  double ltol = h.tol;
-  int leb = h.ebtype;
-  if (pt.decomposed) {
-    ltol = local_abs_tol(dtype, h.ebtype, h.norm, h.tol, h.s, pt.count);
-    leb = MGB_ABS;
-  }
+  DecodeSetup ds;
+  rc = decode_setup(h, cfg_in, ds);
+  if (rc)
+    return rc;
+  const size_t tsize = h.dtype == MGB_F32 ? 4 : 8;
   unsigned char *obuf;
   if (!output_pre_allocated) {
     if (in_dev) {
       void *p = nullptr;
-      MGB_CUDA_CHECK(cudaMalloc(&p, N * tsize));
+      MGB_CUDA_CHECK(cudaMalloc(&p, ds.N * tsize));
       obuf = (unsigned char *)p;
     } else {
-      obuf = (unsigned char *)malloc(N * tsize);
+      obuf = (unsigned char *)malloc(ds.N * tsize);
       if (!obuf)
         return MGB_FAILURE;
     }
   } else {
     obuf = (unsigned char *)*out;
   }
-  const bool out_dev = is_device_pointer(obuf);
-  cudaStream_t st = 0;
-  uint64_t offset = hb;
-  const unsigned char *ip = (const unsigned char *)in;
-  for (uint64_t id = 0; id < pt.count && !rc; id++) {
-    uint64_t sub[MGB_MAX_DIMS];
-    subdomain_shape(pt, ndim, h.shape, id, sub);
-    uint64_t nsub = 1;
-    for (int d = 0; d < ndim; d++)
-      nsub *= sub[d];
-    const uint64_t raw_bytes = nsub * tsize;
-    if (offset + 8 > in_size) {
-      rc = MGB_BAD_STREAM;
-      break;
-    }
-    uint64_t psize = 0;
-    if (in_dev)
-      cudaMemcpy(&psize, ip + offset, 8, cudaMemcpyDeviceToHost);
-    else
-      memcpy(&psize, ip + offset, 8);
-    offset += 8;
-    if (psize > in_size - offset) {
-      rc = MGB_BAD_STREAM;
-      break;
-    }
-    // dense device destination for this sub-domain
-    const bool contiguous = !pt.decomposed || pt.dim == 0;
-    unsigned char *d_dst;
-    uint64_t plane = raw_bytes / sub[pt.decomposed ? pt.dim : 0];
-    unsigned char *final_dst = obuf + (pt.decomposed && contiguous ? id * pt.size * plane : 0);
-    if (out_dev && contiguous) {
-      d_dst = final_dst;
-    } else {
-      rc = ensure_bytes(&g_cache.d_stage, &g_cache.stage_bytes, raw_bytes);
-      if (rc)
-        break;
-      d_dst = g_cache.d_stage;
-    }
-    if (psize >= raw_bytes) {
-      // raw sub-domain (GPUPipelines.hpp:417,458-466)
-      if (cudaMemcpyAsync(d_dst, ip + offset, raw_bytes, cudaMemcpyDefault, st) != cudaSuccess)
-        rc = MGB_CUDA_ERROR;
-    } else {
-      const void *subcoords[MGB_MAX_DIMS];
-      if (nonuniform) {
-        for (int d = 0; d < ndim; d++)
-          subcoords[d] = cptr[d];
-        if (pt.decomposed)
-          subcoords[pt.dim] = (const unsigned char *)cptr[pt.dim] + id * pt.size * tsize;
-      }
-      mgb_plan *plan = nullptr;
-      bool owned = false;
-      rc = get_plan(ndim, dtype, sub, nonuniform ? subcoords : nullptr, &cfg, &plan, &owned);
-      if (rc)
-        break;
-      uint64_t hsize = psize; // size of the Huffman block
-      if (h.lossless == 2) {
-        // Zstd.hpp:100-125: `size_t count | zstd frame` -> Huffman block, on the host
-        const ZstdApi &z = zstd_api();
-        std::vector<unsigned char> rec(psize), hpay;
-        if (!z.ok || psize < sizeof(size_t))
-          rc = z.ok ? MGB_BAD_STREAM : MGB_FAILURE;
-        if (!rc && cudaMemcpy(rec.data(), ip + offset, psize, cudaMemcpyDefault) != cudaSuccess)
-          rc = MGB_CUDA_ERROR;
-        if (!rc) {
-          size_t count = 0;
-          memcpy(&count, rec.data(), sizeof(size_t));
-          if (count > (size_t)raw_bytes * 2 + (1u << 24))
-            rc = MGB_BAD_STREAM;
-          if (!rc) {
-            hpay.resize(count);
-            const size_t got = z.decompress(hpay.data(), count, rec.data() + sizeof(size_t),
-                                            psize - sizeof(size_t));
-            if (z.is_error(got) || got != count)
-              rc = MGB_BAD_STREAM;
-          }
-          hsize = count;
-        }
-        if (!rc)
-          rc = ensure_bytes(&g_cache.d_payload, &g_cache.payload_bytes, hsize + 64);
-        if (!rc && cudaMemcpy(g_cache.d_payload, hpay.data(), hsize, cudaMemcpyHostToDevice) !=
-                       cudaSuccess)
-          rc = MGB_CUDA_ERROR;
-      } else {
-        rc = ensure_bytes(&g_cache.d_payload, &g_cache.payload_bytes, psize + 64);
-        if (!rc && cudaMemcpyAsync(g_cache.d_payload, ip + offset, psize, cudaMemcpyDefault,
-                                   st) != cudaSuccess)
-          rc = MGB_CUDA_ERROR;
-      }
-      if (!rc)
-        rc = mgb_decompress_lowlevel(plan, g_cache.d_payload, hsize, leb, ltol, h.s,
-                                     h.norm, d_dst, st);
-      if (owned)
-        mgb_plan_destroy(plan);
-      if (rc)
-        break;
-    }
-    if (d_dst != final_dst || !contiguous) {
-      if (contiguous) {
-        if (cudaMemcpyAsync(final_dst, d_dst, raw_bytes, cudaMemcpyDefault, st) != cudaSuccess)
-          rc = MGB_CUDA_ERROR;
-      } else {
-        rc = copy_subdomain(pt, ndim, h.shape, tsize, id, obuf, d_dst, false, st);
-      }
-    }
-    if (cudaStreamSynchronize(st) != cudaSuccess)
-      rc = MGB_CUDA_ERROR;
-    offset += psize;
-  }
+  DecompressJob j;
+  j.h = &h;
+  j.pt = ds.pt;
+  j.first = 0;
+  j.count = ds.pt.count;
+  j.in = (const unsigned char *)in;
+  j.in_size = in_size;
+  j.offset = hb;
+  j.out = obuf;
+  j.local = false;
+  j.cfg = &ds.cfg;
+  j.coords = ds.nonuniform ? ds.cptr : nullptr;
+  rc = decompress_core(j);
   if (rc) {
+    cudaDeviceSynchronize();
     if (!output_pre_allocated) {
       if (in_dev)
         cudaFree(obuf);
@@ -1067,24 +1471,320 @@ static int decompress_impl(const void *in, size_t in_size, void **out,
     return rc;
   }
   *out = obuf;
-  if (ndim_out) *ndim_out = ndim;
-  if (dtype_out) *dtype_out = dtype;
+  if (ndim_out) *ndim_out = h.ndim;
+  if (dtype_out) *dtype_out = h.dtype;
   if (shape_out)
-    for (int d = 0; d < ndim; d++)
+    for (int d = 0; d < h.ndim; d++)
       shape_out[d] = h.shape[d];
   return MGB_SUCCESS;
 }
 
 extern "C" void mgb_release_cache(void) {
   std::lock_guard<std::mutex> lock(g_cache.mu);
+  cudaDeviceSynchronize();
   for (auto &kv : g_cache.plans)
     mgb_plan_destroy(kv.second);
   g_cache.plans.clear();
-  cudaFree(g_cache.d_stage);
-  cudaFree(g_cache.d_payload);
-  g_cache.d_stage = g_cache.d_payload = nullptr;
-  g_cache.stage_bytes = g_cache.payload_bytes = 0;
+  for (auto &kv : g_devres) {
+    DevRes &r = kv.second;
+    for (int k = 0; k < 2; k++) {
+      cudaFree(r.stage[k]);
+      cudaFree(r.payload[k]);
+      r.stage[k] = r.payload[k] = nullptr;
+      r.stage_bytes[k] = r.payload_bytes[k] = 0;
+    }
+    cudaFree(r.d_full);
+    r.d_full = nullptr;
+    r.full_bytes = 0;
+  }
 }
+
+// ---- one process per GPU ------------------------------------------------------------
+// The MaxDim partition along dim 0 (DomainDecomposer.hpp:124-169) spread over the
+// processes of a communicator: process r owns a contiguous block of sub-domains
+// (owned_range), `local` holds them back to back.  Exchanges: one all-reduce of the
+// {max |x|, sum x^2} pairs behind relative bounds, stream-ordered on the device (the
+// norm never visits the host before the quantizer has used it), and one all-gather
+// of the container sizes (GPUPipelines.hpp:189-193: every record is `u64 size |
+// payload`, so a process needs the bytes written before it).  The records are the
+// ones mgb_compress writes for the same domain, whatever the number of processes.
+static int compress_sharded_impl(mgb_comm *comm, int ndim, int dtype, const uint64_t *shape, double tol, double s,
+                                 int ebtype, const void *local, const mgb_config *cfg_in, void *out, uint64_t cap,
+                                 uint64_t *local_size, uint64_t *offset, uint64_t *total_size, uint64_t *all_sizes,
+                                 double *norm, uint8_t *header, uint64_t header_cap, uint64_t *header_size) {
+  int rc = check_args(ndim, dtype, shape);
+  if (rc)
+    return rc;
+  if (!local || !out || !local_size || !cfg_in)
+    return MGB_BAD_ARGUMENT;
+  std::lock_guard<std::mutex> lock(g_cache.mu);
+  mgb_config cfg = *cfg_in;
+  if (cfg.lossless != 0 && cfg.lossless != 2)
+    return MGB_FAILURE;
+  if (is_device_pointer(local)) {
+    cudaPointerAttributes a;
+    cudaPointerGetAttributes(&a, local);
+    cudaSetDevice(a.device);
+  } else if (cfg.dev_id >= 0) {
+    cudaSetDevice(cfg.dev_id);
+  }
+  const size_t tsize = dtype == MGB_F32 ? 4 : 8;
+  uint64_t nall = 0;
+  if (!mgb_checked_elems(ndim, shape, tsize, &nall))
+    return MGB_BAD_ARGUMENT;
+  CompressJob j;
+  cfg.domain_decomposition_dim = 0;
+  rc = make_partition(ndim, shape, tsize, &cfg, j.pt);
+  if (rc)
+    return rc;
+  const int rank = comm ? comm->rank : 0, nranks = comm ? comm->nranks : 1;
+  if (!j.pt.decomposed && nranks > 1)
+    return MGB_BAD_ARGUMENT;
+  j.ndim = ndim;
+  j.dtype = dtype;
+  j.shape = shape;
+  owned_range(j.pt.count, rank, nranks, &j.first, &j.count);
+  j.in = local;
+  j.local = true;
+  j.cfg = &cfg;
+  j.tol = tol;
+  j.s = s;
+  j.ebtype = ebtype;
+  j.out = (unsigned char *)out;
+  j.out_dev = is_device_pointer(out);
+  j.cap = cap;
+  j.offset = 0;
+  j.comm = comm;
+  rc = compress_core(j);
+  if (rc)
+    return rc;
+  *local_size = j.offset;
+  mgb_header h;
+  header_from(ndim, dtype, shape, tol, s, ebtype, j.norm, nullptr, &cfg, j.pt, h);
+  std::vector<uint8_t> hdr = mgb_encode_stream_header(h);
+  if (header_size)
+    *header_size = hdr.size();
+  if (header) {
+    if (hdr.size() > header_cap)
+      return MGB_OUTPUT_TOO_LARGE;
+    memcpy(header, hdr.data(), hdr.size());
+  }
+  if (norm)
+    *norm = j.norm;
+  // sizes of all containers -> my byte offset in the stream
+  std::vector<uint64_t> sizes(nranks, 0);
+  sizes[rank] = j.offset;
+  if (nranks > 1) {
+    DevRes *r = nullptr;
+    rc = dev_res(&r);
+    if (rc)
+      return rc;
+    const NcclApi &nc = nccl_api();
+    if (!nc.ok || !comm->nccl)
+      return MGB_FAILURE;
+    if (r->sizes_cap < (uint64_t)nranks) {
+      cudaFree(r->d_sizes);
+      r->d_sizes = nullptr;
+      MGB_CUDA_CHECK(cudaMalloc(&r->d_sizes, (8 + nranks) * sizeof(unsigned long long)));
+      r->sizes_cap = nranks;
+    }
+    r->h_pin[0] = j.offset;
+    MGB_CUDA_CHECK(cudaMemcpyAsync(r->d_sizes, r->h_pin, 8, cudaMemcpyHostToDevice, r->s_comp));
+    MGB_NCCL_CHECK(nc.AllGather(r->d_sizes, r->d_sizes + 8, 1, NCCL_UINT64, comm->nccl, r->s_comp));
+    if (nranks > 48)
+      return MGB_FAILURE;
+    MGB_CUDA_CHECK(cudaMemcpyAsync(r->h_pin + 8, r->d_sizes + 8, nranks * 8, cudaMemcpyDeviceToHost, r->s_comp));
+    MGB_CUDA_CHECK(cudaStreamSynchronize(r->s_comp));
+    for (int k = 0; k < nranks; k++)
+      sizes[k] = r->h_pin[8 + k];
+  }
+  uint64_t off = hdr.size(), tot = hdr.size();
+  for (int k = 0; k < nranks; k++) {
+    if (k < rank)
+      off += sizes[k];
+    tot += sizes[k];
+    if (all_sizes)
+      all_sizes[k] = sizes[k];
+  }
+  if (offset)
+    *offset = off;
+  if (total_size)
+    *total_size = tot;
+  return MGB_SUCCESS;
+}
+
+// Inverse: `header` = the stream's preamble + metadata (host), `records` = this
+// process's records (host or device), `local_out` = its sub-domains back to back.
+// No exchange is needed: every process decodes what it owns.
+static int decompress_sharded_impl(mgb_comm *comm, const uint8_t *header, uint64_t header_size, const void *records,
+                                   uint64_t records_size, void *local_out, const mgb_config *cfg_in) {
+  if (!header || !records || !local_out)
+    return MGB_BAD_ARGUMENT;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return MGB_BACKEND_NOT_AVAILABLE;
+  }
+  std::lock_guard<std::mutex> lock(g_cache.mu);
+  if (is_device_pointer(local_out)) {
+    cudaPointerAttributes a;
+    cudaPointerGetAttributes(&a, local_out);
+    cudaSetDevice(a.device);
+  } else if (cfg_in && cfg_in->dev_id >= 0) {
+    cudaSetDevice(cfg_in->dev_id);
+  }
+  mgb_header h;
+  uint64_t hb = 0;
+  int rc = mgb_parse_stream_header(header, header_size, h, hb);
+  if (rc)
+    return rc;
+  DecodeSetup ds;
+  rc = decode_setup(h, cfg_in, ds);
+  if (rc)
+    return rc;
+  const int rank = comm ? comm->rank : 0, nranks = comm ? comm->nranks : 1;
+  if (nranks > 1 && (!ds.pt.decomposed || ds.pt.dim != 0))
+    return MGB_BAD_ARGUMENT;
+  DecompressJob j;
+  j.h = &h;
+  j.pt = ds.pt;
+  owned_range(ds.pt.count, rank, nranks, &j.first, &j.count);
+  j.in = (const unsigned char *)records;
+  j.in_size = records_size;
+  j.offset = 0;
+  j.out = (unsigned char *)local_out;
+  j.local = true;
+  j.cfg = &ds.cfg;
+  j.coords = ds.nonuniform ? ds.cptr : nullptr;
+  rc = decompress_core(j);
+  if (rc)
+    cudaDeviceSynchronize();
+  return rc;
+}
+
+// offsets / sizes of the records of a stream in host memory (walks the u64 chain)
+static int stream_records_impl(const void *stream, uint64_t size, uint64_t *offsets, uint64_t *sizes, uint64_t cap,
+                               uint64_t *count) {
+  if (!stream || !count)
+    return MGB_BAD_ARGUMENT;
+  mgb_header h;
+  uint64_t hb = 0;
+  int rc = read_header(stream, size, h, hb);
+  if (rc)
+    return rc;
+  DecodeSetup ds;
+  rc = decode_setup(h, nullptr, ds);
+  if (rc)
+    return rc;
+  *count = ds.pt.count;
+  const bool dev = is_device_pointer(stream);
+  uint64_t off = hb;
+  for (uint64_t k = 0; k < ds.pt.count; k++) {
+    if (off + 8 > size)
+      return MGB_BAD_STREAM;
+    uint64_t ps = 0;
+    if (dev)
+      MGB_CUDA_CHECK(cudaMemcpy(&ps, (const unsigned char *)stream + off, 8, cudaMemcpyDeviceToHost));
+    else
+      memcpy(&ps, (const unsigned char *)stream + off, 8);
+    if (ps > size - off - 8)
+      return MGB_BAD_STREAM;
+    if (k < cap) {
+      if (offsets)
+        offsets[k] = off;
+      if (sizes)
+        sizes[k] = 8 + ps;
+    }
+    off += 8 + ps;
+  }
+  return MGB_SUCCESS;
+}
+
+static int comm_unique_id_impl(uint8_t *id128) {
+  const NcclApi &nc = nccl_api();
+  if (!nc.ok || !id128)
+    return nc.ok ? MGB_BAD_ARGUMENT : MGB_BACKEND_NOT_AVAILABLE;
+  mgb_nccl_uid u;
+  MGB_NCCL_CHECK(nc.GetUniqueId(&u));
+  memcpy(id128, u.internal, 128);
+  return MGB_SUCCESS;
+}
+static int comm_init_rank_impl(const uint8_t *id128, int nranks, int rank, mgb_comm **out) {
+  if (!out || nranks < 1 || rank < 0 || rank >= nranks)
+    return MGB_BAD_ARGUMENT;
+  mgb_comm *c = new mgb_comm();
+  c->rank = rank;
+  c->nranks = nranks;
+  if (nranks > 1) {
+    const NcclApi &nc = nccl_api();
+    if (!nc.ok || !id128) {
+      delete c;
+      return nc.ok ? MGB_BAD_ARGUMENT : MGB_BACKEND_NOT_AVAILABLE;
+    }
+    mgb_nccl_uid u;
+    memcpy(u.internal, id128, 128);
+    int e = nc.CommInitRank(&c->nccl, nranks, u, rank);
+    if (e != 0) {
+      fprintf(stderr, "mgard_b200: ncclCommInitRank failed: %s\n", nc.GetErrorString ? nc.GetErrorString(e) : "?");
+      delete c;
+      return MGB_FAILURE;
+    }
+    c->owned = true;
+  }
+  *out = c;
+  return MGB_SUCCESS;
+}
+
+extern "C" int mgb_comm_unique_id(uint8_t *id128) { MGB_NOEXCEPT_CALL(comm_unique_id_impl(id128)); }
+extern "C" int mgb_comm_init_rank(const uint8_t *id128, int nranks, int rank, mgb_comm **comm) {
+  MGB_NOEXCEPT_CALL(comm_init_rank_impl(id128, nranks, rank, comm));
+}
+extern "C" int mgb_comm_from_nccl(void *nccl_comm, int nranks, int rank, mgb_comm **comm) {
+  if (!comm || !nccl_comm || nranks < 1 || rank < 0 || rank >= nranks)
+    return MGB_BAD_ARGUMENT;
+  mgb_comm *c = new (std::nothrow) mgb_comm();
+  if (!c)
+    return MGB_FAILURE;
+  c->nccl = nccl_comm;
+  c->rank = rank;
+  c->nranks = nranks;
+  c->owned = false;
+  *comm = c;
+  return MGB_SUCCESS;
+}
+extern "C" void mgb_comm_destroy(mgb_comm *comm) {
+  if (!comm)
+    return;
+  if (comm->owned && comm->nccl && nccl_api().ok)
+    nccl_api().CommDestroy(comm->nccl);
+  delete comm;
+}
+extern "C" int mgb_comm_rank(const mgb_comm *comm) { return comm ? comm->rank : 0; }
+extern "C" int mgb_comm_size(const mgb_comm *comm) { return comm ? comm->nranks : 1; }
+extern "C" int mgb_owned_subdomains(const mgb_comm *comm, uint64_t num_subdomains, uint64_t *first, uint64_t *count) {
+  if (!first || !count)
+    return MGB_BAD_ARGUMENT;
+  owned_range(num_subdomains, comm ? comm->rank : 0, comm ? comm->nranks : 1, first, count);
+  return MGB_SUCCESS;
+}
+extern "C" int mgb_compress_sharded(mgb_comm *comm, int ndim, int dtype, const uint64_t *shape, double tol, double s,
+                                    int ebtype, const void *local, const mgb_config *cfg, void *out, uint64_t cap,
+                                    uint64_t *local_size, uint64_t *offset, uint64_t *total_size,
+                                    uint64_t *all_sizes, double *norm, uint8_t *header, uint64_t header_cap,
+                                    uint64_t *header_size) {
+  MGB_NOEXCEPT_CALL(compress_sharded_impl(comm, ndim, dtype, shape, tol, s, ebtype, local, cfg, out, cap, local_size,
+                                          offset, total_size, all_sizes, norm, header, header_cap, header_size));
+}
+extern "C" int mgb_decompress_sharded(mgb_comm *comm, const uint8_t *header, uint64_t header_size,
+                                      const void *records, uint64_t records_size, void *local_out,
+                                      const mgb_config *cfg) {
+  MGB_NOEXCEPT_CALL(decompress_sharded_impl(comm, header, header_size, records, records_size, local_out, cfg));
+}
+extern "C" int mgb_stream_records(const void *stream, uint64_t size, uint64_t *offsets, uint64_t *sizes,
+                                  uint64_t cap, uint64_t *count) {
+  MGB_NOEXCEPT_CALL(stream_records_impl(stream, size, offsets, sizes, cap, count));
+}
+
 
 static int compress_subdomains_impl(int ndim, int dtype, const uint64_t *shape,
                                        double tol, double s, int ebtype, double norm,
@@ -1101,20 +1801,33 @@ static int compress_subdomains_impl(int ndim, int dtype, const uint64_t *shape,
   uint64_t nall = 0;
   if (!mgb_checked_elems(ndim, shape, tsize, &nall))
     return MGB_BAD_ARGUMENT;
-  Partition pt;
-  rc = make_partition(ndim, shape, tsize, cfg_in, pt);
+  CompressJob j;
+  rc = make_partition(ndim, shape, tsize, cfg_in, j.pt);
   if (rc)
     return rc;
-  if (!pt.decomposed || pt.dim != 0 || first + count > pt.count)
+  if (!j.pt.decomposed || j.pt.dim != 0 || first + count > j.pt.count)
     return MGB_BAD_ARGUMENT;
-  double ltol = local_abs_tol(dtype, ebtype, norm, tol, s, pt.count);
-  uint64_t offset = 0;
-  double nrm = norm;
-  rc = compress_records(ndim, dtype, shape, pt, ltol, s, MGB_ABS, &nrm, d_in_first, true,
-                        first, count, nullptr, cfg_in, d_out, true, cap, &offset, 0);
+  j.ndim = ndim;
+  j.dtype = dtype;
+  j.shape = shape;
+  j.first = first;
+  j.count = count;
+  j.in = d_in_first;
+  j.local = true;
+  j.cfg = cfg_in;
+  j.tol = tol;
+  j.s = s;
+  j.ebtype = ebtype;
+  j.norm_given = true;
+  j.norm = norm;
+  j.out = d_out;
+  j.out_dev = true;
+  j.cap = cap;
+  j.offset = 0;
+  rc = compress_core(j);
   if (rc)
     return rc;
-  *size = offset;
+  *size = j.offset;
   return MGB_SUCCESS;
 }
 

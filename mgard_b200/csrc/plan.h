@@ -156,6 +156,9 @@ struct mgb_zstd_fns {
 };
 const mgb_zstd_fns &mgb_zstd();
 
+// quantize.cu: scratch of the two-stage norm reduction (2 doubles per block + result)
+#define MGB_NORM_PART_DOUBLES (2 * 148 * 8 + 2)
+
 // plan.cu
 int mgb_plan_ensure_workspace(mgb_plan *p);
 uint64_t mgb_level_elems(const mgb_plan *p, int l);

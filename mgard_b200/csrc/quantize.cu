@@ -866,20 +866,29 @@ int mgb_prepare_quantizers(mgb_plan *plan, int ebtype, double tol, double s, int
 
 // max |x| and sum x^2 of n elements into d_red[0..1] (doubles), asynchronously:
 // two-stage deterministic reduction (norm_partial_kernel / norm_final_kernel)
-int mgb_norm_async(mgb_plan *plan, const void *d_in, uint64_t n, double *d_red, cudaStream_t st) {
+int mgb_norm_raw(int dtype, const void *d_in, uint64_t n, double *d_part, double *d_red, cudaStream_t st) {
+  // d_part: MGB_NORM_PART_DOUBLES doubles of scratch
   const int nblocks = 148 * 8;
-  if (!plan->d_norm_tmp)
-    MGB_CUDA_CHECK(cudaMalloc(&plan->d_norm_tmp, (2 * nblocks + 2) * sizeof(double)));
-  double *part = (double *)plan->d_norm_tmp;
-  if (plan->dtype == MGB_F32)
+  if (dtype == MGB_F32)
     MGB_LAUNCH(MGB_K_NORM, st,
-               (norm_partial_kernel<float><<<nblocks, 256, 0, st>>>((const float *)d_in, (i64)n, part)));
+               (norm_partial_kernel<float><<<nblocks, 256, 0, st>>>((const float *)d_in, (i64)n, d_part)));
   else
     MGB_LAUNCH(MGB_K_NORM, st,
-               (norm_partial_kernel<double><<<nblocks, 256, 0, st>>>((const double *)d_in, (i64)n, part)));
-  MGB_LAUNCH(MGB_K_NORM, st, (norm_final_kernel<<<1, 32, 0, st>>>(part, nblocks, d_red)));
+               (norm_partial_kernel<double><<<nblocks, 256, 0, st>>>((const double *)d_in, (i64)n, d_part)));
+  MGB_LAUNCH(MGB_K_NORM, st, (norm_final_kernel<<<1, 32, 0, st>>>(d_part, nblocks, d_red)));
   MGB_CUDA_CHECK(cudaGetLastError());
   return MGB_SUCCESS;
+}
+// {max, sum} pairs of several sub-domains -> one pair (fixed order: deterministic)
+int mgb_norm_combine(const double *d_pairs, int count, double *d_red, cudaStream_t st) {
+  MGB_LAUNCH(MGB_K_NORM, st, (norm_final_kernel<<<1, 32, 0, st>>>(d_pairs, count, d_red)));
+  MGB_CUDA_CHECK(cudaGetLastError());
+  return MGB_SUCCESS;
+}
+int mgb_norm_async(mgb_plan *plan, const void *d_in, uint64_t n, double *d_red, cudaStream_t st) {
+  if (!plan->d_norm_tmp)
+    MGB_CUDA_CHECK(cudaMalloc(&plan->d_norm_tmp, MGB_NORM_PART_DOUBLES * sizeof(double)));
+  return mgb_norm_raw(plan->dtype, d_in, n, (double *)plan->d_norm_tmp, d_red, st);
 }
 
 // Outliers are appended with atomics, so their order depends on scheduling.

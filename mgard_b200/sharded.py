@@ -20,6 +20,13 @@ decodable by mgard_x::decompress.
 
 `local_compress` is injectable so that the host-side logic can be exercised on
 CPU with the gloo backend (tests/test_sharded_gloo.py).
+
+On CUDA tensors the work is done by the C entry points mgb_compress_sharded /
+mgb_decompress_sharded (include/mgard_b200.h) over the library's own NCCL
+communicator (class Comm): the norm all-reduce runs stream-ordered on the device
+and the quantizer reads it from device memory - no host round trip, one
+synchronisation per record.  Sub-domain ownership: mgb_owned_subdomains ==
+owned_range below.
 """
 import ctypes as C
 import math
@@ -110,6 +117,9 @@ def compress_sharded(local, global_shape, tol, s, mode, decomposition_size, conf
     is_torch = type(local).__module__.startswith("torch")
     device = local.device if is_torch and local.is_cuda else None
     np_dtype = np.float32 if ("float32" in str(local.dtype)) else np.float64
+    if local_compress is None and device is not None:
+        return compress_sharded_native(local, global_shape, tol, s, mode, decomposition_size, config=config,
+                                       comm=default_comm(dist, group))
     if local_compress is None:
         local_compress, local_partials, write_header = _cuda_backend(config)
     norm = 1.0
@@ -182,3 +192,124 @@ def _cuda_backend(config):
         return buf[:sz.value].tobytes()
 
     return compress, partials, header
+
+
+# ---------------------------------------------------------------------------------
+# native path: mgb_compress_sharded / mgb_decompress_sharded over the library's NCCL
+# communicator
+# ---------------------------------------------------------------------------------
+class Comm:
+    """mgb_comm: rank / size + an NCCL communicator created by the library
+    (ncclGetUniqueId on rank 0, shipped through torch.distributed, ncclCommInitRank)."""
+
+    def __init__(self, dist=None, group=None):
+        import torch
+        from . import _lib
+        L = _lib.lib()
+        self.rank, self.size = 0, 1
+        if dist is not None and dist.is_initialized():
+            self.rank, self.size = dist.get_rank(group), dist.get_world_size(group)
+        uid = (C.c_uint8 * 128)()
+        if self.size > 1:
+            if self.rank == 0:
+                _lib.check(L.mgb_comm_unique_id(uid), "ncclGetUniqueId")
+            box = [bytes(uid)]
+            dist.broadcast_object_list(box, src=0, group=group)
+            uid = (C.c_uint8 * 128).from_buffer_copy(box[0])
+        h = C.c_void_p(0)
+        _lib.check(L.mgb_comm_init_rank(uid, self.size, self.rank, C.byref(h)), "ncclCommInitRank")
+        self._h = h
+
+    def close(self):
+        from . import _lib
+        if getattr(self, "_h", None):
+            _lib.lib().mgb_comm_destroy(self._h)
+            self._h = None
+
+    def owned(self, num_subdomains):
+        from . import _lib
+        f, c = C.c_uint64(0), C.c_uint64(0)
+        _lib.check(_lib.lib().mgb_owned_subdomains(self._h, num_subdomains, C.byref(f), C.byref(c)), "owned")
+        return f.value, c.value
+
+
+_DEFAULT_COMM = {}
+
+
+def default_comm(dist=None, group=None):
+    key = id(group)
+    c = _DEFAULT_COMM.get(key)
+    if c is None:
+        c = _DEFAULT_COMM[key] = Comm(dist, group)
+    return c
+
+
+def compress_sharded_native(local, global_shape, tol, s, mode, decomposition_size, config=None, comm=None,
+                            out=None):
+    """mgb_compress_sharded.  local / out: torch CUDA tensors or numpy (host) arrays."""
+    from . import _lib
+    from .api import Config, _shape_arg, _dtype_code, _is_torch
+    L = _lib.lib()
+    cfg = (config or Config())._c()
+    cfg.domain_decomposition_dim = 0
+    cfg.domain_decomposition_size = int(decomposition_size)
+    tdev = _is_torch(local)
+    if tdev:
+        import torch
+        local = local.contiguous()
+        npdt = np.float32 if local.dtype == torch.float32 else np.float64
+        in_ptr, nbytes = local.data_ptr(), local.numel() * local.element_size()
+        if local.is_cuda:
+            cfg.dev_id = local.device.index or 0
+    else:
+        local = np.ascontiguousarray(local)
+        npdt = local.dtype
+        in_ptr, nbytes = local.ctypes.data, local.nbytes
+    ext = partition(int(global_shape[0]), int(decomposition_size))
+    nranks = comm.size if comm else 1
+    if out is None:
+        cap = nbytes + len(ext) * (8 * (128 + cfg.huff_dict_size) + (1 << 20))
+        if tdev:
+            import torch
+            out = torch.empty(cap, dtype=torch.uint8, device=local.device)
+        else:
+            out = np.empty(cap, dtype=np.uint8)
+    if _is_torch(out):
+        out_ptr, cap = out.data_ptr(), out.numel()
+    else:
+        out_ptr, cap = out.ctypes.data, out.size
+    lsz, off, tot, nrm, hsz = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_double(0), C.c_uint64(0)
+    sizes = (C.c_uint64 * nranks)()
+    hdr = (C.c_uint8 * (1 << 16))()
+    _lib.check(L.mgb_compress_sharded(comm._h if comm else None, len(global_shape), int(_dtype_code(npdt)),
+                                      _shape_arg(global_shape), float(tol), float(s), int(mode), in_ptr,
+                                      C.byref(cfg), out_ptr, cap, C.byref(lsz), C.byref(off), C.byref(tot), sizes,
+                                      C.byref(nrm), hdr, len(hdr), C.byref(hsz)), "compress_sharded")
+    first, count = owned_range(len(ext), comm.rank if comm else 0, nranks)
+    return dict(records=out[:lsz.value], sizes=[int(x) for x in sizes], offset=off.value - hsz.value,
+                stream_offset=off.value, total=tot.value, header=bytes(hdr[:hsz.value]), norm=nrm.value,
+                first=first, count=count)
+
+
+def decompress_sharded_native(header, records, out, config=None, comm=None):
+    """mgb_decompress_sharded: `records` (this rank's, host or device) -> `out` (this
+    rank's sub-domains back to back, host or device)."""
+    from . import _lib
+    from .api import Config, _is_torch
+    L = _lib.lib()
+    cfg = (config or Config())._c()
+    if _is_torch(records):
+        rp, rn = records.data_ptr(), records.numel()
+    else:
+        records = np.ascontiguousarray(records, dtype=np.uint8)
+        rp, rn = records.ctypes.data, records.size
+    if _is_torch(out):
+        op = out.data_ptr()
+        if out.is_cuda:
+            cfg.dev_id = out.device.index or 0
+    else:
+        op = out.ctypes.data
+    hb = (C.c_uint8 * len(header)).from_buffer_copy(header)
+    _lib.check(L.mgb_decompress_sharded(comm._h if comm else None, hb, len(header), rp, rn, op, C.byref(cfg)),
+               "decompress_sharded")
+    return out

@@ -1393,8 +1393,8 @@ int ensure_huff_workspace(mgb_plan *p) {
   MGB_CUDA_CHECK(cudaMalloc(&p->d_decodebook, (128 + dict) * sizeof(u64)));
   MGB_CUDA_CHECK(cudaMalloc(&p->d_chunk_bits, nchunk * sizeof(u64)));
   MGB_CUDA_CHECK(cudaMalloc(&p->d_chunk_woff, (nchunk + 1) * sizeof(u64)));
-  MGB_CUDA_CHECK(cudaMalloc(&p->d_scalars, 16 * sizeof(u64)));
-  MGB_CUDA_CHECK(cudaMemset(p->d_scalars, 0, 16 * sizeof(u64)));
+  MGB_CUDA_CHECK(cudaMalloc(&p->d_scalars, 24 * sizeof(u64))); // [16..17]: grid barrier of the outlier sort
+  MGB_CUDA_CHECK(cudaMemset(p->d_scalars, 0, 24 * sizeof(u64)));
   size_t cbw = npow2 * sizeof(u64) + (size_t)dict * (9 * 4 + 8) + 256;
   MGB_CUDA_CHECK(cudaMalloc(&p->d_cbwork, cbw));
   MGB_CUDA_CHECK(cudaMallocHost(&p->h_pinned, 16 * sizeof(u64)));

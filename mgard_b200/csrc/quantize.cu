@@ -893,15 +893,64 @@ int mgb_norm_async(mgb_plan *plan, const void *d_in, uint64_t n, double *d_red, 
 
 // Outliers are appended with atomics, so their order depends on scheduling.
 // Sorting them by index (what the reference's SERIAL adapter produces) makes the
-// stream deterministic and byte-identical to the reference's.  One block,
-// bitonic sort in place; lists longer than 65536 entries (or that do not fit
-// their power-of-two padding) are left as they are.
+// stream deterministic and byte-identical to the reference's.  Bitonic sort of the
+// (index, value) pairs, in place: ST_BLOCKS blocks, each owning tiles of ST_TILE pairs.
+// Compare-exchange distances below a tile run out of shared memory; the larger ones go
+// through global memory with a grid barrier in between (the blocks are few enough to be
+// co-resident; a block that has to wait for an SM only delays the others).  Lists longer
+// than 65536 entries (or that do not fit their power-of-two padding) are left as they are.
 namespace {
+constexpr unsigned ST_TILE = 4096, ST_BLOCKS = 16, ST_MAX = ST_TILE * ST_BLOCKS;
+
+// bar[0] arrivals, bar[1] generation (zero-initialised words of the plan)
+__device__ __forceinline__ void sort_grid_barrier(unsigned *bar, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned *gen = &bar[1];
+    const unsigned my = *gen;
+    __threadfence();
+    if (atomicAdd(&bar[0], 1u) == nblocks - 1) {
+      bar[0] = 0;
+      __threadfence();
+      atomicAdd(&bar[1], 1u);
+    } else {
+      while (*gen == my)
+        __nanosleep(64);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// distances j = jmax .. 1 of stage k on the tile in shared memory
+__device__ __forceinline__ void sort_tile_passes(uint64_t *sk, long long *sv, unsigned base, unsigned k,
+                                                 unsigned jmax) {
+  for (unsigned j = jmax; j > 0; j >>= 1) {
+    for (unsigned t = threadIdx.x; t < ST_TILE / 2; t += blockDim.x) {
+      // t-th pair (lo, lo ^ j) of the tile
+      const unsigned lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+      const uint64_t a = sk[lo], b = sk[hi];
+      const bool up = ((base + lo) & k) == 0;
+      if ((a > b) == up) {
+        sk[lo] = b;
+        sk[hi] = a;
+        const long long va = sv[lo];
+        sv[lo] = sv[hi];
+        sv[hi] = va;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(1024)
-sort_outliers_kernel(const unsigned long long *__restrict__ ocount, uint64_t *__restrict__ oidx,
-                     long long *__restrict__ oval, unsigned long long cap) {
+sort_outliers_kernel(const unsigned long long *__restrict__ ocount, uint64_t *oidx,
+                     long long *oval, unsigned long long cap, unsigned *bar) {
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  uint64_t *sk = reinterpret_cast<uint64_t *>(sort_smem);
+  long long *sv = reinterpret_cast<long long *>(sort_smem) + ST_TILE;
   const unsigned long long n64 = *ocount;
-  if (n64 < 2 || n64 > 65536 || n64 > cap)
+  if (n64 < 2 || n64 > ST_MAX || n64 > cap)
     return;
   const unsigned n = (unsigned)n64;
   unsigned np = 1;
@@ -909,35 +958,82 @@ sort_outliers_kernel(const unsigned long long *__restrict__ ocount, uint64_t *__
     np <<= 1;
   if (np > cap)
     return;
-  for (unsigned i = n + threadIdx.x; i < np; i += blockDim.x)
-    oidx[i] = ~0ull; // padding sorts to the end
-  __syncthreads();
-  for (unsigned k = 2; k <= np; k <<= 1) {
-    for (unsigned j = k >> 1; j > 0; j >>= 1) {
-      for (unsigned i = threadIdx.x; i < np; i += blockDim.x) {
-        const unsigned ixj = i ^ j;
-        if (ixj > i) {
-          const uint64_t a = oidx[i], b = oidx[ixj];
-          const bool up = (i & k) == 0;
-          if ((a > b) == up) {
-            oidx[i] = b;
-            oidx[ixj] = a;
-            const long long va = oval[i];
-            oval[i] = oval[ixj];
-            oval[ixj] = va;
-          }
+  // every decision below depends on n only, so all blocks take the same barriers
+  const unsigned ntiles = (np + ST_TILE - 1) / ST_TILE; // power of two (or 1)
+  const unsigned tile = blockIdx.x;
+  const bool active = tile < ntiles;
+  const unsigned base = tile * ST_TILE;
+  const unsigned tlen = min(ST_TILE, np); // np < ST_TILE: one short tile
+  // stages up to the tile size, entirely in shared memory
+  if (active) {
+    for (unsigned i = threadIdx.x; i < ST_TILE; i += blockDim.x) {
+      const unsigned g = base + i;
+      const bool real = i < tlen && g < n;
+      sk[i] = real ? __ldcg(oidx + g) : ~0ull; // padding sorts to the end
+      sv[i] = real ? __ldcg(oval + g) : 0;
+    }
+    __syncthreads();
+    for (unsigned k = 2; k <= tlen; k <<= 1)
+      sort_tile_passes(sk, sv, base, k, k >> 1);
+    if (ntiles > 1)
+      for (unsigned i = threadIdx.x; i < ST_TILE; i += blockDim.x) {
+        __stcg(oidx + base + i, sk[i]);
+        __stcg(oval + base + i, sv[i]);
+      }
+  }
+  // larger stages: distances >= ST_TILE through global memory, the rest per tile
+  for (unsigned k = 2 * ST_TILE; k <= np && ntiles > 1; k <<= 1) {
+    for (unsigned j = k >> 1; j >= ST_TILE; j >>= 1) {
+      __threadfence();
+      sort_grid_barrier(bar, gridDim.x);
+      // np / 2 pairs over all threads of the grid
+      for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < np / 2; t += gridDim.x * blockDim.x) {
+        const unsigned lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+        // other blocks wrote these in the previous pass: read them from the L2
+        const uint64_t a = __ldcg(oidx + lo), b = __ldcg(oidx + hi);
+        const bool up = (lo & k) == 0;
+        if ((a > b) == up) {
+          __stcg(oidx + lo, b);
+          __stcg(oidx + hi, a);
+          const long long va = __ldcg(oval + lo), vb = __ldcg(oval + hi);
+          __stcg(oval + lo, vb);
+          __stcg(oval + hi, va);
         }
       }
+    }
+    __threadfence();
+    sort_grid_barrier(bar, gridDim.x);
+    if (active) {
+      for (unsigned i = threadIdx.x; i < ST_TILE; i += blockDim.x) {
+        sk[i] = __ldcg(oidx + base + i);
+        sv[i] = __ldcg(oval + base + i);
+      }
       __syncthreads();
+      sort_tile_passes(sk, sv, base, k, ST_TILE >> 1);
+      for (unsigned i = threadIdx.x; i < ST_TILE; i += blockDim.x) {
+        __stcg(oidx + base + i, sk[i]);
+        __stcg(oval + base + i, sv[i]);
+      }
     }
   }
+  if (ntiles == 1 && active)
+    for (unsigned i = threadIdx.x; i < tlen; i += blockDim.x) {
+      __stcg(oidx + i, sk[i]);
+      __stcg(oval + i, sv[i]);
+    }
 }
 } // namespace
 
+// d_ocount: the plan's scalar block (d_scalars: [0] the count, [16..17] the barrier words)
 int mgb_sort_outliers(const unsigned long long *d_ocount, uint64_t *d_oidx, int64_t *d_oval,
                       uint64_t cap, cudaStream_t st) {
+  static bool configured[64] = {};
+  if (mgb_first_use_on_device(configured))
+    MGB_CUDA_CHECK(cudaFuncSetAttribute(sort_outliers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(ST_TILE * 16)));
   MGB_LAUNCH(MGB_K_OUTLIER_RESTORE, st,
-             (sort_outliers_kernel<<<1, 1024, 0, st>>>(d_ocount, d_oidx, (long long *)d_oval, cap)));
+             (sort_outliers_kernel<<<ST_BLOCKS, 1024, ST_TILE * 16, st>>>(
+                 d_ocount, d_oidx, (long long *)d_oval, cap, (unsigned *)(d_ocount + 16))));
   MGB_CUDA_CHECK(cudaGetLastError());
   return MGB_SUCCESS;
 }

@@ -27,6 +27,7 @@
 
 #include "coef3d.cuh"
 #include "masstrans3d.cuh"
+#include "thomas_tma.cuh"
 #include "restore3d.cuh"
 #include "plan.h"
 
@@ -926,6 +927,29 @@ void axpy(T *acc, const T *w, i64 n, int subtract, cudaStream_t st) {
   MGB_LAUNCH(MGB_K_AXPY, st, (axpy_kernel<T><<<blocks, 256, 0, st>>>(acc, w, n, subtract)));
 }
 
+// contiguous axis through the TMA-staged kernel (thomas_tma.cuh): G lines per warp, as
+// many warps as shared memory holds
+template <typename T, int G>
+bool launch_thomas_tma(T *w, int n, i64 lines, int nwarp, const T *fw, const T *am, const T *bm, T *acc,
+                       int mode, cudaStream_t st) {
+  static bool configured[64] = {};
+  if (mgb_first_use_on_device(configured)) {
+    if (cudaFuncSetAttribute(thomas_tma_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             227 * 1024) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+  }
+  const size_t stage = (((size_t)G * n * sizeof(T)) + 127) & ~(size_t)127;
+  const size_t smem = (((size_t)nwarp * 8 + 127) & ~(size_t)127) + (size_t)nwarp * stage;
+  const i64 ngroups = (lines + G - 1) / G;
+  const unsigned blocks = (unsigned)std::min<i64>(148, (ngroups + nwarp - 1) / nwarp);
+  MGB_LAUNCH(MGB_K_THOMAS_CONTIG, st,
+             (thomas_tma_kernel<T, G><<<blocks, nwarp * 32, smem, st>>>(w, n, (long long)lines, fw, am, bm, acc,
+                                                                      mode)));
+  return cudaGetLastError() == cudaSuccess;
+}
+
 template <typename T, int W>
 bool launch_thomas_smem(T *w, int n, i64 inner, i64 outer, const T *fw, const T *am,
                         const T *bm, T *acc, int mode, cudaStream_t st) {
@@ -1087,7 +1111,56 @@ void thomas_all(mgb_plan *p, int l, T *w, T *acc, int mode, cudaStream_t st) {
                                                                   accp, md)));
       continue;
     }
-    // contiguous axis: whole lines staged in shared memory when they fit
+    // contiguous axis: whole lines staged in shared memory by the TMA engine when the
+    // natural pitch is free of bank conflicts (odd n: the 2^k + 1 sizes)
+    if (getenv("MGB_NO_TMA_THOMAS") == nullptr) {
+      const int banks = sizeof(T) == 4 ? 32 : 16;
+      int gcd = n, b = banks;
+      while (b) {
+        const int t = gcd % b;
+        gcd = b;
+        b = t;
+      }
+      // lines per warp (G) against warps per block (S): a warp instruction costs the same
+      // with 4 or 32 active lanes, so small G multiplies the issue work; large G leaves
+      // few lines in flight to hide the dependent chain.  Crude cycle model per SM:
+      const size_t avail = 220 * 1024;
+      int bestG = 0, bestS = 0;
+      double best_cost = 0;
+      const int Gs[4] = {32, 16, 8, 4};
+      const double chain = sizeof(T) == 4 ? 40.0 : 110.0, instr = sizeof(T) == 4 ? 22.0 : 40.0;
+      for (int k = 0; k < 4; k++) {
+        const size_t stage = (((size_t)Gs[k] * n * sizeof(T)) + 127) & ~(size_t)127;
+        int S = (int)std::min<size_t>(32, (avail - 256) / stage);
+        // no more warps than there are groups for one block per SM
+        const i64 ngroups = (outer + Gs[k] - 1) / Gs[k];
+        S = (int)std::min<i64>(S, std::max<i64>(1, (ngroups + 147) / 148));
+        if (S < 1)
+          continue;
+        const double groups_sm = (double)ngroups / 148.0;
+        const double t_chain = std::ceil(groups_sm / S) * n * chain;
+        const double t_issue = groups_sm * n * instr / 4.0;
+        const double cost = std::max(t_chain, t_issue);
+        if (!bestG || cost < best_cost) {
+          bestG = Gs[k];
+          bestS = S;
+          best_cost = cost;
+        }
+      }
+      bool ok = false;
+      if (gcd <= 2 && bestG) {
+        if (bestG == 32)
+          ok = launch_thomas_tma<T, 32>(w, n, outer, bestS, fw, am, bm, accp, md, st);
+        else if (bestG == 16)
+          ok = launch_thomas_tma<T, 16>(w, n, outer, bestS, fw, am, bm, accp, md, st);
+        else if (bestG == 8)
+          ok = launch_thomas_tma<T, 8>(w, n, outer, bestS, fw, am, bm, accp, md, st);
+        else
+          ok = launch_thomas_tma<T, 4>(w, n, outer, bestS, fw, am, bm, accp, md, st);
+      }
+      if (ok)
+        continue;
+    }
     int bestW = 0;
     i64 best = 0;
     const int Ws[3] = {32, 16, 8};

@@ -109,7 +109,9 @@ def test_serial_and_block_kernels_agree_at_scale(env):
             assert float((back - u).abs().max()) <= tol * norm
             sym, oi, ov = p.huffman_decompress(payload, u.numel())
             outs.append((payload.clone(), back.clone(), sym.clone()))
-        assert torch.equal(outs[0][0], outs[1][0])
+        # more than 65536 outliers keep their append order:
+        # the blocks are compared field by field with the outlier list as a set
+        parsed_equal(outs[0][0].cpu().numpy().tobytes(), outs[1][0].cpu().numpy().tobytes())
         assert torch.equal(outs[0][1], outs[1][1])
         assert torch.equal(outs[0][2], outs[1][2])
         # cross: bytes written by one family decoded by the other

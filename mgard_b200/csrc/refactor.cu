@@ -941,7 +941,8 @@ bool launch_thomas_tma(T *w, int n, i64 lines, int nwarp, const T *fw, const T *
     }
   }
   const size_t stage = (((size_t)G * n * sizeof(T)) + 127) & ~(size_t)127;
-  const size_t smem = (((size_t)nwarp * 8 + 127) & ~(size_t)127) + (size_t)nwarp * stage;
+  const size_t tables = (((size_t)4 * n * sizeof(T)) + 127) & ~(size_t)127;
+  const size_t smem = (((size_t)nwarp * 8 + 127) & ~(size_t)127) + tables + (size_t)nwarp * stage;
   const i64 ngroups = (lines + G - 1) / G;
   const unsigned blocks = (unsigned)std::min<i64>(148, (ngroups + nwarp - 1) / nwarp);
   MGB_LAUNCH(MGB_K_THOMAS_CONTIG, st,
@@ -1131,7 +1132,10 @@ void thomas_all(mgb_plan *p, int l, T *w, T *acc, int mode, cudaStream_t st) {
       const double chain = sizeof(T) == 4 ? 40.0 : 110.0, instr = sizeof(T) == 4 ? 22.0 : 40.0;
       for (int k = 0; k < 4; k++) {
         const size_t stage = (((size_t)Gs[k] * n * sizeof(T)) + 127) & ~(size_t)127;
-        int S = (int)std::min<size_t>(32, (avail - 256) / stage);
+        const size_t tables = (((size_t)4 * n * sizeof(T)) + 127) & ~(size_t)127;
+        if (avail < 256 + tables + stage)
+          continue;
+        int S = (int)std::min<size_t>(32, (avail - 256 - tables) / stage);
         // no more warps than there are groups for one block per SM
         const i64 ngroups = (outer + Gs[k] - 1) / Gs[k];
         S = (int)std::min<i64>(S, std::max<i64>(1, (ngroups + 147) / 148));

@@ -47,8 +47,10 @@ enum { MGB_REL = 0, MGB_ABS = 1 };
 
 #define MGB_MAX_DIMS 5
 
-/* Subset of mgard_x::Config (include/mgard-x/Config/Config.h:10-42) that the
- * hot path reads; defaults as src/mgard-x/Config/Config.cpp:14-43. */
+/* The fields of mgard_x::Config (include/mgard-x/Config/Config.h:10-42) that change what
+ * the hot path computes; defaults as src/mgard-x/Config/Config.cpp:14-43.  The remaining
+ * fields of the reference's struct (logging, prefetch, CPU threading, MDR / ZFP / LZ4
+ * knobs ...) are carried by the C++ mirror include/mgard_b200/compress_x.hpp. */
 typedef struct mgb_config {
   int32_t dev_id;          /* Config::dev_id */
   int32_t huff_dict_size;  /* 8192 */
@@ -60,7 +62,16 @@ typedef struct mgb_config {
   int32_t zstd_compress_level; /* Config::zstd_compress_level, 3 */
   int32_t reorder;             /* Config::reorder: 1 = quantised symbols in level-linearised order (LevelLinearizer) */
   int32_t decomposition;       /* mgard_x::decomposition_type: 0 MultiDim (default), 1 SingleDim (D <= 3) */
-  int32_t reserved;
+  int32_t domain_decomposition; /* mgard_x::domain_decomposition_type: 0 MaxDim (default), 1 Block, 2 Variable */
+  uint64_t max_larget_level;   /* Config::max_larget_level: l_target = min(levels - 1, this); UINT64_MAX = no limit
+                                  (Hierarchy.hpp:195-217).  Not stored in the stream: the decompressing call must
+                                  pass the same value, as with the reference */
+  uint64_t block_size;         /* Config::block_size (256): edge of the Block sub-domains */
+  const uint64_t *domain_decomposition_sizes; /* Config::domain_decomposition_sizes (Variable): extents along */
+  uint64_t num_domain_decomposition_sizes;    /* domain_decomposition_dim; not stored in the stream either */
+  uint64_t max_memory_footprint; /* Config::max_memory_footprint: bytes the working set of one sub-domain may
+                                    take when the MaxDim / Block size is chosen automatically; UINT64_MAX: what
+                                    the device has free */
 } mgb_config;
 
 void mgb_config_default(mgb_config *cfg);

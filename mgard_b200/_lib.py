@@ -20,14 +20,19 @@ STATUS_NAMES = {
 
 
 class MgbConfig(C.Structure):
-    """mgb_config (subset of mgard_x::Config, include/mgard-x/Config/Config.h:10-42)."""
+    """mgb_config: the fields of mgard_x::Config (include/mgard-x/Config/Config.h:10-42) that change
+    what the hot path computes."""
     _fields_ = [
         ("dev_id", C.c_int32), ("huff_dict_size", C.c_int32),
         ("huff_block_size", C.c_int32), ("domain_decomposition_dim", C.c_int32),
         ("domain_decomposition_size", C.c_uint64),
         ("normalize_coordinates", C.c_int32), ("lossless", C.c_int32),
         ("zstd_compress_level", C.c_int32), ("reorder", C.c_int32),
-        ("decomposition", C.c_int32), ("reserved", C.c_int32),
+        ("decomposition", C.c_int32), ("domain_decomposition", C.c_int32),
+        ("max_larget_level", C.c_uint64), ("block_size", C.c_uint64),
+        ("domain_decomposition_sizes", C.POINTER(C.c_uint64)),
+        ("num_domain_decomposition_sizes", C.c_uint64),
+        ("max_memory_footprint", C.c_uint64),
     ]
 
 

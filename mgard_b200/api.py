@@ -53,20 +53,53 @@ class lossless_type(enum.IntEnum):
     CPU_Lossless = 3  # not built
 
 
+class domain_decomposition_type(enum.IntEnum):
+    MaxDim = 0
+    Block = 1
+    Variable = 2
+
+
 class Config:
-    """mgard_x::Config defaults (src/mgard-x/Config/Config.cpp:14-43)."""
+    """mgard_x::Config with its defaults (include/mgard-x/Config/Config.h:10-42,
+    src/mgard-x/Config/Config.cpp:14-43).  Fields that select code this engine does
+    not have (ZFP, Hybrid decomposition, LZ4, CPU threading, MDR knobs) are carried for
+    source compatibility and checked by `_c()`: unsupported choices raise, they are
+    never ignored."""
+
+    UNLIMITED = (1 << 64) - 1
 
     def __init__(self):
+        self.dev_type = "AUTO"
         self.dev_id = 0
+        self.compressor = "MGARD"
+        self.domain_decomposition = domain_decomposition_type.MaxDim
+        self.decomposition = decomposition_type.MultiDim
+        self.estimate_outlier_ratio = 1.0
         self.huff_dict_size = 8192
         self.huff_block_size = 1024 * 20
-        self.domain_decomposition_dim = -1
-        self.domain_decomposition_size = 0
+        self.lz4_block_size = 1 << 15
+        self.zstd_compress_level = 3
         self.normalize_coordinates = True
         self.lossless = lossless_type.Huffman
-        self.zstd_compress_level = 3
         self.reorder = 0
-        self.decomposition = decomposition_type.MultiDim
+        self.log_level = 0
+        self.prefetch = False
+        self.auto_pin_host_buffers = True
+        self.max_larget_level = Config.UNLIMITED
+        self.max_memory_footprint = Config.UNLIMITED
+        self.total_num_bitplanes = 32
+        self.block_size = 256
+        self.domain_decomposition_dim = -1   # -1: the largest dimension (MaxDim)
+        self.domain_decomposition_sizes = []
+        self.mdr_adaptive_resolution = False
+        self.adjust_shape = False
+        self.compress_with_dryrun = False
+        self.num_local_refactoring_level = 1
+        self.auto_cache_release = False
+        self.cpu_mode = "INTER_BLOCK"
+        # mgard_b200 extension: planes per MaxDim sub-domain (0: from free device memory,
+        # DomainDecomposer.hpp:199-230)
+        self.domain_decomposition_size = 0
 
     def _c(self):
         c = MgbConfig()
@@ -81,6 +114,16 @@ class Config:
         c.zstd_compress_level = int(self.zstd_compress_level)
         c.reorder = int(self.reorder)
         c.decomposition = int(self.decomposition)
+        if self.compressor != "MGARD" or self.dev_type not in ("AUTO", "CUDA") or not self.normalize_coordinates:
+            raise MgardError(_lib.FAILURE, "Config: compressor / device / coordinate choice not supported")
+        c.domain_decomposition = int(self.domain_decomposition)
+        c.max_larget_level = int(self.max_larget_level)
+        c.block_size = int(self.block_size)
+        c.max_memory_footprint = int(self.max_memory_footprint)
+        if self.domain_decomposition_sizes:
+            self._sizes = (C.c_uint64 * len(self.domain_decomposition_sizes))(*self.domain_decomposition_sizes)
+            c.domain_decomposition_sizes = self._sizes
+            c.num_domain_decomposition_sizes = len(self.domain_decomposition_sizes)
         return c
 
 
@@ -150,6 +193,35 @@ def release_cache():
     _lib.lib().mgb_release_cache()
 
 
+def adjust_shape(shape, config=None):
+    """Config::adjust_shape (CompressionHighLevel/ShapeAdjustment.hpp:43-84): the prime
+    factors of the largest extent, largest first, are handed to whichever dimension is
+    currently the smallest; the data are reinterpreted with that shape (same bytes)."""
+    shape = [int(n) for n in shape]
+    steps = 1
+    variable = config is not None and int(config.domain_decomposition) == 2
+    if variable:
+        steps = shape[0] // int(config.domain_decomposition_sizes[0])
+        shape[0] = int(config.domain_decomposition_sizes[0])
+    big = max(range(len(shape)), key=lambda d: (shape[d], -d))
+    n, factors, z = shape[big], [], 2
+    while z * z <= n:
+        if n % z == 0:
+            factors.append(z)
+            n //= z
+        else:
+            z += 1
+    if n > 1:
+        factors.append(n)
+    shape[big] = 1
+    for f in reversed(factors):
+        small = min(range(len(shape)), key=lambda d: (shape[d], d))
+        shape[small] *= f
+    if variable:
+        shape[0] *= steps
+    return tuple(shape)
+
+
 def compress(data, tol, s, mode, coords=None, config=None, out=None):
     """mgard_x::compress(D, dtype, shape, tol, s, mode, original_data,
     compressed_data, compressed_size[, coords][, config], output_pre_allocated).
@@ -182,6 +254,10 @@ def compress(data, tol, s, mode, coords=None, config=None, out=None):
         npdt = data.dtype
         shape = data.shape
         in_ptr = data.ctypes.data
+    if config is not None and config.adjust_shape:
+        if coords is not None:
+            raise MgardError(_lib.BAD_ARGUMENT, "adjust_shape with explicit coordinates")
+        shape = adjust_shape(shape, config)
     dt = _dtype_code(npdt)
     carr = _coords_arg(coords, npdt, keep)
     outp = C.c_void_p(0)

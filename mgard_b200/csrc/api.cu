@@ -304,6 +304,7 @@ namespace {
 
 struct CacheKey {
   int ndim, dtype, dict, chunk;
+  uint64_t max_level;
   uint64_t shape[MGB_MAX_DIMS];
   int dev;
   bool operator<(const CacheKey &o) const {
@@ -369,6 +370,7 @@ int get_plan(int ndim, int dtype, const uint64_t *shape, const void *const *coor
   k.dtype = dtype;
   k.dict = cfg->huff_dict_size;
   k.chunk = cfg->huff_block_size;
+  k.max_level = cfg->max_larget_level;
   cudaGetDevice(&k.dev);
   for (int d = 0; d < ndim; d++)
     k.shape[d] = shape[d];
@@ -397,24 +399,66 @@ bool is_device_pointer(const void *p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// DomainDecomposer (DomainDecomposer/DomainDecomposer.hpp:90-169,199-262): MaxDim and
+// Variable cut one dimension (equal extents + a remainder / caller-given extents), Block
+// cuts every dimension into edges of `size`; sub-domain ids run row-major over the cuts.
 struct Partition {
   bool decomposed = false;
+  int method = 1; // pb::DomainDecomposition::Method: 1 MAX_DIMENSION, 2 BLOCK, 3 VARIABLE
   int dim = 0;
-  uint64_t size = 0; // chunk size along dim
+  uint64_t size = 0; // extent of a full cut
   uint64_t count = 1;
+  uint64_t cuts[MGB_MAX_DIMS] = {1, 1, 1, 1, 1}; // sub-domains per dimension
+  std::vector<uint64_t> var_sizes, var_offsets;  // Variable
+  // sub-domains are consecutive runs of planes of dim 0 (copied / used in place as one range)
+  bool slabs() const { return !decomposed || (method != 2 && dim == 0); }
 };
 
-void subdomain_shape(const Partition &pt, int ndim, const uint64_t *shape, uint64_t id,
-                     uint64_t *out) {
-  for (int d = 0; d < ndim; d++)
-    out[d] = shape[d];
+// extent and first index of sub-domain `id` per dimension
+void subdomain_box(const Partition &pt, int ndim, const uint64_t *shape, uint64_t id,
+                   uint64_t *ext, uint64_t *off) {
+  for (int d = 0; d < ndim; d++) {
+    ext[d] = shape[d];
+    off[d] = 0;
+  }
   if (!pt.decomposed)
     return;
-  // DomainDecomposer.hpp:131-144
-  if (id < shape[pt.dim] / pt.size)
-    out[pt.dim] = pt.size;
-  else
-    out[pt.dim] = shape[pt.dim] % pt.size;
+  if (pt.method == 3) {
+    ext[pt.dim] = pt.var_sizes[id];
+    off[pt.dim] = pt.var_offsets[id];
+  } else if (pt.method == 2) {
+    // DomainDecomposer.hpp:104-111,146-157
+    for (int d = ndim - 1; d >= 0; d--) {
+      const uint64_t k = id % pt.cuts[d];
+      id /= pt.cuts[d];
+      ext[d] = k < shape[d] / pt.size ? pt.size : shape[d] % pt.size;
+      off[d] = k * pt.size;
+    }
+  } else {
+    // DomainDecomposer.hpp:131-144
+    ext[pt.dim] = id < shape[pt.dim] / pt.size ? pt.size : shape[pt.dim] % pt.size;
+    off[pt.dim] = id * pt.size;
+  }
+}
+// slab partitions: first plane (index along dim 0) of sub-domain `id`
+uint64_t subdomain_first_plane(const Partition &pt, uint64_t id) {
+  if (!pt.decomposed)
+    return 0;
+  return pt.method == 3 ? pt.var_offsets[id] : id * pt.size;
+}
+// coordinates of sub-domain `id`: every cut dimension starts at its own offset
+// (DomainDecomposer.hpp:258-300)
+void subdomain_coords(const Partition &pt, int ndim, const uint64_t *shape, size_t tsize, uint64_t id,
+                      const void *const *coords, const void **out) {
+  uint64_t ext[MGB_MAX_DIMS], off[MGB_MAX_DIMS];
+  subdomain_box(pt, ndim, shape, id, ext, off);
+  for (int d = 0; d < ndim; d++)
+    out[d] = (const unsigned char *)coords[d] + off[d] * tsize;
+}
+void subdomain_shape(const Partition &pt, int ndim, const uint64_t *shape, uint64_t id,
+                     uint64_t *out) {
+  uint64_t off[MGB_MAX_DIMS];
+  subdomain_box(pt, ndim, shape, id, out, off);
 }
 
 // copy sub-domain `id` between the full array and a dense buffer
@@ -422,15 +466,52 @@ void subdomain_shape(const Partition &pt, int ndim, const uint64_t *shape, uint6
 int copy_subdomain(const Partition &pt, int ndim, const uint64_t *shape, size_t tsize,
                    uint64_t id, const void *full, void *dense, bool to_dense,
                    cudaStream_t st) {
-  uint64_t sub[MGB_MAX_DIMS];
-  subdomain_shape(pt, ndim, shape, id, sub);
+  uint64_t sub[MGB_MAX_DIMS], off[MGB_MAX_DIMS];
+  subdomain_box(pt, ndim, shape, id, sub, off);
+  if (pt.decomposed && pt.method == 2) {
+    // a D-dimensional box: one pitched copy per index of the dimensions above the last two
+    uint64_t fstride[MGB_MAX_DIMS], dstride[MGB_MAX_DIMS];
+    uint64_t a = 1, b = 1;
+    for (int d = ndim - 1; d >= 0; d--) {
+      fstride[d] = a;
+      dstride[d] = b;
+      a *= shape[d];
+      b *= sub[d];
+    }
+    const int nlead = ndim >= 2 ? ndim - 2 : 0;
+    uint64_t lead = 1;
+    for (int d = 0; d < nlead; d++)
+      lead *= sub[d];
+    const size_t width = sub[ndim - 1] * tsize;
+    const uint64_t rows = ndim >= 2 ? sub[ndim - 2] : 1;
+    const size_t fpitch = shape[ndim - 1] * tsize;
+    for (uint64_t k = 0; k < lead; k++) {
+      uint64_t rem = k, fo = 0, dn = 0;
+      for (int d = nlead - 1; d >= 0; d--) {
+        const uint64_t i = rem % sub[d];
+        rem /= sub[d];
+        fo += (off[d] + i) * fstride[d];
+        dn += i * dstride[d];
+      }
+      if (ndim >= 2)
+        fo += off[ndim - 2] * fstride[ndim - 2];
+      fo += off[ndim - 1];
+      const unsigned char *fp = (const unsigned char *)full + fo * tsize;
+      unsigned char *dp = (unsigned char *)dense + dn * tsize;
+      if (to_dense)
+        MGB_CUDA_CHECK(cudaMemcpy2DAsync(dp, width, fp, fpitch, width, rows, cudaMemcpyDefault, st));
+      else
+        MGB_CUDA_CHECK(cudaMemcpy2DAsync((void *)fp, fpitch, dp, width, width, rows, cudaMemcpyDefault, st));
+    }
+    return MGB_SUCCESS;
+  }
   uint64_t inner = 1, outer = 1;
   const int dim = pt.decomposed ? pt.dim : 0;
   for (int d = dim + 1; d < ndim; d++)
     inner *= shape[d];
   for (int d = 0; d < dim; d++)
     outer *= shape[d];
-  uint64_t start = pt.decomposed ? id * pt.size : 0;
+  uint64_t start = pt.decomposed ? off[dim] : 0;
   size_t width = sub[dim] * inner * tsize;
   size_t fpitch = shape[dim] * inner * tsize;
   const unsigned char *fp = (const unsigned char *)full + start * inner * tsize;
@@ -460,6 +541,63 @@ double local_abs_tol(int dtype, int ebtype, double norm, double tol, double s,
 int make_partition(int ndim, const uint64_t *shape, size_t tsize, const mgb_config *cfg,
                    Partition &pt) {
   pt = Partition();
+  size_t free_b = 0, total_b = 0;
+  auto budget = [&]() {
+    if (!total_b)
+      cudaMemGetInfo(&free_b, &total_b);
+    return std::min<double>(0.85 * (double)free_b, (double)cfg->max_memory_footprint);
+  };
+  // working set of one sub-domain of `elems` nodes (input copy, coefficients, symbols,
+  // coarse boxes and correction workspaces, payload)
+  auto footprint = [&](double elems) { return elems * (tsize * 5.5 + 2.0) + (double)(64ull << 20); };
+  if (cfg->domain_decomposition == 2) {
+    // Variable: caller-given extents along domain_decomposition_dim (DomainDecomposer.hpp:335-348)
+    const int dim = cfg->domain_decomposition_dim < 0 ? 0 : cfg->domain_decomposition_dim;
+    if (dim >= ndim || !cfg->domain_decomposition_sizes || !cfg->num_domain_decomposition_sizes)
+      return MGB_BAD_ARGUMENT;
+    uint64_t sum = 0;
+    for (uint64_t k = 0; k < cfg->num_domain_decomposition_sizes; k++) {
+      const uint64_t e = cfg->domain_decomposition_sizes[k];
+      if (e < 3)
+        return MGB_BAD_ARGUMENT; // Hierarchy.hpp:748-756
+      pt.var_offsets.push_back(sum);
+      pt.var_sizes.push_back(e);
+      sum += e;
+    }
+    if (sum != shape[dim])
+      return MGB_BAD_ARGUMENT;
+    pt.decomposed = true;
+    pt.method = 3;
+    pt.dim = dim;
+    pt.size = pt.var_sizes[0];
+    pt.count = pt.var_sizes.size();
+    pt.cuts[dim] = pt.count;
+    return MGB_SUCCESS;
+  }
+  if (cfg->domain_decomposition == 1) {
+    // Block: every dimension in edges of block_size, halved until one block fits
+    // (DomainDecomposer.hpp:232-256,329-334); always decomposed, even into one block
+    uint64_t S = cfg->block_size;
+    if (S < 3)
+      return MGB_BAD_ARGUMENT;
+    while (footprint(std::pow((double)S, ndim)) > budget() && S > 3)
+      S = (S - 1) / 2 + 1;
+    pt.decomposed = true;
+    pt.method = 2;
+    pt.dim = 0;
+    pt.size = S;
+    pt.count = 1;
+    for (int d = 0; d < ndim; d++) {
+      pt.cuts[d] = (shape[d] - 1) / S + 1;
+      pt.count *= pt.cuts[d];
+      const uint64_t left = shape[d] % S;
+      if (left != 0 && left < 3)
+        return MGB_BAD_ARGUMENT; // Hierarchy.hpp:748-756
+    }
+    return MGB_SUCCESS;
+  }
+  if (cfg->domain_decomposition != 0)
+    return MGB_BAD_ARGUMENT;
   uint64_t S = cfg->domain_decomposition_size;
   int dim = cfg->domain_decomposition_dim;
   if (dim < 0) {
@@ -474,19 +612,14 @@ int make_partition(int ndim, const uint64_t *shape, size_t tsize, const mgb_conf
   if (dim >= ndim)
     return MGB_BAD_ARGUMENT;
   if (S == 0) {
-    // fit the working set into free device memory by halving the chunk
-    // (DomainDecomposer.hpp:208-230)
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
+    // fit the working set into (free device memory, max_memory_footprint) by halving
+    // the chunk (DomainDecomposer.hpp:208-230)
     uint64_t rest = 1;
     for (int d = 0; d < ndim; d++)
       if (d != dim)
         rest *= shape[d];
     uint64_t chunk = shape[dim];
-    auto footprint = [&](uint64_t c) {
-      return (double)c * rest * (tsize * 5.5 + 2.0) + (double)(64ull << 20);
-    };
-    while (footprint(chunk) > 0.85 * (double)free_b && chunk > 3)
+    while (footprint((double)chunk * rest) > budget() && chunk > 3)
       chunk = (chunk - 1) / 2 + 1;
     S = chunk;
   }
@@ -498,9 +631,11 @@ int make_partition(int ndim, const uint64_t *shape, size_t tsize, const mgb_conf
     return MGB_SUCCESS;
   }
   pt.decomposed = true;
+  pt.method = 1;
   pt.dim = dim;
   pt.size = S;
   pt.count = (shape[dim] - 1) / S + 1;
+  pt.cuts[dim] = pt.count;
   uint64_t left = shape[dim] % S;
   if (S < 3 || (left != 0 && left < 3))
     return MGB_BAD_ARGUMENT; // Hierarchy.hpp:748-756
@@ -519,6 +654,7 @@ void header_from(int ndim, int dtype, const uint64_t *shape, double tol, double 
   h.s = s;
   h.norm = norm;
   h.decomposed = pt.decomposed;
+  h.dd_method = pt.method;
   h.dd_dim = pt.dim;
   h.dd_size = pt.size;
   h.dict_size = cfg->huff_dict_size;
@@ -698,12 +834,8 @@ int subdomain_plan(const CompressJob &j, uint64_t id, PlanGuard &g, uint64_t *su
   subdomain_shape(j.pt, j.ndim, j.shape, id, sub);
   const size_t tsize = j.dtype == MGB_F32 ? 4 : 8;
   const void *subcoords[MGB_MAX_DIMS];
-  if (j.coords) {
-    for (int d = 0; d < j.ndim; d++)
-      subcoords[d] = j.coords[d];
-    if (j.pt.decomposed)
-      subcoords[j.pt.dim] = (const unsigned char *)j.coords[j.pt.dim] + id * j.pt.size * tsize;
-  }
+  if (j.coords)
+    subdomain_coords(j.pt, j.ndim, j.shape, tsize, id, j.coords, subcoords);
   return get_plan(j.ndim, j.dtype, sub, j.coords ? subcoords : nullptr, j.cfg, &g.p, &g.owned);
 }
 
@@ -711,8 +843,8 @@ int subdomain_plan(const CompressJob &j, uint64_t id, PlanGuard &g, uint64_t *su
 const unsigned char *subdomain_ptr(const CompressJob &j, uint64_t id, uint64_t plane) {
   if (!j.pt.decomposed)
     return (const unsigned char *)j.in;
-  const uint64_t rel = j.local ? id - j.first : id;
-  return (const unsigned char *)j.in + rel * j.pt.size * plane;
+  const uint64_t p0 = subdomain_first_plane(j.pt, id) - (j.local ? subdomain_first_plane(j.pt, j.first) : 0);
+  return (const unsigned char *)j.in + p0 * plane;
 }
 
 // dense copy of sub-domain `id` into device memory `dst` on stream st
@@ -737,7 +869,7 @@ int compress_core(CompressJob &j) {
   const mgb_config *cfg = j.cfg;
   const size_t tsize = j.dtype == MGB_F32 ? 4 : 8;
   const bool in_dev = is_device_pointer(j.in);
-  const bool contiguous = !j.pt.decomposed || j.pt.dim == 0;
+  const bool contiguous = j.pt.slabs();
   if (j.local && !contiguous)
     return MGB_BAD_ARGUMENT;
   uint64_t plane = tsize; // bytes of one index along dim 0
@@ -1177,7 +1309,7 @@ int decompress_core(DecompressJob &j) {
   const int ndim = h.ndim, dtype = h.dtype;
   const size_t tsize = dtype == MGB_F32 ? 4 : 8;
   const bool in_dev = is_device_pointer(j.in), out_dev = is_device_pointer(j.out);
-  const bool contiguous = !j.pt.decomposed || j.pt.dim == 0;
+  const bool contiguous = j.pt.slabs();
   if (j.local && !contiguous)
     return MGB_BAD_ARGUMENT;
   double ltol = h.tol;
@@ -1240,8 +1372,8 @@ int decompress_core(DecompressJob &j) {
         return rc;
     }
     // dense device destination of this sub-domain
-    const uint64_t rel = j.local ? k : id;
-    unsigned char *final_dst = j.out + (j.pt.decomposed && contiguous ? rel * j.pt.size * plane : 0);
+    const uint64_t p0 = subdomain_first_plane(j.pt, id) - (j.local ? subdomain_first_plane(j.pt, j.first) : 0);
+    unsigned char *final_dst = j.out + (j.pt.decomposed && contiguous ? p0 * plane : 0);
     unsigned char *d_dst;
     const bool direct_out = out_dev && contiguous;
     if (direct_out) {
@@ -1259,12 +1391,8 @@ int decompress_core(DecompressJob &j) {
     } else {
       PlanGuard g;
       const void *subcoords[MGB_MAX_DIMS];
-      if (j.coords) {
-        for (int d = 0; d < ndim; d++)
-          subcoords[d] = j.coords[d];
-        if (j.pt.decomposed)
-          subcoords[j.pt.dim] = (const unsigned char *)j.coords[j.pt.dim] + id * j.pt.size * tsize;
-      }
+      if (j.coords)
+        subdomain_coords(j.pt, ndim, h.shape, tsize, id, j.coords, subcoords);
       rc = get_plan(ndim, dtype, sub, j.coords ? subcoords : nullptr, j.cfg, &g.p, &g.owned);
       if (rc)
         return rc;
@@ -1374,14 +1502,48 @@ int decode_setup(const mgb_header &h, const mgb_config *cfg_in, DecodeSetup &d) 
   // a header that passes its CRC can still announce an absurd shape
   if (!mgb_checked_elems(ndim, h.shape, tsize, &d.N))
     return MGB_BAD_STREAM;
+  // not in the stream: the caller repeats them (as with the reference)
+  if (cfg_in)
+    d.cfg.max_larget_level = cfg_in->max_larget_level;
   d.pt.decomposed = h.decomposed;
+  d.pt.method = h.dd_method;
   d.pt.dim = (int)h.dd_dim;
   d.pt.size = h.dd_size;
   d.pt.count = 1;
-  if (d.pt.decomposed) {
+  if (d.pt.decomposed && d.pt.method == 3) {
+    // Variable: the extents come from the caller's Config (CompressionHighLevel.hpp:485-493)
+    if (!cfg_in || !cfg_in->domain_decomposition_sizes || !cfg_in->num_domain_decomposition_sizes ||
+        d.pt.dim >= ndim)
+      return MGB_BAD_ARGUMENT;
+    uint64_t sum = 0;
+    for (uint64_t k = 0; k < cfg_in->num_domain_decomposition_sizes; k++) {
+      const uint64_t e = cfg_in->domain_decomposition_sizes[k];
+      if (e < 3 || e > h.shape[d.pt.dim])
+        return MGB_BAD_ARGUMENT;
+      d.pt.var_offsets.push_back(sum);
+      d.pt.var_sizes.push_back(e);
+      sum += e;
+    }
+    if (sum != h.shape[d.pt.dim])
+      return MGB_BAD_ARGUMENT;
+    d.pt.count = d.pt.var_sizes.size();
+    d.pt.cuts[d.pt.dim] = d.pt.count;
+  } else if (d.pt.decomposed && d.pt.method == 2) {
+    if (d.pt.size < 3)
+      return MGB_BAD_STREAM;
+    d.pt.dim = 0;
+    for (int k = 0; k < ndim; k++) {
+      d.pt.cuts[k] = (h.shape[k] - 1) / d.pt.size + 1;
+      const uint64_t left = h.shape[k] % d.pt.size;
+      if ((left != 0 && left < 3) || d.pt.count > (1ull << 40) / d.pt.cuts[k])
+        return MGB_BAD_STREAM;
+      d.pt.count *= d.pt.cuts[k];
+    }
+  } else if (d.pt.decomposed) {
     if (d.pt.dim >= ndim || d.pt.size < 3 || d.pt.size >= h.shape[d.pt.dim])
       return MGB_BAD_STREAM;
     d.pt.count = (h.shape[d.pt.dim] - 1) / d.pt.size + 1;
+    d.pt.cuts[d.pt.dim] = d.pt.count;
   }
   // CompressionHighLevel.hpp:456-464: coordinates go through float
   d.nonuniform = !h.coords.empty();
@@ -1534,6 +1696,8 @@ static int compress_sharded_impl(mgb_comm *comm, int ndim, int dtype, const uint
     return MGB_BAD_ARGUMENT;
   CompressJob j;
   cfg.domain_decomposition_dim = 0;
+  if (cfg.domain_decomposition == 1)
+    return MGB_BAD_ARGUMENT; // Block sub-domains are not runs of planes
   rc = make_partition(ndim, shape, tsize, &cfg, j.pt);
   if (rc)
     return rc;
@@ -1643,7 +1807,7 @@ static int decompress_sharded_impl(mgb_comm *comm, const uint8_t *header, uint64
   if (rc)
     return rc;
   const int rank = comm ? comm->rank : 0, nranks = comm ? comm->nranks : 1;
-  if (nranks > 1 && (!ds.pt.decomposed || ds.pt.dim != 0))
+  if (nranks > 1 && (!ds.pt.decomposed || !ds.pt.slabs()))
     return MGB_BAD_ARGUMENT;
   DecompressJob j;
   j.h = &h;
@@ -1805,7 +1969,7 @@ static int compress_subdomains_impl(int ndim, int dtype, const uint64_t *shape,
   rc = make_partition(ndim, shape, tsize, cfg_in, j.pt);
   if (rc)
     return rc;
-  if (!j.pt.decomposed || j.pt.dim != 0 || first + count > j.pt.count)
+  if (!j.pt.decomposed || !j.pt.slabs() || first + count > j.pt.count)
     return MGB_BAD_ARGUMENT;
   j.ndim = ndim;
   j.dtype = dtype;

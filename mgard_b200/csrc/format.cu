@@ -241,7 +241,7 @@ std::vector<uint8_t> mgb_encode_stream_header(const mgb_header &h) {
     f_double(err, 4, h.norm);
   f_double(err, 5, h.tol);
   std::string dd;
-  f_varint(dd, 1, h.decomposed ? 1 : 0); // MAX_DIMENSION
+  f_varint(dd, 1, h.decomposed ? h.dd_method : 0); // NOOP_METHOD / MAX_DIMENSION / BLOCK / VARIABLE
   f_varint(dd, 2, h.dd_dim);
   f_varint(dd, 3, h.dd_size);
   std::string fd;
@@ -403,9 +403,10 @@ int mgb_parse_stream_header(const uint8_t *data, size_t size, mgb_header &h,
         if (f2 == 2 && w2 == 0) h.dd_dim = v2;
         if (f2 == 3 && w2 == 0) h.dd_size = v2;
       }
-      if (method != 0 && method != 1)
-        return MGB_BAD_STREAM; // BLOCK / VARIABLE partitions not supported
-      h.decomposed = method == 1;
+      if (method < 0 || method > 3)
+        return MGB_BAD_STREAM;
+      h.decomposed = method != 0;
+      h.dd_method = method ? method : 1;
       break;
     }
     case 8:

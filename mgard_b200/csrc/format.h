@@ -13,6 +13,7 @@ struct mgb_header {
   double tol = 0, s = 0, norm = 0;
   bool decomposed = false;
   uint64_t dd_dim = 0, dd_size = 0;
+  int dd_method = 1; // pb::DomainDecomposition::Method when decomposed: 1 MAX_DIMENSION, 2 BLOCK, 3 VARIABLE
   int dict_size = 8192, block_size = 20480;
   int lossless = 0; // 0: X_HUFFMAN, 2: X_HUFFMAN_ZSTD (mgard_x::lossless_type values)
   // 0: MGARD-X stream (Metadata.cpp); 1: MGARD-CPU stream (src/format.cpp:110-140:

@@ -277,6 +277,12 @@ extern "C" void mgb_config_default(mgb_config *cfg) {
   cfg->zstd_compress_level = 3;
   cfg->reorder = 0;
   cfg->decomposition = 0;
+  cfg->domain_decomposition = 0;
+  cfg->max_larget_level = ~0ull;
+  cfg->block_size = 256;
+  cfg->domain_decomposition_sizes = nullptr;
+  cfg->num_domain_decomposition_sizes = 0;
+  cfg->max_memory_footprint = ~0ull;
 }
 
 static int plan_create_impl(int ndim, const uint64_t *shape, int dtype,
@@ -332,6 +338,9 @@ static int plan_create_impl(int ndim, const uint64_t *shape, int dtype,
     nlevel = std::min(nlevel, per_dim[d].size());
   }
   p->L = (int)nlevel - 1;
+  // Config::max_larget_level (Hierarchy.hpp:216-217): fewer levels, a larger coarsest mesh
+  if ((uint64_t)p->L > p->cfg.max_larget_level)
+    p->L = (int)p->cfg.max_larget_level;
   if (p->L >= MGB_MAX_LEVELS) {
     delete p;
     return MGB_BAD_ARGUMENT;

@@ -1009,7 +1009,7 @@ def _f_msg(field, body):
 
 def encode_header(shape, dtype, ebtype, tol, s, norm, coords=None,
                   decomposed=False, dd_dim=0, dd_size=0, dict_size=8192,
-                  chunk_size=20480, backend=3, lossless=3, reorder=0):
+                  chunk_size=20480, backend=3, lossless=3, reorder=0, dd_method=1):
     """proto3 canonical bytes of mgard.pb.Header as MetadataBase::Serialize
     fills it (including the version-field quirk, Metadata.cpp:267-271).
     backend: Device.Backend (1 X_SERIAL, 3 X_CUDA); lossless: Encoding.Compressor."""
@@ -1035,7 +1035,8 @@ def encode_header(shape, dtype, ebtype, tol, s, norm, coords=None,
     if not decomposed:
         # DomainDecomposer.hpp:333-337: dim 0 / size shape[0] when not decomposed
         dd_dim, dd_size = 0, int(shape[0])
-    dd = (_f_varint(1, 1 if decomposed else 0) + _f_varint(2, dd_dim)
+    # DomainDecomposition.Method: 1 MAX_DIMENSION, 2 BLOCK, 3 VARIABLE (Metadata.cpp:335-354)
+    dd = (_f_varint(1, dd_method if decomposed else 0) + _f_varint(2, dd_dim)
           + _f_varint(3, dd_size))
     fd = _f_varint(2, 1)
     quant = _f_varint(1, 1) + _f_varint(3, 3)

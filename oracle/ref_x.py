@@ -34,6 +34,7 @@ class RefxArgs(C.Structure):
         ("payload_size", C.c_uint64),
         ("lossless", C.c_int32), ("zstd_level", C.c_int32),
         ("reorder", C.c_int32), ("decomposition", C.c_int32),
+        ("max_level", C.c_int32),
     ]
 
 
@@ -137,13 +138,15 @@ def recompose(v, coords=None, decomposition=0):
     return u
 
 
-def compress(u, ebtype, tol, s, coords=None, dict_size=8192, chunk_size=20480, lossless=0, reorder=0, decomposition=0):
+def compress(u, ebtype, tol, s, coords=None, dict_size=8192, chunk_size=20480, lossless=0, reorder=0, decomposition=0,
+             max_level=0):
     """Low-level Compressor::Compress staged; returns dict with payload bytes,
     norm, decomposed coefficients, quantized (dict-shifted) int64, outlier count."""
     keep = []
     v = np.array(u, copy=True, order="C")
     a = _base_args(v.shape, v.dtype, coords, dict_size, chunk_size, keep)
     a.op = OP_COMPRESS
+    a.max_level = max_level
     a.lossless = lossless
     a.reorder = reorder
     a.decomposition = decomposition
@@ -167,11 +170,12 @@ def compress(u, ebtype, tol, s, coords=None, dict_size=8192, chunk_size=20480, l
 
 
 def decompress(payload, shape, dtype, ebtype, tol, s, norm, coords=None,
-               dict_size=8192, chunk_size=20480, lossless=0, reorder=0, decomposition=0):
+               dict_size=8192, chunk_size=20480, lossless=0, reorder=0, decomposition=0, max_level=0):
     keep = []
     out = np.zeros(shape, dtype=dtype)
     a = _base_args(shape, dtype, coords, dict_size, chunk_size, keep)
     a.op = OP_DECOMPRESS
+    a.max_level = max_level
     a.lossless = lossless
     a.reorder = reorder
     a.decomposition = decomposition

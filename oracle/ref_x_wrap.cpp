@@ -54,6 +54,8 @@ static Config make_config(const refx_args *a) {
   cfg.huff_block_size = a->chunk_size;
   cfg.normalize_coordinates = true;
   cfg.log_level = log::ERR;
+  if (a->max_level > 0)
+    cfg.max_larget_level = a->max_level;
   return cfg;
 }
 

@@ -37,6 +37,7 @@ typedef struct refx_args {
   int32_t zstd_level;    /* 0: reference default (3) */
   int32_t reorder;       /* Config::reorder: 1 = level-linearised quantised order */
   int32_t decomposition; /* decomposition_type: 0 MultiDim, 1 SingleDim */
+  int32_t max_level;     /* Config::max_larget_level; <= 0: no limit */
 } refx_args;
 
 #ifdef __cplusplus

@@ -287,6 +287,20 @@ int mgb_cpu_decompose(mgb_cpu_plan *plan, const void *d_nodal, void *d_coef,
                       void *stream);
 int mgb_cpu_recompose(mgb_cpu_plan *plan, const void *d_coef, void *d_nodal,
                       void *stream);
+/* One constituent operator of the multilevel transform on every line of level `level`
+ * along user dimension `dim`, in place on a NODAL device array: ConstituentMassMatrix
+ * (include/TensorMassMatrix.tpp:15-90), ConstituentMassMatrixInverse (:123-290),
+ * ConstituentRestriction (include/TensorRestriction.tpp:24-71),
+ * ConstituentProlongationAddition (include/TensorProlongation.tpp:22-69).  The reference
+ * applies them to shuffled arrays; shuffle -> operator -> unshuffle is this call. */
+enum {
+  MGB_CPU_OP_MASS = 0,
+  MGB_CPU_OP_MASS_INVERSE = 1,
+  MGB_CPU_OP_RESTRICTION = 2,
+  MGB_CPU_OP_PROLONGATION_ADDITION = 3
+};
+int mgb_cpu_apply_operator(mgb_cpu_plan *plan, int op, int level, int dim,
+                           void *d_nodal, void *stream);
 /* TensorMultilevelCoefficientQuantizer / Dequantizer on shuffled coefficients
  * (include/TensorMultilevelCoefficientQuantizer.tpp:13-77,242-259).  quantize
  * synchronises and returns MGB_FAILURE where the reference throws

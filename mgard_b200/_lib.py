@@ -91,6 +91,7 @@ SIGNATURES = {
     "mgb_cpu_unshuffle": (_i32, [_vp, _vp, _vp, _vp]),
     "mgb_cpu_decompose": (_i32, [_vp, _vp, _vp, _vp]),
     "mgb_cpu_recompose": (_i32, [_vp, _vp, _vp, _vp]),
+    "mgb_cpu_apply_operator": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "mgb_cpu_quantize": (_i32, [_vp, _vp, _dbl, _dbl, _vp, _vp]),
     "mgb_cpu_dequantize": (_i32, [_vp, _vp, _dbl, _dbl, _vp, _vp]),
     "mgb_cpu_compress": (_i32, [_i32, _i32, _pu64, C.POINTER(_vp), _dbl, _dbl, _i32, _vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]),

@@ -95,6 +95,19 @@ class TensorMeshHierarchy:
     def unshuffle(self, u):
         return self._stage(_lib.lib().mgb_cpu_unshuffle, u).reshape(self.shape)
 
+    MASS, MASS_INVERSE, RESTRICTION, PROLONGATION_ADDITION = range(4)
+
+    def apply_operator(self, op, level, dimension, v):
+        """Constituent{MassMatrix, MassMatrixInverse, Restriction, ProlongationAddition}
+        (hierarchy, level, dimension) applied to every line of a nodal array (a copy is
+        returned): what shuffle -> operator on each line -> unshuffle gives in the
+        reference (tests/src/test_Tensor{MassMatrix,Restriction,Prolongation}.cpp)."""
+        import torch
+        out = v.contiguous().clone()
+        check(_lib.lib().mgb_cpu_apply_operator(self._h, int(op), int(level), int(dimension), out.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream), "apply_operator")
+        return out
+
     def decompose(self, v):
         """shuffle + decompose: nodal values -> shuffled multilevel coefficients."""
         return self._stage(_lib.lib().mgb_cpu_decompose, v)

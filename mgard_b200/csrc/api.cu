@@ -314,6 +314,8 @@ struct CacheKey {
 
 struct HighLevelCache {
   std::map<CacheKey, mgb_plan *> plans;
+  std::map<CacheKey, uint64_t> last_use; // call stamp of the last use (eviction order)
+  uint64_t stamp = 0;
   std::mutex mu;
 };
 HighLevelCache g_cache;
@@ -374,6 +376,7 @@ int get_plan(int ndim, int dtype, const uint64_t *shape, const void *const *coor
   cudaGetDevice(&k.dev);
   for (int d = 0; d < ndim; d++)
     k.shape[d] = shape[d];
+  g_cache.last_use[k] = g_cache.stamp;
   auto it = g_cache.plans.find(k);
   if (it != g_cache.plans.end()) {
     *plan = it->second;
@@ -388,6 +391,25 @@ int get_plan(int ndim, int dtype, const uint64_t *shape, const void *const *coor
   g_cache.plans[k] = *plan;
   *owned = false;
   return MGB_SUCCESS;
+}
+
+// The reference's CompressorCache holds one hierarchy per <D, T> and rebuilds it when
+// the shape changes; this cache keeps several shapes (the sub-domains of a decomposed
+// domain alternate between two) but not without bound: at the START of a high-level call
+// (nothing of this library is in flight then) the least recently used plans beyond
+// MAX_PLANS are destroyed together with their workspaces.
+void trim_plan_cache() {
+  constexpr size_t MAX_PLANS = 12;
+  g_cache.stamp++;
+  while (g_cache.plans.size() > MAX_PLANS) {
+    auto victim = g_cache.plans.begin();
+    for (auto it = g_cache.plans.begin(); it != g_cache.plans.end(); ++it)
+      if (g_cache.last_use[it->first] < g_cache.last_use[victim->first])
+        victim = it;
+    mgb_plan_destroy(victim->second);
+    g_cache.last_use.erase(victim->first);
+    g_cache.plans.erase(victim);
+  }
 }
 
 bool is_device_pointer(const void *p) {
@@ -1155,6 +1177,7 @@ static int compress_impl(int ndim, int dtype, const uint64_t *shape, double tol,
   if (cfg.lossless != 0 && cfg.lossless != 2)
     return MGB_FAILURE; // Huffman_LZ4 (nvcomp) / CPU_Lossless are not built
   std::lock_guard<std::mutex> lock(g_cache.mu);
+  trim_plan_cache();
   const bool in_dev = is_device_pointer(in);
   if (in_dev) {
     cudaPointerAttributes a;
@@ -1577,6 +1600,7 @@ static int decompress_impl(const void *in, size_t in_size, void **out,
     return MGB_BACKEND_NOT_AVAILABLE;
   }
   std::lock_guard<std::mutex> lock(g_cache.mu);
+  trim_plan_cache();
   const bool in_dev = is_device_pointer(in);
   if (in_dev) {
     cudaPointerAttributes a;
@@ -1647,6 +1671,7 @@ extern "C" void mgb_release_cache(void) {
   for (auto &kv : g_cache.plans)
     mgb_plan_destroy(kv.second);
   g_cache.plans.clear();
+  g_cache.last_use.clear();
   for (auto &kv : g_devres) {
     DevRes &r = kv.second;
     for (int k = 0; k < 2; k++) {
@@ -1680,6 +1705,7 @@ static int compress_sharded_impl(mgb_comm *comm, int ndim, int dtype, const uint
   if (!local || !out || !local_size || !cfg_in)
     return MGB_BAD_ARGUMENT;
   std::lock_guard<std::mutex> lock(g_cache.mu);
+  trim_plan_cache();
   mgb_config cfg = *cfg_in;
   if (cfg.lossless != 0 && cfg.lossless != 2)
     return MGB_FAILURE;
@@ -1790,6 +1816,7 @@ static int decompress_sharded_impl(mgb_comm *comm, const uint8_t *header, uint64
     return MGB_BACKEND_NOT_AVAILABLE;
   }
   std::lock_guard<std::mutex> lock(g_cache.mu);
+  trim_plan_cache();
   if (is_device_pointer(local_out)) {
     cudaPointerAttributes a;
     cudaPointerGetAttributes(&a, local_out);
@@ -1961,6 +1988,7 @@ static int compress_subdomains_impl(int ndim, int dtype, const uint64_t *shape,
   if (!d_in_first || !d_out || !size || !cfg_in)
     return MGB_BAD_ARGUMENT;
   std::lock_guard<std::mutex> lock(g_cache.mu);
+  trim_plan_cache();
   const size_t tsize = dtype == MGB_F32 ? 4 : 8;
   uint64_t nall = 0;
   if (!mgb_checked_elems(ndim, shape, tsize, &nall))

@@ -1229,6 +1229,46 @@ int huffman_zstd_decode(const uint8_t *src, size_t src_bytes, std::vector<long l
 
 } // namespace
 
+namespace {
+// One constituent operator on every line of level `level` along `dim`, on a NODAL array
+// in place (the reference applies them to a shuffled array: shuffle, operator,
+// unshuffle give the same nodal result - tests/src/test_TensorMassMatrix.cpp,
+// test_TensorRestriction.cpp, test_TensorProlongation.cpp).
+template <typename T> int apply_operator_t(mgb_cpu_plan *p, int op, int l, int d, T *v, cudaStream_t st) {
+  const T *real = reinterpret_cast<const T *>(p->d_real);
+  if (op == MGB_CPU_OP_MASS) {
+    // out of place: the nodes outside the level keep their values
+    T *tmp = reinterpret_cast<T *>(p->d_b0);
+    MGB_CUDA_CHECK(cudaMemcpyAsync(tmp, v, p->N * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    LevelArgs<T> a = level_args<T>(p, l, d, SEL_ALL);
+    a.src = v;
+    a.dst = tmp;
+    launch_level<T, OP_MASS>(a, st);
+    MGB_CUDA_CHECK(cudaMemcpyAsync(v, tmp, p->N * sizeof(T), cudaMemcpyDeviceToDevice, st));
+  } else if (op == MGB_CPU_OP_RESTRICTION) {
+    LevelArgs<T> a = level_args<T>(p, l, d, SEL_OLD);
+    a.buf = v;
+    launch_level<T, OP_RESTRICT>(a, st);
+  } else if (op == MGB_CPU_OP_PROLONGATION_ADDITION) {
+    LevelArgs<T> a = level_args<T>(p, l, d, SEL_NEW);
+    a.buf = v;
+    launch_level<T, OP_PROLONG>(a, st);
+  } else if (op == MGB_CPU_OP_MASS_INVERSE) {
+    LevelArgs<T> a = level_args<T>(p, l, d, SEL_ONE);
+    a.buf = v;
+    const DimTables<double> &t = p->tab[l][d];
+    const uint64_t blocks = (a.total + 127) / 128;
+    MGB_LAUNCH(MGB_K_THOMAS_STRIDED, st,
+               (cpu_thomas_kernel<T><<<(unsigned)blocks, 128, 0, st>>>(a, real + t.w, real + t.dv, real + t.cc)));
+  } else {
+    return MGB_BAD_ARGUMENT;
+  }
+  MGB_CUDA_CHECK(cudaGetLastError());
+  return MGB_SUCCESS;
+}
+
+} // namespace
+
 extern "C" {
 
 static int cpu_plan_create_impl(int ndim, const uint64_t *shape, int dtype, const void *const *coords,
@@ -1351,6 +1391,24 @@ int mgb_cpu_recompose(mgb_cpu_plan *p, const void *d_in, void *d_out, void *stre
                (level_map<T, OP_UNSHUFFLE>(p, (T *)d_out, (const T *)d_in, nullptr, nullptr, nullptr, 0, 0, st), recompose_nodal<T>(p, (T *)d_out, st)));
   MGB_CUDA_CHECK(cudaGetLastError());
   return MGB_SUCCESS;
+}
+
+int mgb_cpu_apply_operator(mgb_cpu_plan *p, int op, int level, int dim, void *d_nodal, void *stream) {
+  if (!p || !d_nodal || level < 0 || level > p->L || dim < 0 || dim >= p->ndim)
+    return MGB_BAD_ARGUMENT;
+  // restriction / prolongation relate level l to l - 1 (the reference constructors throw for l = 0)
+  if ((op == MGB_CPU_OP_RESTRICTION || op == MGB_CPU_OP_PROLONGATION_ADDITION) && level == 0)
+    return MGB_BAD_ARGUMENT;
+  int rc = ensure_workspace(p, false);
+  if (rc)
+    return rc;
+  const int d = dim + (CD - p->ndim); // user dimensions are right-aligned in the CD-dimensional plan
+  if ((p->flat >> d) & 1)
+    return MGB_SUCCESS; // a dimension of size 1: every operator is the identity
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->dtype == MGB_F32)
+    return apply_operator_t<float>(p, op, level, d, (float *)d_nodal, st);
+  return apply_operator_t<double>(p, op, level, d, (double *)d_nodal, st);
 }
 
 int mgb_cpu_quantize(mgb_cpu_plan *p, const void *d_coef, double s, double tol, int64_t *d_q, void *stream) {

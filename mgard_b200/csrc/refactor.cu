@@ -1000,8 +1000,62 @@ void launch_coef3d(mgb_plan *p, int l, const T *in, T *coef, T *coarse, cudaStre
     MGB_LAUNCH(MGB_K_COEF, st,
                (coef3d::coef3d_kernel<T, false><<<grid, coef3d::NT, 0, st>>>(P, in, coef, coarse, nullptr)));
 }
+// warp-per-tile formulation with TMA-staged rows (masstrans3d.cuh, second half); false:
+// the level is too small to fill the GPU with independent warps (the block formulation
+// splits finer) or the staging does not fit
+template <typename T>
+bool launch_masstrans3d_warp(mgb_plan *p, int l, const T *coef, T *w_out, cudaStream_t st) {
+  namespace mt = masstrans3d;
+  mt::WParams<T> P;
+  i64 full[5], dc[5];
+  dense_strides(p->shape, 3, full);
+  dense_strides(p->lshape[l - 1], 3, dc);
+  for (int d = 0; d < 3; d++) {
+    P.n[d] = (int)p->lshape[l][d];
+    P.nc[d] = (int)p->lshape[l - 1][d];
+    P.sin[d] = full[d];
+    P.sw[d] = dc[d];
+    P.mt[d] = (const T *)p->dtab(p->tab[l][d].mt);
+  }
+  if (full[2] != 1 || sizeof(T) != 4)
+    return false;
+  P.total = (i64)p->N;
+  P.ctiles = (P.nc[1] + mt::TC - 1) / mt::TC;
+  P.ftiles = (P.nc[2] + mt::TF - 1) / mt::TF;
+  const int tiles = P.ctiles * P.ftiles;
+  // 16 warps per SM; every r segment re-reads three warm-up planes, so segments of at
+  // least 8 coarse planes, at most 32 (the r constants of a segment sit in shared memory)
+  const long long want = 148ll * 2 * mt::W_NW;
+  const int max_segs = std::max(1, P.nc[0] / 8);
+  if ((long long)tiles * max_segs < want)
+    return false;
+  int rsegs = (int)std::min<long long>(max_segs, (want * 4 + tiles - 1) / tiles);
+  int per = std::min(32, (P.nc[0] + rsegs - 1) / rsegs);
+  P.per = per;
+  P.rsegs = (P.nc[0] + per - 1) / per;
+  const size_t smem = mt::warp_smem_base<T>() + (size_t)mt::W_NW * mt::warp_smem_bytes<T>(per);
+  if (smem > 113 * 1024)
+    return false;
+  static bool configured[64] = {};
+  if (mgb_first_use_on_device(configured)) {
+    if (cudaFuncSetAttribute(mt::masstrans3d_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             113 * 1024) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+  }
+  const long long warps = (long long)tiles * P.rsegs;
+  const unsigned grid = (unsigned)((warps + mt::W_NW - 1) / mt::W_NW);
+  MGB_LAUNCH(MGB_K_MASSTRANS, st,
+             (mt::masstrans3d_warp_kernel<T><<<grid, mt::W_NW * 32, smem, st>>>(P, coef, w_out)));
+  return true;
+}
+
 template <typename T>
 void launch_masstrans3d(mgb_plan *p, int l, const T *coef, T *w_out, cudaStream_t st) {
+  static const bool v1 = getenv("MGB_MASSTRANS_V1") != nullptr;
+  if (!v1 && launch_masstrans3d_warp<T>(p, l, coef, w_out, st))
+    return;
   masstrans3d::Params<T> P;
   i64 full[5], dc[5];
   dense_strides(p->shape, 3, full);

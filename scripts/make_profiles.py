@@ -1,11 +1,17 @@
-"""Builds profiles/r1_ncu_kernels.md and profiles/r1_ncu_traffic.json from the
-`ncu --set full` captures of the finest-level launches (gpurun_out/r1_final_*.ncu-rep)."""
+"""Builds profiles/<out>_kernels.md and profiles/<out>_traffic.json from `ncu --set full`
+captures of the finest-level launches of every kernel family.
+Usage: make_profiles.py <out prefix, e.g. r2_ncu_c5> "<title line>" <report stems under gpurun_out/ ...>
+(no arguments: the round-1 set)"""
 import csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REPS = ["r1_final_levels", "r1_final_huff", "r1_final_restore"]
-FAM = [("norm_partial", "norm"), ("coef3d", "coef"), ("masstrans3d", "mass_trans"), ("thomas_smem", "thomas_contig"),
+OUT = sys.argv[1] if len(sys.argv) > 1 else "r1_ncu"
+TITLE = sys.argv[2] if len(sys.argv) > 2 else "513^3 fp32 bench field (scripts/prof_one.py); one launch per family; durations under ncu are cold-cache."
+REPS = sys.argv[3:] if len(sys.argv) > 3 else ["r1_final_levels", "r1_final_huff", "r1_final_restore"]
+FAM = [("norm_partial", "norm"), ("coef3d", "coef"), ("masstrans3d", "mass_trans"), ("thomas_tma", "thomas_contig"),
+       ("thomas_smem", "thomas_contig"),
        ("thomas_strided", "thomas_strided"), ("restore3d", "restore"), ("quantize_linear", "quantize_hist"),
-       ("codebook", "codebook"), ("chunk_bits", "chunk_bits"), ("encode_kernel", "encode"), ("decode_fast", "decode")]
+       ("codebook", "codebook"), ("chunk_bits", "chunk_bits"), ("encode_kernel", "encode"), ("encode_serial", "encode"),
+       ("decode_fast", "decode"), ("decode_serial", "decode"), ("sort_outliers", "outlier_sort")]
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
@@ -22,8 +28,8 @@ def to_bytes(v, unit):
 def to_us(v, unit):
     f = float(v.replace(",", ""))
     return f * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}[unit]
-traffic, md = {}, ["# r1: `ncu --set full --clock-control none` of the finest-level launch of every kernel family",
-                   "", "513^3 fp32 bench field (scripts/prof_one.py); one launch per family; durations under ncu are cold-cache.", ""]
+traffic, md = {}, [f"# {OUT}: `ncu --set full --clock-control none` of the largest launch of every kernel family",
+                   "", TITLE, ""]
 for rep in REPS:
     path = os.path.join(ROOT, "gpurun_out", rep + ".ncu-rep")
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -33,7 +39,11 @@ for rep in REPS:
     for r in rows[2:]:
         d = dict(zip(h, r)); u = dict(zip(h, units))
         fam = next((f for k, f in FAM if k in d["Kernel Name"]), None)
-        if fam is None or fam in seen:
+        if fam is None:
+            continue
+        # keep the longest launch of the family (the finest level)
+        us0 = to_us(d["gpu__time_duration.sum"], u["gpu__time_duration.sum"])
+        if fam in traffic and traffic[fam]["ncu_duration_us"] >= us0:
             continue
         seen.add(fam)
         rd = to_bytes(d["dram__bytes_read.sum"], u["dram__bytes_read.sum"])
@@ -50,7 +60,7 @@ for rep in REPS:
             if k in d and d[k] != "":
                 md.append(f"| {k} | {d[k]} | {u[k]} |")
         md.append("")
-json.dump(traffic, open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json"), "w"), indent=1)
-open(os.path.join(ROOT, "profiles", "r1_ncu_kernels.md"), "w").write("\n".join(md) + "\n")
+json.dump(traffic, open(os.path.join(ROOT, "profiles", OUT + "_traffic.json"), "w"), indent=1)
+open(os.path.join(ROOT, "profiles", OUT + "_kernels.md"), "w").write("\n".join(md) + "\n")
 for f, t in traffic.items():
     print(f"{f:16s} {t['ncu_duration_us']:9.1f} us  dram {(t['dram_read_bytes']+t['dram_write_bytes'])/1e6:8.1f} MB  {t['dram_gbs_under_ncu']:7.0f} GB/s  issue {t['issue_active_pct']:5.1f}%  regs {t['registers']}")

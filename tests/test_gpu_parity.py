@@ -331,6 +331,20 @@ def test_cxx_api_mirror_compiles_and_round_trips(env, tmp_path):
     assert "compress status 0" in out.stdout and "decompress status 0" in out.stdout
 
 
+def test_cxx_lowlevel_mirror_compiles_and_round_trips(env, tmp_path):
+    """include/mgard_b200/compress_x_lowlevel.hpp: Hierarchy / Compressor / Array of the
+    reference's low-level API (doc/MGARD-X.md:205-262), the documentation's example."""
+    import subprocess
+    root = os.path.dirname(HERE)
+    exe = tmp_path / "lowlevel_roundtrip"
+    subprocess.check_call(["g++", "-std=c++17", f"-I{root}/include", "-I/usr/local/cuda/include",
+                           f"{HERE}/cxx/lowlevel_roundtrip.cpp", "-o", str(exe), f"-L{root}/mgard_b200",
+                           "-lmgard_b200", f"-Wl,-rpath,{root}/mgard_b200", "-L/usr/local/cuda/lib64", "-lcudart"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "lowlevel ok" in out.stdout
+
+
 def _huff_roundtrip(torch, mg, d, sym, dict_size, block, oracle=True):
     """encode + decode of a symbol stream through the stage API; optionally the
     payload against the oracle's."""

@@ -1272,16 +1272,23 @@ int launch_decoders(mgb_plan *p, const u64 *ddata, u64 total_words, const u64 *b
       cudaFuncSetAttribute(serial::decode_serial_kernel<OUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }
     MGB_LAUNCH(MGB_K_PARSE, st, (serial::build_lut_kernel<<<1, 1024, 0, st>>>(decodebook, dict, (unsigned char *)p->d_declut)));
-    const unsigned blocks = (unsigned)((nchunk + serial::DS_T - 1) / serial::DS_T);
+    // Threads (= chunks) per block so that the chunks spread evenly over the SMs: the
+    // tables allow two blocks per SM, and a launch is as slow as its fullest SM (52 700
+    // chunks of a C5 slab in blocks of 256: 58 SMs with 512 threads, 90 with 256)
+    const u64 slots = 148ull * 2;
+    const u64 waves = (nchunk + slots * serial::DS_T - 1) / (slots * serial::DS_T);
+    unsigned threads = (unsigned)((nchunk + slots * waves - 1) / (slots * waves));
+    threads = std::min<unsigned>(serial::DS_T, std::max<unsigned>(64, (threads + 31) & ~31u));
+    const unsigned blocks = (unsigned)((nchunk + threads - 1) / threads);
     const bool vec = ((uintptr_t)out & 31) == 0 && ((size_t)chunk * sizeof(OUT)) % 32 == 0;
     if (vec)
       MGB_LAUNCH(MGB_K_DECODE, st,
-                 (serial::decode_serial_kernel<OUT, true><<<blocks, serial::DS_T, tabb, st>>>(
+                 (serial::decode_serial_kernel<OUT, true><<<blocks, threads, tabb, st>>>(
                      ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict,
                      (const unsigned char *)p->d_declut, out, scale)));
     else
       MGB_LAUNCH(MGB_K_DECODE, st,
-                 (serial::decode_serial_kernel<OUT, false><<<blocks, serial::DS_T, tabb, st>>>(
+                 (serial::decode_serial_kernel<OUT, false><<<blocks, threads, tabb, st>>>(
                      ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict,
                      (const unsigned char *)p->d_declut, out, scale)));
     MGB_CUDA_CHECK(cudaGetLastError());

@@ -22,7 +22,7 @@
 
 namespace serial {
 
-constexpr int DS_T = 256;          // threads (= chunks) per block, decoder
+constexpr int DS_T = 512;          // most threads (= chunks) per block, decoder (chosen per launch)
 constexpr int ES_T = 128;          // encoder
 constexpr int LUT_BITS = 16;       // code lengths resolved by one table lookup
 
@@ -134,11 +134,11 @@ decode_serial_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *
     const uint4 *g4 = reinterpret_cast<const uint4 *>(gtab);
     uint4 *s4 = reinterpret_cast<uint4 *>(s_tab);
     const int n16 = (int)(tab_bytes(dict) / 16);
-    for (int i = threadIdx.x; i < n16; i += DS_T)
+    for (int i = threadIdx.x; i < n16; i += blockDim.x)
       s4[i] = g4[i];
   }
   __syncthreads();
-  const u64 c = (u64)blockIdx.x * DS_T + threadIdx.x;
+  const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nchunk)
     return;
   // shared addresses as plain 32-bit registers (no generic-pointer arithmetic in the loop)

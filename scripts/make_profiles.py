@@ -31,8 +31,13 @@ def to_us(v, unit):
 traffic, md = {}, [f"# {OUT}: `ncu --set full --clock-control none` of the largest launch of every kernel family",
                    "", TITLE, ""]
 for rep in REPS:
+    # a report, or the `ncu -i report --page raw --csv` export of one (made on the GPU box
+    # when the report itself is too large to bring back)
     path = os.path.join(ROOT, "gpurun_out", rep + ".ncu-rep")
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if os.path.exists(os.path.join(ROOT, "gpurun_out", rep + ".csv")):
+        out = open(os.path.join(ROOT, "gpurun_out", rep + ".csv")).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     h, units = rows[0], rows[1]
     seen = set()

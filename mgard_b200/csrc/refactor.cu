@@ -28,6 +28,7 @@
 #include "coef3d.cuh"
 #include "masstrans3d.cuh"
 #include "thomas_tma.cuh"
+#include "thomas_stream.cuh"
 #include "restore3d.cuh"
 #include "plan.h"
 
@@ -1164,6 +1165,18 @@ void thomas_all(mgb_plan *p, int l, T *w, T *acc, int mode, cudaStream_t st) {
       MGB_LAUNCH(MGB_K_THOMAS_STRIDED, st,
                  (thomas_strided_kernel<T><<<blocks, 128, 0, st>>>(w, n, inner, lines, fw, am, bm,
                                                                   accp, md)));
+      continue;
+    }
+    // contiguous axis, plain solve, enough lines for 128-line blocks on every SM: the
+    // streaming kernel (thomas_stream.cuh)
+    static const int stream_mode = getenv("MGB_THOMAS_STREAM") ? atoi(getenv("MGB_THOMAS_STREAM")) : 1;
+    // (lines of up to ~400 nodes fit in shared memory by the hundred per SM: the resident
+    // formulation below is faster there - 0.077 against 0.097 ms at 257 x 257 lines of 257)
+    if (stream_mode && md == 0 && outer >= 148ll * thomas_stream::LINES && (n >= 400 || stream_mode == 2)) {
+      const unsigned blocks = (unsigned)((outer + thomas_stream::LINES - 1) / thomas_stream::LINES);
+      MGB_LAUNCH(MGB_K_THOMAS_CONTIG, st,
+                 (thomas_stream::thomas_stream_kernel<T><<<blocks, thomas_stream::LINES, 0, st>>>(
+                     w, n, (long long)outer, fw, am, bm)));
       continue;
     }
     // contiguous axis: whole lines staged in shared memory by the TMA engine when the

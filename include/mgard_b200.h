@@ -340,8 +340,10 @@ int mgb_cpu_decompress(const void *in, size_t in_size, void **out, int *ndim,
 /* Tuning knobs (tests and A/B measurements; results never depend on them).
  * MGB_TUNE_SERIAL_MIN_CHUNKS: Huffman blocks with at least this many chunks are
  * encoded / decoded by the thread-per-chunk kernels, smaller ones by the
- * block-per-chunk kernels (0: always thread-per-chunk, negative: never). */
-enum { MGB_TUNE_SERIAL_MIN_CHUNKS = 0 };
+ * block-per-chunk kernels (0: always thread-per-chunk, negative: never).
+ * MGB_TUNE_RING_DECODER: 1 (default): the thread-per-chunk decoder reads its bit
+ * stream through a shared-memory ring; 0: the register-queue formulation. */
+enum { MGB_TUNE_SERIAL_MIN_CHUNKS = 0, MGB_TUNE_RING_DECODER = 1 };
 int mgb_tune(int key, long long value);
 
 /* kernel launch counter (bench.py's gpu_launches) */

@@ -176,6 +176,7 @@ def unpin_memory(array):
 
 
 TUNE_SERIAL_MIN_CHUNKS = 0
+TUNE_RING_DECODER = 1
 
 
 def tune(key, value):

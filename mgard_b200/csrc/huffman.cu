@@ -1254,6 +1254,9 @@ namespace {
 u64 g_serial_min_chunks = getenv("MGB_SERIAL_MIN_CHUNKS") ? strtoull(getenv("MGB_SERIAL_MIN_CHUNKS"), nullptr, 10)
                                                           : 16384ull;
 u64 serial_min_chunks() { return g_serial_min_chunks; }
+// the ring formulation of the thread-per-chunk decoder (MGB_TUNE_RING_DECODER; 0: first formulation)
+bool g_ring_decoder = !getenv("MGB_NO_RING_DECODER");
+int g_ring_lanes = getenv("MGB_RING_LANES") ? std::min(32, std::max(1, atoi(getenv("MGB_RING_LANES")))) : 8;
 
 // Launches the decoders for one serialised block.  OUT = uint16_t: symbols;
 // OUT = float / double: values dequantized with `scale` while a chunk is flushed.
@@ -1261,11 +1264,60 @@ template <typename OUT>
 int launch_decoders(mgb_plan *p, const u64 *ddata, u64 total_words, const u64 *bits,
                     const u64 *woff, u64 nchunk, int chunk, u64 n, const u64 *decodebook, int dict,
                     OUT *out, OUT scale, cudaStream_t st) {
+  const bool out_vec = ((uintptr_t)out & 31) == 0 && ((size_t)chunk * sizeof(OUT)) % 32 == 0;
+  if (nchunk >= serial_min_chunks() && g_ring_decoder && out_vec && dict <= 65536 &&
+      serial::ring_smem_bytes<OUT>(0, 64) <= 200 * 1024) {
+    // thread per chunk, stream through a shared-memory ring (huffman_serial.cuh)
+    const size_t budget = 200 * 1024;
+    if (!p->d_declut)
+      MGB_CUDA_CHECK(cudaMalloc(&p->d_declut, std::max(serial::ring_tab_bytes<float>(serial::RL2_MAX),
+                                                       serial::tab_bytes(dict))));
+    static bool configured[64] = {};
+    if (mgb_first_use_on_device(configured))
+      cudaFuncSetAttribute(serial::decode_ring_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+    // Threads (= chunks) per block: the chunks of one wave spread evenly over the SMs, k
+    // blocks on each, for the smallest k whose blocks fit (tables + 128 bytes of ring per
+    // thread); what is left of the shared memory goes to second-level tables.
+    const unsigned L = (unsigned)g_ring_lanes; // lanes of a warp that take a chunk
+    cudaFuncAttributes fa;
+    MGB_CUDA_CHECK(cudaFuncGetAttributes(&fa, serial::decode_ring_kernel<OUT>));
+    const unsigned max_thr = std::min(2048u, 65536u / (unsigned)std::max(fa.numRegs, 32) / 32 * 32); // per SM
+    const unsigned act_max = serial::RING_T / 32 * L;
+    unsigned act = act_max, resident = 0;      // chunks per block | blocks per SM
+    for (unsigned k = 1; k <= 8; k++) {
+      unsigned t = (unsigned)((nchunk + 148ull * k - 1) / (148ull * k));
+      t = std::max(2 * L, (t + L - 1) / L * L);
+      if (t <= act_max && t / L * 32 * k <= max_thr && budget / serial::ring_smem_bytes<OUT>(0, (int)t) >= k) {
+        act = t;
+        resident = k;
+        break;
+      }
+    }
+    const size_t base = serial::ring_smem_bytes<OUT>(0, (int)act);
+    if (base > budget)
+      return MGB_FAILURE;
+    // blocks per SM (several waves: as many as fit)
+    const size_t per_sm = resident ? resident : std::max<size_t>(1, std::min<size_t>(budget / base, max_thr / (act / L * 32)));
+    const int nsub = (int)std::min<size_t>(serial::RL2_MAX, (budget / per_sm - base) / (sizeof(typename serial::RingLut<OUT>::entry) << serial::RL2_BITS));
+    // warps work in groups of RING_S on L * RING_S chunks: whole groups
+    const unsigned threads = act / L * 32;
+    const u64 warps = (nchunk + (u64)L * serial::RING_S - 1) / ((u64)L * serial::RING_S) * serial::RING_S;
+    const unsigned blocks = (unsigned)((warps + threads / 32 - 1) / (threads / 32));
+    MGB_LAUNCH(MGB_K_PARSE, st,
+               (serial::build_ring_lut_kernel<OUT><<<1, 1024, 0, st>>>(decodebook, dict, nsub,
+                                                                       (unsigned char *)p->d_declut, scale)));
+    MGB_LAUNCH(MGB_K_DECODE, st,
+               (serial::decode_ring_kernel<OUT><<<blocks, threads, serial::ring_smem_bytes<OUT>(nsub, (int)act), st>>>(
+                   ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict, nsub, (int)L,
+                   (const unsigned char *)p->d_declut, out, scale)));
+    MGB_CUDA_CHECK(cudaGetLastError());
+    return MGB_SUCCESS;
+  }
   if (nchunk >= serial_min_chunks() && serial::tab_bytes(dict) <= 200 * 1024) {
     // thread per chunk (huffman_serial.cuh)
     const size_t tabb = serial::tab_bytes(dict);
     if (!p->d_declut)
-      MGB_CUDA_CHECK(cudaMalloc(&p->d_declut, tabb));
+      MGB_CUDA_CHECK(cudaMalloc(&p->d_declut, std::max(tabb, serial::ring_tab_bytes<float>(serial::RL2_MAX))));
     static bool configured[64] = {};
     if (mgb_first_use_on_device(configured)) {
       cudaFuncSetAttribute(serial::decode_serial_kernel<OUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1416,6 +1468,9 @@ extern "C" int mgb_tune(int key, long long value) {
   switch (key) {
   case MGB_TUNE_SERIAL_MIN_CHUNKS:
     g_serial_min_chunks = value < 0 ? ~0ull : (u64)value;
+    return MGB_SUCCESS;
+  case MGB_TUNE_RING_DECODER:
+    g_ring_decoder = value != 0;
     return MGB_SUCCESS;
   default:
     return MGB_BAD_ARGUMENT;

@@ -19,6 +19,7 @@
 //     the uncoalesced-by-construction access pattern still moves whole sectors.
 // The block-per-chunk kernels of huffman.cu stay for inputs with few chunks.
 #pragma once
+#include <type_traits>
 
 namespace serial {
 
@@ -229,6 +230,344 @@ decode_serial_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *
   }
   for (; i < nsym; i++)
     dst[i] = sym_value<OUT>(step(), scale, half);
+}
+
+// ----------------------- decoder, second formulation ------------------------
+// Thread per chunk again, written so that the lanes of a warp never part ways
+// although each is at a different bit position of a different chunk — a warp pays
+// for a branch whenever ANY of its lanes takes it, and with 32 independent decoders
+// in a warp "rare" events (a new word of the bit stream, a codeword that misses the
+// table) happen at almost every symbol — and with as few instructions per symbol as
+// it takes: with one warp per 32 chunks there are only ~3 warps per scheduler, each
+// a chain of dependent instructions, so the instruction count IS the run time.
+//   * The reader holds 64 stream bits (w0:w1), the next 32 (w2) and a bit offset
+//     o < 32; the 32-bit window at o is ONE funnel shift.  After a codeword: o += l,
+//     and if o >= 32 the words move up and w2 is reloaded — predicated, no branch.
+//   * Codewords of up to RL_BITS bits: one lookup by the first RL_BITS bits of the
+//     window: lut[x] = {dequantized value, length} (fp32 output) or symbol << 8 | length.
+//   * Codewords of up to RL_BITS + RL2_BITS bits: a miss of the first table carries
+//     the offset of a second-level table for its prefix (codes longer than RL_BITS
+//     bits are the numerically smallest ones: their prefixes are 0, 1, 2, ...), looked
+//     up with the following RL2_BITS bits by a PREDICATED load.
+//   * Longer codewords (a few in 10^4 symbols): canonical walk on the window, out of
+//     line; beyond 32 bits (never seen): from global memory.
+//   * The bit stream of a thread's chunk reaches it through a private 128-byte ring
+//     in shared memory that the thread keeps full itself with 16-byte cp.async copies,
+//     RING - 1 pieces ahead of its reader (pieces and words XOR-swizzled by the lane,
+//     so the lanes of a warp hit different banks).
+// Consecutive chunks go to different thread blocks and warps: chunks of one part of
+// the coefficient array are alike, and the ones that hold the coarse levels (long
+// codewords throughout) would otherwise share a warp.
+// Requires 32-byte aligned chunk starts in `out` (8 values per store).
+constexpr int RL_BITS = 12;
+constexpr int RL2_BITS = 8;        // second-level tables: RL2_BITS more bits
+constexpr int RING = 8;            // 16-byte pieces per thread
+constexpr int RL2_MAX = 96;        // second-level tables at most
+
+template <typename OUT> struct RingLut { typedef unsigned entry; };
+template <> struct RingLut<float> { typedef uint2 entry; };
+
+// Tables (E = table entry): lut[1 << RL_BITS] | t32[36] | b32[36] | lstart[36] | pad[4] | sub[nsub + 1][1 << RL2_BITS]
+//   lut     first level; a miss (length 0) carries the byte offset of the second-level
+//           table of its prefix x: table x + 1 for x < nsub, else table 0 (all misses)
+//   sub     second level, same entries, for codes of up to RL_BITS + RL2_BITS bits, by the
+//           RL2_BITS bits that follow the prefix; length 0: longer
+//   t32[l]  first code of length l left aligned in 32 bits (0xffffffff: none), b32[l] =
+//           entry[l] - first[l], lstart[z] = shortest length a 32-bit window with z leading
+//           zeros can have: where the canonical walk starts
+template <typename OUT> __host__ __device__ inline size_t ring_tab_bytes(int nsub) {
+  return sizeof(typename RingLut<OUT>::entry) * ((size_t)(1 << RL_BITS) + ((size_t)(nsub + 1) << RL2_BITS)) + 112 * 4;
+}
+template <typename OUT> __host__ __device__ inline size_t ring_smem_bytes(int nsub, int slots) {
+  return ring_tab_bytes<OUT>(nsub) + (size_t)RING * 16 * slots;
+}
+
+template <typename OUT>
+__global__ void __launch_bounds__(1024)
+build_ring_lut_kernel(const u64 *__restrict__ decodebook, int dict, int nsub, unsigned char *__restrict__ g,
+                      OUT scale) {
+  typedef typename RingLut<OUT>::entry E;
+  __shared__ u64 s_first[64], s_entry[64];
+  const int tid = threadIdx.x;
+  if (tid < 128)
+    (tid < 64 ? s_first : s_entry)[tid & 63] = decodebook[tid];
+  __syncthreads();
+  E *lut = reinterpret_cast<E *>(g);
+  unsigned *t32 = reinterpret_cast<unsigned *>(lut + (1 << RL_BITS)), *b32 = t32 + 36, *lstart = b32 + 36;
+  E *sub = reinterpret_cast<E *>(lstart + 40);
+  auto t32_of = [&](int l) -> unsigned {
+    const bool valid = l >= 1 && l <= 32 && s_first[l] != ~0ull && (s_first[l] >> l) == 0;
+    return valid ? (unsigned)(s_first[l] << (32 - l)) : 0xffffffffu;
+  };
+  if (tid < 36) {
+    t32[tid] = t32_of(tid);
+    b32[tid] = t32_of(tid) != 0xffffffffu ? (unsigned)(s_entry[tid] - s_first[tid]) : 0u;
+    // windows with z = tid leading zeros are at most hi_max: no length whose first code lies above it
+    const unsigned hi_max = tid >= 32 ? 0u : (0xffffffffu >> tid);
+    int l = RL_BITS + 1;
+    while (l <= 32 && t32_of(l) > hi_max)
+      l++;
+    lstart[tid] = (unsigned)l;
+  }
+  int lmin = 1;
+  while (lmin < 63 && s_first[lmin] == ~0ull)
+    lmin++;
+  const int half = dict / 2;
+  // symbol << 8 | length of the codeword at the top of the `width`-bit value x (0: longer)
+  auto lookup = [&](unsigned x, int width) -> unsigned {
+    for (int l = lmin; l <= width; l++) {
+      const u64 v = (u64)x >> (width - l);
+      if (v >= s_first[l]) {
+        const u64 ki = s_entry[l] + v - s_first[l];
+        const unsigned sym = ki < (u64)dict ? (unsigned)(decodebook[128 + ki] & 0xffffu) : 0u;
+        return (sym << 8) | (unsigned)l;
+      }
+    }
+    return 0u;
+  };
+  // table entry of a codeword (e != 0) or of a miss that continues at byte offset `off`
+  auto entry_of = [&](unsigned e, unsigned off) -> E {
+    if constexpr (sizeof(E) == 8) {
+      const float val = scale * (float)((int)(e >> 8) - half);
+      return (e & 0xffu) ? make_uint2(__float_as_uint(val), e & 0xffu) : make_uint2(off, 0u);
+    } else {
+      return (e & 0xffu) ? e : (off << 8);
+    }
+  };
+  for (int x = tid; x < (1 << RL_BITS); x += 1024)
+    lut[x] = entry_of(lookup((unsigned)x, RL_BITS), (x < nsub ? (unsigned)x + 1 : 0u) * (unsigned)(sizeof(E) << RL2_BITS));
+  for (int x = tid; x < ((nsub + 1) << RL2_BITS); x += 1024) {
+    const unsigned e = x < (1 << RL2_BITS) ? 0u : lookup((unsigned)x - (1u << RL2_BITS), RL_BITS + RL2_BITS);
+    sub[x] = entry_of((e & 0xffu) > RL_BITS ? e : 0u, 0u); // (shorter: never looked up here)
+  }
+}
+
+// helpers of the ring decoder's cold paths (inlined: a call in the kernel makes the compiler
+// keep what lives across it in local memory, which the hot loop then reads back)
+// 32 stream bits starting at half-word h of the chunk whose words are [A, lim), counted from A16
+__device__ __forceinline__ unsigned ring_half_global(unsigned h, unsigned long long A16, unsigned long long A,
+                                                  unsigned long long lim) {
+  const unsigned long long a = A16 + (u64)(h >> 1) * 8 + ((h & 1) ^ 1) * 4;
+  return (a >= A && a < lim) ? __ldg(reinterpret_cast<const unsigned *>(a)) : 0u;
+}
+// codeword of RL_BITS + 1 .. 32 bits at the top of `hi`: symbol | length << 16; ~0: longer
+__device__ __forceinline__ unsigned ring_walk(unsigned hi, unsigned a_t32, const u64 *__restrict__ decodebook, int dict) {
+  const unsigned a_b32 = a_t32 + 36 * 4, a_lstart = a_b32 + 36 * 4;
+  unsigned l = lds_u32(a_lstart + __clz(hi) * 4);
+#pragma unroll 1
+  while (l <= 32 && hi < lds_u32(a_t32 + l * 4))
+    l++;
+  if (l > 32)
+    return ~0u;
+  const unsigned ki = lds_u32(a_b32 + l * 4) + (hi >> (32 - l));
+  const unsigned sym = ki < (unsigned)dict ? (unsigned)(__ldg(decodebook + 128 + ki) & 0xffffu) : 0u;
+  return sym | (l << 16);
+}
+// codeword of 33 .. 63 bits at stream bit `bitpos` (from A16): symbol | length << 16
+__device__ __forceinline__ unsigned ring_walk_long(u64 bitpos, unsigned long long A16, unsigned long long A,
+                                                unsigned long long lim, const u64 *__restrict__ decodebook,
+                                                int dict) {
+  const unsigned h = (unsigned)(bitpos >> 5), off = (unsigned)(bitpos & 31);
+  const u64 x0 = ((u64)ring_half_global(h, A16, A, lim) << 32) | ring_half_global(h + 1, A16, A, lim);
+  const u64 win = off ? ((x0 << off) | ((u64)ring_half_global(h + 2, A16, A, lim) >> (32 - off))) : x0;
+  const u64 *first = decodebook, *entry = decodebook + 64, *keys = decodebook + 128;
+  int ll = 33;
+  u64 v = win >> (64 - ll);
+  while (v < __ldg(first + ll) && ll < 63) {
+    ll++;
+    v = win >> (64 - ll);
+  }
+  const u64 ki = __ldg(entry + ll) + v - __ldg(first + ll);
+  const unsigned sym = ki < (u64)dict ? (unsigned)(__ldg(keys + ki) & 0xffffu) : 0u;
+  return sym | ((unsigned)ll << 16);
+}
+
+constexpr int RING_T = 768;        // most threads per block
+constexpr int RING_S = 32;         // the lanes of a warp take every RING_S-th chunk
+template <typename OUT>
+__global__ void __launch_bounds__(RING_T)
+decode_ring_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__restrict__ bits,
+                   const u64 *__restrict__ woff, u64 nchunk, int chunk, u64 n,
+                   const u64 *__restrict__ decodebook, int dict, int nsub, int lanes,
+                   const unsigned char *__restrict__ gtab, OUT *__restrict__ out, OUT scale) {
+  typedef typename RingLut<OUT>::entry E;
+  constexpr bool VAL_LUT = sizeof(E) == 8; // the tables hold dequantized values
+  constexpr int ES = VAL_LUT ? 3 : 2;      // log2 of the entry size
+  extern __shared__ __align__(128) unsigned char s_tab[];
+  {
+    const uint4 *g4 = reinterpret_cast<const uint4 *>(gtab);
+    uint4 *s4 = reinterpret_cast<uint4 *>(s_tab);
+    const int n16 = (int)(ring_tab_bytes<OUT>(nsub) / 16);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x)
+      s4[i] = g4[i];
+  }
+  __syncthreads();
+  // Chunk of this thread.  Only the first `lanes` lanes of a warp take one (32: all of them).
+  // Chunks of one part of the coefficient array are alike, and the ones that hold the coarse
+  // levels (long codewords throughout, a few dozen in a row) should not share a warp: warps
+  // work in groups of RING_S, the lanes of a warp take every RING_S-th chunk of the group's
+  // lanes * RING_S chunks.  (Spreading further costs more than it gains: the 32 stores of a
+  // warp then go to 32 pages that are not in the TLB.)
+  const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const u64 wg = (u64)blockIdx.x * (blockDim.x >> 5) + wib;
+  const u64 c = (wg / RING_S) * ((u64)lanes * RING_S) + (u64)lane * RING_S + wg % RING_S;
+  if (lane >= (unsigned)lanes || c >= nchunk)
+    return;
+  // shared addresses held in registers (opaque to the compiler, which otherwise
+  // recomputes the window base in front of every access)
+  unsigned a_lut = (unsigned)__cvta_generic_to_shared(s_tab);
+  asm volatile("mov.u32 %0, %0;" : "+r"(a_lut));
+  const unsigned a_t32 = a_lut + (unsigned)(sizeof(E) << RL_BITS);
+  unsigned a_sub = a_t32 + 112 * 4;
+  // this thread's ring: 128 bytes; piece q at ((q ^ lane) & 7) * 16, half-word h (32 stream
+  // bits, the HIGH half of a 64-bit word first) at ((4 * h) ^ cx) & 124
+  unsigned a_ring = a_lut + (unsigned)ring_tab_bytes<OUT>(nsub) + (wib * lanes + lane) * (RING * 16u);
+  unsigned cx = 4u ^ ((lane & 7u) << 4);
+  asm volatile("mov.u32 %0, %0;" : "+r"(a_sub));
+  asm volatile("mov.u32 %0, %0;" : "+r"(a_ring));
+  asm volatile("mov.u32 %0, %0;" : "+r"(cx));
+  const int half = dict / 2;
+  const unsigned nsym = (unsigned)min((u64)chunk, n - c * (u64)chunk);
+  OUT *dst = out + c * (u64)chunk;
+  const u64 B64 = bits[c], w0_ = woff[c];
+  const u64 nw = (B64 - 1) / 64 + 1;
+  // the per-chunk fields come from the stream: a chunk that does not lie inside the
+  // bit stream decodes to zeros (as in decode_kernel)
+  if (B64 == 0 || B64 > (u64)chunk * 64 || w0_ > total_words || nw > total_words - w0_) {
+    for (unsigned i = 0; i < nsym; i++)
+      dst[i] = (OUT)0;
+    return;
+  }
+  // byte addresses: the chunk's words are [A, lim); pieces and half-words are counted from A16
+  const unsigned long long A = (unsigned long long)(ddata + w0_), lim = A + nw * 8, A16 = A & ~15ull;
+  unsigned iss = 0; // pieces requested so far: the ring is full after every request phase
+  // piece `iss` if it is below `top` (no branch)
+  auto request = [&](unsigned top) {
+    const unsigned long long g = A16 + (u64)iss * 16;
+    const unsigned nbytes = g < lim ? (unsigned)min((unsigned long long)16, lim - g) : 0u;
+    const unsigned go = iss < top;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}" ::"r"(
+                     a_ring + (((iss ^ lane) & 7u) << 4)),
+                 "l"(nbytes ? g : A16), "r"(nbytes), "r"(go)
+                 : "memory");
+    iss += go;
+  };
+  auto half_ring = [&](unsigned hb) -> unsigned { // hb = 4 * half-word index
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a_ring + ((hb ^ cx) & 124u)) : "memory");
+    return v;
+  };
+#pragma unroll
+  for (int q = 0; q < RING; q++)
+    request(RING);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // A round (8 symbols) ends with the ring full (RING pieces from the one the reader's next
+  // word is in) and all but the requests of the last two rounds complete.  A round takes
+  // at most 8 * 32 bits = 2 pieces, so what is read during the next round was requested
+  // three rounds ago or earlier: always there.  (Codewords of more than 32 bits: see `rare`.)
+  unsigned w0, w1, w2; // stream bits: the window is at bit o of w0:w1; w2 follows
+  unsigned o;          // < 32
+  unsigned hb;         // 4 * (half-word that follows w2)
+  {
+    const unsigned h0 = (unsigned)(A - A16) / 4;
+    w0 = half_ring(4 * h0), w1 = half_ring(4 * h0 + 4), w2 = half_ring(4 * h0 + 8);
+    hb = 4 * h0 + 12;
+    o = 0;
+  }
+  auto value = [&](unsigned sym) -> OUT {
+    if (sizeof(OUT) == 2)
+      return (OUT)sym;
+    return scale * (OUT)((int)sym - half); // = (T)(long long)(sym - half): |sym - half| < 2^16
+  };
+  // a codeword longer than RL_BITS + RL2_BITS bits: symbol and length
+  auto rare = [&](unsigned win, unsigned &l) -> unsigned {
+    unsigned r = ring_walk(win, a_t32, decodebook, dict);
+    if (r == ~0u) {
+      // more than 32 bits: from global memory, and the reader restarts behind it
+      const u64 bitpos = (u64)(hb / 4 - 3) * 32 + o;
+      r = ring_walk_long(bitpos, A16, A, lim, decodebook, dict);
+      const u64 np = bitpos + (r >> 16);
+      const unsigned h = (unsigned)(np >> 5);
+      w0 = ring_half_global(h, A16, A, lim), w1 = ring_half_global(h + 1, A16, A, lim);
+      w2 = ring_half_global(h + 2, A16, A, lim);
+      hb = 4 * h + 12;
+      o = (unsigned)(np & 31);
+      asm volatile("cp.async.wait_group 0;" ::: "memory"); // everything requested is there
+      l = 0;
+      return r & 0xffffu;
+    }
+    l = r >> 16;
+    return r & 0xffffu;
+  };
+  // One symbol.  FAST: a codeword that is in neither table leaves the reader where it is
+  // (length 0) and is not counted in `ndec`; the caller deals with it.
+  unsigned ndec = 0;
+  auto step = [&](auto fast) -> OUT {
+    constexpr bool FAST = decltype(fast)::value;
+    const unsigned win = __funnelshift_l(w1, w0, o);
+    unsigned l, e0;
+    OUT v;
+    // first level, and the second one predicated on its miss (e0 = offset of the table)
+    const unsigned x2 = (win >> (32 - RL_BITS - RL2_BITS - ES)) & (((1u << RL2_BITS) - 1) << ES);
+    if constexpr (VAL_LUT) {
+      asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e0), "=r"(l) : "r"(a_lut + ((win >> (32 - RL_BITS)) << 3)));
+      asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, 0;\n\t@p ld.shared.v2.u32 {%0, %1}, [%2];\n\t}"
+          : "+r"(e0), "+r"(l)
+          : "r"(a_sub + e0 + x2));
+      v = __uint_as_float(e0);
+    } else {
+      e0 = lds_u32(a_lut + ((win >> (32 - RL_BITS)) << 2));
+      asm("{\n\t.reg .pred p;\n\t.reg .u32 t;\n\tand.b32 t, %0, 255;\n\tsetp.eq.u32 p, t, 0;\n\tshr.u32 t, %0, 8;\n\t"
+          "add.u32 t, t, %1;\n\t@p ld.shared.u32 %0, [t];\n\t}"
+          : "+r"(e0)
+          : "r"(a_sub + x2));
+      l = e0 & 0xffu;
+      v = value(e0 >> 8);
+    }
+    if (FAST)
+      ndec += l != 0;
+    else if (l == 0)
+      v = value(rare(win, l));
+    // behind the codeword; a new word when the offset leaves w0
+    o += l;
+    const bool p = o >= 32;
+    o = p ? o - 32 : o;
+    w0 = p ? w1 : w0;
+    w1 = p ? w2 : w1;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}"
+                 : "+r"(w2)
+                 : "r"(a_ring + ((hb ^ cx) & 124u)), "r"((unsigned)p)
+                 : "memory");
+    hb += p ? 4u : 0u;
+    return v;
+  };
+
+  unsigned i = 0;
+  for (; i + 8 <= nsym; i += 8) {
+    OUT v[8];
+    ndec = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      v[k] = step(std::true_type());
+    Store8<OUT>::run(dst + i, v);
+    if (__builtin_expect(ndec < 8, 0)) {
+      // the reader stands at a long codeword: this one and the rest of the round one by one
+#pragma unroll 1
+      for (unsigned k = ndec; k < 8; k++)
+        dst[i + k] = step(std::false_type());
+    }
+    // the pieces below the one the next word is in have been read: their slots take the next
+    // pieces (two at most: a round takes no more)
+    const unsigned top = (hb >> 4) + RING;
+    request(top);
+    request(top);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+  }
+  for (; i < nsym; i++)
+    dst[i] = step(std::false_type());
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------- encoder -----------------------------------

@@ -1256,7 +1256,7 @@ u64 g_serial_min_chunks = getenv("MGB_SERIAL_MIN_CHUNKS") ? strtoull(getenv("MGB
 u64 serial_min_chunks() { return g_serial_min_chunks; }
 // the ring formulation of the thread-per-chunk decoder (MGB_TUNE_RING_DECODER; 0: first formulation)
 bool g_ring_decoder = !getenv("MGB_NO_RING_DECODER");
-int g_ring_lanes = getenv("MGB_RING_LANES") ? std::min(32, std::max(1, atoi(getenv("MGB_RING_LANES")))) : 8;
+int g_ring_lanes = getenv("MGB_RING_LANES") ? std::min(32, std::max(1, atoi(getenv("MGB_RING_LANES")))) : 32;
 
 // Launches the decoders for one serialised block.  OUT = uint16_t: symbols;
 // OUT = float / double: values dequantized with `scale` while a chunk is flushed.

@@ -572,7 +572,7 @@ decode_ring_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__
 
 // ------------------------------- encoder -----------------------------------
 // Thread per chunk: codewords (len << 56 | code) appended MSB first into a 64-bit
-// accumulator, full words stored as they complete.  CB_SHARED: the codebook is
+// accumulator, full words stored as they complete (predicated, no branch).  CB_SHARED: the codebook is
 // copied to shared memory (dict * 8 bytes); otherwise it is read through L1.
 template <bool CB_SHARED, bool VEC>
 __global__ void __launch_bounds__(ES_T)
@@ -596,23 +596,29 @@ encode_serial_kernel(const uint16_t *__restrict__ sym, u64 n, int chunk, const u
   const uint16_t *src = sym + lo;
   u64 *dst = ddata + woff[c];
   u64 acc = 0;
-  unsigned fill = 0; // bits used in acc
+  unsigned fill = 0; // bits used in acc (< 64)
+  // Appends the codeword of s without a branch (the lanes of a warp complete their words at
+  // different symbols: a branch would be taken by some lane at almost every one).  The
+  // codeword goes to bit `fill` of the 128-bit pair acc : next word; PTX shifts by 64 or
+  // more give 0, which selects the part that applies.
   auto put = [&](unsigned s) {
     const u64 cw = CB_SHARED ? s_cb[s] : __ldg(codebook + s);
     const unsigned len = (unsigned)(cw >> 56);
-    if (len) {
-      const u64 code = cw & 0x00ffffffffffffffull;
-      const unsigned room = 64 - fill;
-      if (len < room) {
-        acc |= code << (room - len);
-        fill += len;
-      } else {
-        const unsigned rem = len - room;
-        *dst++ = acc | (code >> rem);
-        acc = rem ? code << (64 - rem) : 0ull;
-        fill = rem;
-      }
-    }
+    const u64 code = cw & 0x00ffffffffffffffull;
+    const int sh = 64 - (int)fill - (int)len; // >= 0: the codeword ends inside acc
+    u64 hi1, hi2, lo;
+    asm("shl.b64 %0, %1, %2;" : "=l"(hi1) : "l"(code), "r"((unsigned)sh));
+    asm("shr.b64 %0, %1, %2;" : "=l"(hi2) : "l"(code), "r"((unsigned)-sh));
+    asm("shl.b64 %0, %1, %2;" : "=l"(lo) : "l"(code), "r"((unsigned)(64 + sh)));
+    const u64 out = acc | hi1 | hi2;
+    const unsigned nf = fill + len;
+    const unsigned full = nf >= 64;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u64 [%0], %1;\n\t}" ::"l"(dst), "l"(out),
+                 "r"(full)
+                 : "memory");
+    dst += full;
+    acc = full ? lo : out;
+    fill = full ? nf - 64 : nf;
   };
   unsigned i = 0;
   if (VEC && cnt >= 16) {

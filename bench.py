@@ -396,7 +396,7 @@ def bench_c2(mg, L, dev, cfg, W, K, peak, peak_src):
     torch.cuda.synchronize()
     L.mgb_profile_enable(0)
     fam = kernel_table(L, reps)
-    roof, per_kernel = roofline_tables(fam, SHAPE, stream, peak, peak_src, "r2_ncu_traffic.json")
+    roof, per_kernel = roofline_tables(fam, SHAPE, stream, peak, peak_src, "r2_ncu_c2_traffic.json")
     res = {"workload": "3D fp32 513x513x513 synthetic field, relative L-inf 1e-3 (s=inf), Huffman lossless, one "
                        "sub-domain, Compressor::Compress / Decompress device resident",
            "value": 2 * nbytes / ((tc + td) * 1e-3) / 1e9, "unit": "GB/s", "compress_ms": tc, "decompress_ms": td,
@@ -557,7 +557,7 @@ def main():
         line["kernel_breakdown"] = fam
         sub_stream = int(r1["records"].numel()) / max(count, 1)
         roof, per_kernel = roofline_tables(fam, (ext[first],) + gshape[1:], sub_stream, peak, peak_src,
-                                           "r2_ncu_traffic_c5.json")
+                                           "r2_ncu_c5_traffic.json")
         if roof:
             line["roofline"] = roof
         line["roofline_kernels"] = per_kernel

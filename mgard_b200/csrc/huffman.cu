@@ -1266,11 +1266,11 @@ int launch_decoders(mgb_plan *p, const u64 *ddata, u64 total_words, const u64 *b
                     OUT *out, OUT scale, cudaStream_t st) {
   const bool out_vec = ((uintptr_t)out & 31) == 0 && ((size_t)chunk * sizeof(OUT)) % 32 == 0;
   if (nchunk >= serial_min_chunks() && g_ring_decoder && out_vec && dict <= 65536 &&
-      serial::ring_smem_bytes<OUT>(0, 64) <= 200 * 1024) {
+      serial::ring_smem_bytes<OUT>(dict, 0, 64) <= 200 * 1024) {
     // thread per chunk, stream through a shared-memory ring (huffman_serial.cuh)
     const size_t budget = 200 * 1024;
     if (!p->d_declut)
-      MGB_CUDA_CHECK(cudaMalloc(&p->d_declut, std::max(serial::ring_tab_bytes<float>(serial::RL2_MAX),
+      MGB_CUDA_CHECK(cudaMalloc(&p->d_declut, std::max(serial::ring_tab_bytes<float>(dict, serial::RL2_MAX),
                                                        serial::tab_bytes(dict))));
     static bool configured[64] = {};
     if (mgb_first_use_on_device(configured))
@@ -1287,13 +1287,13 @@ int launch_decoders(mgb_plan *p, const u64 *ddata, u64 total_words, const u64 *b
     for (unsigned k = 1; k <= 8; k++) {
       unsigned t = (unsigned)((nchunk + 148ull * k - 1) / (148ull * k));
       t = std::max(2 * L, (t + L - 1) / L * L);
-      if (t <= act_max && t / L * 32 * k <= max_thr && budget / serial::ring_smem_bytes<OUT>(0, (int)t) >= k) {
+      if (t <= act_max && t / L * 32 * k <= max_thr && budget / serial::ring_smem_bytes<OUT>(dict, 0, (int)t) >= k) {
         act = t;
         resident = k;
         break;
       }
     }
-    const size_t base = serial::ring_smem_bytes<OUT>(0, (int)act);
+    const size_t base = serial::ring_smem_bytes<OUT>(dict, 0, (int)act);
     if (base > budget)
       return MGB_FAILURE;
     // blocks per SM (several waves: as many as fit)
@@ -1307,7 +1307,7 @@ int launch_decoders(mgb_plan *p, const u64 *ddata, u64 total_words, const u64 *b
                (serial::build_ring_lut_kernel<OUT><<<1, 1024, 0, st>>>(decodebook, dict, nsub,
                                                                        (unsigned char *)p->d_declut, scale)));
     MGB_LAUNCH(MGB_K_DECODE, st,
-               (serial::decode_ring_kernel<OUT><<<blocks, threads, serial::ring_smem_bytes<OUT>(nsub, (int)act), st>>>(
+               (serial::decode_ring_kernel<OUT><<<blocks, threads, serial::ring_smem_bytes<OUT>(dict, nsub, (int)act), st>>>(
                    ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict, nsub, (int)L,
                    (const unsigned char *)p->d_declut, out, scale)));
     MGB_CUDA_CHECK(cudaGetLastError());
@@ -1317,7 +1317,7 @@ int launch_decoders(mgb_plan *p, const u64 *ddata, u64 total_words, const u64 *b
     // thread per chunk (huffman_serial.cuh)
     const size_t tabb = serial::tab_bytes(dict);
     if (!p->d_declut)
-      MGB_CUDA_CHECK(cudaMalloc(&p->d_declut, std::max(tabb, serial::ring_tab_bytes<float>(serial::RL2_MAX))));
+      MGB_CUDA_CHECK(cudaMalloc(&p->d_declut, std::max(tabb, serial::ring_tab_bytes<float>(dict, serial::RL2_MAX))));
     static bool configured[64] = {};
     if (mgb_first_use_on_device(configured)) {
       cudaFuncSetAttribute(serial::decode_serial_kernel<OUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -267,19 +267,21 @@ constexpr int RL2_MAX = 96;        // second-level tables at most
 template <typename OUT> struct RingLut { typedef unsigned entry; };
 template <> struct RingLut<float> { typedef uint2 entry; };
 
-// Tables (E = table entry): lut[1 << RL_BITS] | t32[36] | b32[36] | lstart[36] | pad[4] | sub[nsub + 1][1 << RL2_BITS]
+// Tables (E = table entry): lut[1 << RL_BITS] | t32[36] | b32[36] | lstart[36] | pad[4] | sub[nsub + 1][1 << RL2_BITS] | key16[dict]
 //   lut     first level; a miss (length 0) carries the byte offset of the second-level
 //           table of its prefix x: table x + 1 for x < nsub, else table 0 (all misses)
 //   sub     second level, same entries, for codes of up to RL_BITS + RL2_BITS bits, by the
 //           RL2_BITS bits that follow the prefix; length 0: longer
 //   t32[l]  first code of length l left aligned in 32 bits (0xffffffff: none), b32[l] =
 //           entry[l] - first[l], lstart[z] = shortest length a 32-bit window with z leading
-//           zeros can have: where the canonical walk starts
-template <typename OUT> __host__ __device__ inline size_t ring_tab_bytes(int nsub) {
-  return sizeof(typename RingLut<OUT>::entry) * ((size_t)(1 << RL_BITS) + ((size_t)(nsub + 1) << RL2_BITS)) + 112 * 4;
+//           zeros can have: where the canonical walk starts; key16: the symbols in canonical order
+__host__ __device__ inline size_t ring_key_bytes(int dict) { return ((size_t)dict * 2 + 127) & ~(size_t)127; }
+template <typename OUT> __host__ __device__ inline size_t ring_tab_bytes(int dict, int nsub) {
+  return sizeof(typename RingLut<OUT>::entry) * ((size_t)(1 << RL_BITS) + ((size_t)(nsub + 1) << RL2_BITS)) + 112 * 4 +
+         ring_key_bytes(dict);
 }
-template <typename OUT> __host__ __device__ inline size_t ring_smem_bytes(int nsub, int slots) {
-  return ring_tab_bytes<OUT>(nsub) + (size_t)RING * 16 * slots;
+template <typename OUT> __host__ __device__ inline size_t ring_smem_bytes(int dict, int nsub, int slots) {
+  return ring_tab_bytes<OUT>(dict, nsub) + (size_t)RING * 16 * slots;
 }
 
 template <typename OUT>
@@ -340,6 +342,9 @@ build_ring_lut_kernel(const u64 *__restrict__ decodebook, int dict, int nsub, un
     const unsigned e = x < (1 << RL2_BITS) ? 0u : lookup((unsigned)x - (1u << RL2_BITS), RL_BITS + RL2_BITS);
     sub[x] = entry_of((e & 0xffu) > RL_BITS ? e : 0u, 0u); // (shorter: never looked up here)
   }
+  uint16_t *key16 = reinterpret_cast<uint16_t *>(sub + ((size_t)(nsub + 1) << RL2_BITS));
+  for (int k = tid; k < dict; k += 1024)
+    key16[k] = (uint16_t)decodebook[128 + k];
 }
 
 // helpers of the ring decoder's cold paths (inlined: a call in the kernel makes the compiler
@@ -351,7 +356,7 @@ __device__ __forceinline__ unsigned ring_half_global(unsigned h, unsigned long l
   return (a >= A && a < lim) ? __ldg(reinterpret_cast<const unsigned *>(a)) : 0u;
 }
 // codeword of RL_BITS + 1 .. 32 bits at the top of `hi`: symbol | length << 16; ~0: longer
-__device__ __forceinline__ unsigned ring_walk(unsigned hi, unsigned a_t32, const u64 *__restrict__ decodebook, int dict) {
+__device__ __forceinline__ unsigned ring_walk(unsigned hi, unsigned a_t32, unsigned a_key, int dict) {
   const unsigned a_b32 = a_t32 + 36 * 4, a_lstart = a_b32 + 36 * 4;
   unsigned l = lds_u32(a_lstart + __clz(hi) * 4);
 #pragma unroll 1
@@ -360,7 +365,7 @@ __device__ __forceinline__ unsigned ring_walk(unsigned hi, unsigned a_t32, const
   if (l > 32)
     return ~0u;
   const unsigned ki = lds_u32(a_b32 + l * 4) + (hi >> (32 - l));
-  const unsigned sym = ki < (unsigned)dict ? (unsigned)(__ldg(decodebook + 128 + ki) & 0xffffu) : 0u;
+  const unsigned sym = ki < (unsigned)dict ? lds_u16(a_key + ki * 2) : 0u;
   return sym | (l << 16);
 }
 // codeword of 33 .. 63 bits at stream bit `bitpos` (from A16): symbol | length << 16
@@ -397,7 +402,7 @@ decode_ring_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__
   {
     const uint4 *g4 = reinterpret_cast<const uint4 *>(gtab);
     uint4 *s4 = reinterpret_cast<uint4 *>(s_tab);
-    const int n16 = (int)(ring_tab_bytes<OUT>(nsub) / 16);
+    const int n16 = (int)(ring_tab_bytes<OUT>(dict, nsub) / 16);
     for (int i = threadIdx.x; i < n16; i += blockDim.x)
       s4[i] = g4[i];
   }
@@ -419,9 +424,10 @@ decode_ring_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__
   asm volatile("mov.u32 %0, %0;" : "+r"(a_lut));
   const unsigned a_t32 = a_lut + (unsigned)(sizeof(E) << RL_BITS);
   unsigned a_sub = a_t32 + 112 * 4;
+  const unsigned a_key = a_sub + (unsigned)(sizeof(E) * ((size_t)(nsub + 1) << RL2_BITS));
   // this thread's ring: 128 bytes; piece q at ((q ^ lane) & 7) * 16, half-word h (32 stream
   // bits, the HIGH half of a 64-bit word first) at ((4 * h) ^ cx) & 124
-  unsigned a_ring = a_lut + (unsigned)ring_tab_bytes<OUT>(nsub) + (wib * lanes + lane) * (RING * 16u);
+  unsigned a_ring = a_lut + (unsigned)ring_tab_bytes<OUT>(dict, nsub) + (wib * lanes + lane) * (RING * 16u);
   unsigned cx = 4u ^ ((lane & 7u) << 4);
   asm volatile("mov.u32 %0, %0;" : "+r"(a_sub));
   asm volatile("mov.u32 %0, %0;" : "+r"(a_ring));
@@ -482,7 +488,7 @@ decode_ring_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__
   };
   // a codeword longer than RL_BITS + RL2_BITS bits: symbol and length
   auto rare = [&](unsigned win, unsigned &l) -> unsigned {
-    unsigned r = ring_walk(win, a_t32, decodebook, dict);
+    unsigned r = ring_walk(win, a_t32, a_key, dict);
     if (r == ~0u) {
       // more than 32 bits: from global memory, and the reader restarts behind it
       const u64 bitpos = (u64)(hb / 4 - 3) * 32 + o;

@@ -22,6 +22,26 @@
 
 namespace thomas_stream {
 
+// x / b of the backward sweep.  fp32: the division written out as in thomas_tma.cuh
+// (mgb_tma::div_by: the same instructions on the same operands as the compiler's
+// division, bit-identical inside the guarded range) with the part that depends on b
+// alone - reciprocal and its refinement - off the dependent chain of the recurrence, and
+// the range guard as a plain branch to the exact division (never taken on sane data).
+__device__ __forceinline__ float div_chain(float x, float b) {
+  const float y = mgb_tma::refined_rcp(b);
+  const bool b_ok = mgb_tma::rcp_in_range(b);
+  const float ax = fabsf(x);
+  const bool oor = !b_ok || !(ax < 1.1529215e18f) || (ax <= 8.6736174e-19f && ax != 0.0f);
+  const float q0 = __fmul_rn(x, y);
+  const float r = __fmaf_rn(-b, q0, x);
+  float q = __fmaf_rn(y, r, q0);
+  q = ax == 0.0f ? x : q;
+  if (oor)
+    q = x / b;
+  return q;
+}
+__device__ __forceinline__ double div_chain(double x, double b) { return x / b; }
+
 constexpr int LINES = 128; // lines (= threads) per block
 // columns per tile: 256 bytes of a line per access
 template <typename T> struct Tile { static constexpr int W = 256 / (int)sizeof(T); };
@@ -113,12 +133,12 @@ thomas_stream_kernel(T *__restrict__ x, int n, long long lines, const T *__restr
     if (cn == TW) {
 #pragma unroll
       for (int k = TW - 1; k >= 0; k--) {
-        prev = (row[k] - __ldg(am + c0 + k + 1) * prev) / __ldg(bm + c0 + k + 1);
+        prev = div_chain(row[k] - __ldg(am + c0 + k + 1) * prev, __ldg(bm + c0 + k + 1));
         row[k] = prev;
       }
     } else {
       for (int k = cn - 1; k >= 0; k--) {
-        prev = (row[k] - __ldg(am + c0 + k + 1) * prev) / __ldg(bm + c0 + k + 1);
+        prev = div_chain(row[k] - __ldg(am + c0 + k + 1) * prev, __ldg(bm + c0 + k + 1));
         row[k] = prev;
       }
     }

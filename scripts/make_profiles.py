@@ -11,7 +11,8 @@ FAM = [("norm_partial", "norm"), ("coef3d", "coef"), ("masstrans3d", "mass_trans
        ("thomas_smem", "thomas_contig"),
        ("thomas_strided", "thomas_strided"), ("restore3d", "restore"), ("quantize_linear", "quantize_hist"),
        ("codebook", "codebook"), ("chunk_bits", "chunk_bits"), ("encode_kernel", "encode"), ("encode_serial", "encode"),
-       ("decode_fast", "decode"), ("decode_serial", "decode"), ("sort_outliers", "outlier_sort")]
+       ("decode_fast", "decode"), ("decode_serial", "decode"), ("decode_ring", "decode"), ("thomas_stream", "thomas_contig"),
+       ("sort_outliers", "outlier_sort")]
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
@@ -28,7 +29,7 @@ def to_bytes(v, unit):
 def to_us(v, unit):
     f = float(v.replace(",", ""))
     return f * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}[unit]
-traffic, md = {}, [f"# {OUT}: `ncu --set full --clock-control none` of the largest launch of every kernel family",
+traffic, sections, md = {}, {}, [f"# {OUT}: `ncu --set full --clock-control none` of the largest launch of every kernel family",
                    "", TITLE, ""]
 for rep in REPS:
     # a report, or the `ncu -i report --page raw --csv` export of one (made on the GPU box
@@ -59,12 +60,15 @@ for rep in REPS:
                         "dram_gbs_under_ncu": (rd + wr) / us / 1e3,
                         "issue_active_pct": float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
                         "registers": int(d["launch__registers_per_thread"]), "source": rep + ".ncu-rep"}
-        md.append(f"## {fam}: `{d['Kernel Name'][:100]}`  grid {d.get('Grid Size')} block {d.get('Block Size')}\n")
-        md.append("| metric | value | unit |\n|---|---:|---|")
+        sec = [f"## {fam}: `{d['Kernel Name'][:100]}`  grid {d.get('Grid Size')} block {d.get('Block Size')}\n",
+               "| metric | value | unit |\n|---|---:|---|"]
         for k in KEYS:
             if k in d and d[k] != "":
-                md.append(f"| {k} | {d[k]} | {u[k]} |")
-        md.append("")
+                sec.append(f"| {k} | {d[k]} | {u[k]} |")
+        sec.append("")
+        sections[fam] = sec  # the longest launch of the family so far
+for fam in traffic:
+    md += sections[fam]
 json.dump(traffic, open(os.path.join(ROOT, "profiles", OUT + "_traffic.json"), "w"), indent=1)
 open(os.path.join(ROOT, "profiles", OUT + "_kernels.md"), "w").write("\n".join(md) + "\n")
 for f, t in traffic.items():

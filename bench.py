@@ -109,6 +109,40 @@ def field_torch(shape, device, seed=SEED, plane0=0, full_n0=None):
     return out
 
 
+def host_link(torch, dist, world, dev, h_src, h_dst):
+    """Pinned-memory copy rates with every rank copying at the same time: H2D, D2H and both
+    directions together (up to 1 GiB each, max time over ranks)."""
+    n = min(h_src.numel(), h_dst.numel(), 1 << 28)
+    src, dst = h_src.view(-1)[:n], h_dst.view(-1)[:n]
+    d_a = torch.empty(n, dtype=torch.float32, device=dev)
+    d_b = torch.zeros(n, dtype=torch.float32, device=dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    out = {}
+    for kind in ("h2d", "d2h", "both"):
+        def once():
+            if kind in ("h2d", "both"):
+                with torch.cuda.stream(s1):
+                    d_a.copy_(src, non_blocking=True)
+            if kind in ("d2h", "both"):
+                with torch.cuda.stream(s2):
+                    dst.copy_(d_b, non_blocking=True)
+        once()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            once()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        out[kind] = round(n * 4 * (2 if kind == "both" else 1) * world / float(dt) / 1e9, 1)
+    out["unit"] = "GB/s, all ranks together"
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -493,9 +527,17 @@ def main():
     launches0 = mg.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    # The K steps are timed as a whole on every rank (CUDA events, barrier + synchronize on
+    # both sides) and the MAX over ranks is the job's time.  The two phases are timed per
+    # step as well, but only to split that time: ranks meet once per step (in the norm
+    # all-reduce of the compression), so a rank whose sub-domain decodes faster spends the
+    # difference WAITING inside its next compression - per-phase maxima over ranks would
+    # count that wait twice.  compress_ms / decompress_ms are therefore means over ranks
+    # (their sum is the step time of every rank), scaled to the job's time.
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     tc = td = 0.0
     barrier()
+    ev[3].record()
     for _ in range(K):
         ev[0].record()
         r = one_compress()
@@ -505,7 +547,9 @@ def main():
         torch.cuda.synchronize()
         tc += ev[0].elapsed_time(ev[1])
         td += ev[1].elapsed_time(ev[2])
+    ev[4].record()
     barrier()
+    t_all = ev[3].elapsed_time(ev[4]) / K
     clocks = sampler.stop()
     launches = mg.launch_count() - launches0
     tc /= K
@@ -514,10 +558,17 @@ def main():
     for a in range(0, planes, 64):
         err = max(err, float((B["back"][a:a + 64] - B["u"][a:a + 64]).abs().max()))
     norm = r["norm"]
+    phase_max = [tc, td]
     if world > 1:
-        t = torch.tensor([tc, td, err], dtype=torch.float64, device=dev)
+        t = torch.tensor([t_all, tc, td, err], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tc, td, err = float(t[0]), float(t[1]), float(t[2])
+        t_all, err = float(t[0]), float(t[3])
+        phase_max = [float(t[1]), float(t[2])]
+        t = torch.tensor([tc, td], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        tc, td = float(t[0]) / world, float(t[1]) / world
+    # split the job's step time in the proportion of the mean phase times
+    tc, td = t_all * tc / (tc + td), t_all * td / (tc + td)
     total_stream = int(r["total"])
     bound = TOL * norm
     value = 2 * total_bytes / ((tc + td) * 1e-3) / 1e9
@@ -537,6 +588,9 @@ def main():
         "compress_gbs": total_bytes / (tc * 1e-3) / 1e9,
         "decompress_gbs": total_bytes / (td * 1e-3) / 1e9,
         "compress_ms": tc, "decompress_ms": td,
+        "phase_ms_max_over_ranks": {"compress": phase_max[0], "decompress": phase_max[1],
+                                    "note": "per-phase maxima include the wait for the slowest rank's previous "
+                                            "phase; they do not add up to ms_per_step"},
         "ratio": total_bytes / total_stream, "stream_bytes": total_stream,
         "max_abs_error": err, "error_bound": bound, "bound_ok": bool(err <= bound),
         "gpu_launches": int(launches), "clocks": clocks,
@@ -603,6 +657,9 @@ def main():
                        "ms_per_step": et * 1e3, "max_abs_error": e2e_err, "steps": ek,
                        "api": "mgb_compress_sharded / mgb_decompress_sharded with pinned host buffers: H2D of "
                               "sub-domain k+1, compute of k and D2H of k-1 overlap on three streams; max over ranks"}
+        # what the host side of the box gives ALL ranks at once (pinned copies of the same
+        # buffers, no codec): the ceiling of e2e
+        line["e2e"]["host_link"] = host_link(torch, dist if world > 1 else None, world, dev, hin, hback)
         del hin, hrec, hback
 
     if rank == 0 and world == 1 and not args.no_c2:

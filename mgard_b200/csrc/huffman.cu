@@ -1266,49 +1266,52 @@ int launch_decoders(mgb_plan *p, const u64 *ddata, u64 total_words, const u64 *b
                     OUT *out, OUT scale, cudaStream_t st) {
   const bool out_vec = ((uintptr_t)out & 31) == 0 && ((size_t)chunk * sizeof(OUT)) % 32 == 0;
   if (nchunk >= serial_min_chunks() && g_ring_decoder && out_vec && dict <= 65536 &&
-      serial::ring_smem_bytes<OUT>(dict, 0, 64) <= 200 * 1024) {
+      serial::ring_smem_bytes<OUT>(dict, 4096, 64) <= 200 * 1024) {
     // thread per chunk, stream through a shared-memory ring (huffman_serial.cuh)
     const size_t budget = 200 * 1024;
     if (!p->d_declut)
-      MGB_CUDA_CHECK(cudaMalloc(&p->d_declut, std::max(serial::ring_tab_bytes<float>(dict, serial::RL2_MAX),
+      MGB_CUDA_CHECK(cudaMalloc(&p->d_declut, std::max(serial::ring_tab_bytes<float>(dict, serial::RL2_MAX_BYTES),
                                                        serial::tab_bytes(dict))));
     static bool configured[64] = {};
     if (mgb_first_use_on_device(configured))
       cudaFuncSetAttribute(serial::decode_ring_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
-    // Threads (= chunks) per block: the chunks of one wave spread evenly over the SMs, k
-    // blocks on each, for the smallest k whose blocks fit (tables + 128 bytes of ring per
-    // thread); what is left of the shared memory goes to second-level tables.
+    // Chunks per block: the chunks of one wave spread evenly over the SMs, k blocks on each,
+    // for the smallest k whose blocks fit (tables + 128 bytes of ring per chunk); what is left
+    // of the shared memory goes to second-level tables.
     const unsigned L = (unsigned)g_ring_lanes; // lanes of a warp that take a chunk
     cudaFuncAttributes fa;
     MGB_CUDA_CHECK(cudaFuncGetAttributes(&fa, serial::decode_ring_kernel<OUT>));
     const unsigned max_thr = std::min(2048u, 65536u / (unsigned)std::max(fa.numRegs, 32) / 32 * 32); // per SM
     const unsigned act_max = serial::RING_T / 32 * L;
+    const size_t sub_min = 16 * 1024; // second-level tables a block should have at least
     unsigned act = act_max, resident = 0;      // chunks per block | blocks per SM
     for (unsigned k = 1; k <= 8; k++) {
       unsigned t = (unsigned)((nchunk + 148ull * k - 1) / (148ull * k));
       t = std::max(2 * L, (t + L - 1) / L * L);
-      if (t <= act_max && t / L * 32 * k <= max_thr && budget / serial::ring_smem_bytes<OUT>(dict, 0, (int)t) >= k) {
+      if (t <= act_max && t / L * 32 * k <= max_thr &&
+          budget / serial::ring_smem_bytes<OUT>(dict, sub_min, (int)t) >= k) {
         act = t;
         resident = k;
         break;
       }
     }
     const size_t base = serial::ring_smem_bytes<OUT>(dict, 0, (int)act);
-    if (base > budget)
+    if (base + 4096 > budget)
       return MGB_FAILURE;
-    // blocks per SM (several waves: as many as fit)
-    const size_t per_sm = resident ? resident : std::max<size_t>(1, std::min<size_t>(budget / base, max_thr / (act / L * 32)));
-    const int nsub = (int)std::min<size_t>(serial::RL2_MAX, (budget / per_sm - base) / (sizeof(typename serial::RingLut<OUT>::entry) << serial::RL2_BITS));
+    // blocks per SM (several waves: as many as fit with the least tables)
+    const size_t per_sm = resident ? resident
+                                   : std::max<size_t>(1, std::min<size_t>(budget / (base + sub_min), max_thr / (act / L * 32)));
+    const unsigned sub_bytes = (unsigned)(std::min<size_t>(serial::RL2_MAX_BYTES, budget / per_sm - base) & ~(size_t)127);
     // warps work in groups of RING_S on L * RING_S chunks: whole groups
     const unsigned threads = act / L * 32;
     const u64 warps = (nchunk + (u64)L * serial::RING_S - 1) / ((u64)L * serial::RING_S) * serial::RING_S;
     const unsigned blocks = (unsigned)((warps + threads / 32 - 1) / (threads / 32));
     MGB_LAUNCH(MGB_K_PARSE, st,
-               (serial::build_ring_lut_kernel<OUT><<<1, 1024, 0, st>>>(decodebook, dict, nsub,
+               (serial::build_ring_lut_kernel<OUT><<<1, 1024, 0, st>>>(decodebook, dict, sub_bytes,
                                                                        (unsigned char *)p->d_declut, scale)));
     MGB_LAUNCH(MGB_K_DECODE, st,
-               (serial::decode_ring_kernel<OUT><<<blocks, threads, serial::ring_smem_bytes<OUT>(dict, nsub, (int)act), st>>>(
-                   ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict, nsub, (int)L,
+               (serial::decode_ring_kernel<OUT><<<blocks, threads, serial::ring_smem_bytes<OUT>(dict, sub_bytes, (int)act), st>>>(
+                   ddata, total_words, bits, woff, nchunk, chunk, n, decodebook, dict, sub_bytes, (int)L,
                    (const unsigned char *)p->d_declut, out, scale)));
     MGB_CUDA_CHECK(cudaGetLastError());
     return MGB_SUCCESS;
@@ -1317,7 +1320,7 @@ int launch_decoders(mgb_plan *p, const u64 *ddata, u64 total_words, const u64 *b
     // thread per chunk (huffman_serial.cuh)
     const size_t tabb = serial::tab_bytes(dict);
     if (!p->d_declut)
-      MGB_CUDA_CHECK(cudaMalloc(&p->d_declut, std::max(tabb, serial::ring_tab_bytes<float>(dict, serial::RL2_MAX))));
+      MGB_CUDA_CHECK(cudaMalloc(&p->d_declut, std::max(tabb, serial::ring_tab_bytes<float>(dict, serial::RL2_MAX_BYTES))));
     static bool configured[64] = {};
     if (mgb_first_use_on_device(configured)) {
       cudaFuncSetAttribute(serial::decode_serial_kernel<OUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

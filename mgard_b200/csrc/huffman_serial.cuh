@@ -260,43 +260,47 @@ decode_serial_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *
 // codewords throughout) would otherwise share a warp.
 // Requires 32-byte aligned chunk starts in `out` (8 values per store).
 constexpr int RL_BITS = 12;
-constexpr int RL2_BITS = 8;        // second-level tables: RL2_BITS more bits
+constexpr int RL2_BITS = 8;        // second-level tables: up to RL2_BITS more bits
+constexpr int RL2_SHALLOW = 4;     // ... or RL2_SHALLOW where no codeword of the prefix needs more
 constexpr int RING = 8;            // 16-byte pieces per thread
-constexpr int RL2_MAX = 96;        // second-level tables at most
+constexpr size_t RL2_MAX_BYTES = 160 * 1024; // second-level tables at most
 
 template <typename OUT> struct RingLut { typedef unsigned entry; };
 template <> struct RingLut<float> { typedef uint2 entry; };
 
-// Tables (E = table entry): lut[1 << RL_BITS] | t32[36] | b32[36] | lstart[36] | pad[4] | sub[nsub + 1][1 << RL2_BITS] | key16[dict]
-//   lut     first level; a miss (length 0) carries the byte offset of the second-level
-//           table of its prefix x: table x + 1 for x < nsub, else table 0 (all misses)
-//   sub     second level, same entries, for codes of up to RL_BITS + RL2_BITS bits, by the
-//           RL2_BITS bits that follow the prefix; length 0: longer
+// Tables (E = table entry): lut[1 << RL_BITS] | t32[36] | b32[36] | lstart[36] | pad[4] | key16[dict] | sub[sub_bytes]
+//   lut     first level; a miss (length 0) carries where its prefix continues: byte offset of
+//           a second-level table in `sub` and 32 - d, d = number of index bits of that table
+//           (RL2_BITS, RL2_SHALLOW if every codeword of the prefix has at most RL_BITS +
+//           RL2_SHALLOW bits, 0 for the one-entry table 0 that misses: no room left)
+//   sub     second level, same entries, indexed by the d bits that follow the prefix
 //   t32[l]  first code of length l left aligned in 32 bits (0xffffffff: none), b32[l] =
 //           entry[l] - first[l], lstart[z] = shortest length a 32-bit window with z leading
 //           zeros can have: where the canonical walk starts; key16: the symbols in canonical order
 __host__ __device__ inline size_t ring_key_bytes(int dict) { return ((size_t)dict * 2 + 127) & ~(size_t)127; }
-template <typename OUT> __host__ __device__ inline size_t ring_tab_bytes(int dict, int nsub) {
-  return sizeof(typename RingLut<OUT>::entry) * ((size_t)(1 << RL_BITS) + ((size_t)(nsub + 1) << RL2_BITS)) + 112 * 4 +
-         ring_key_bytes(dict);
+template <typename OUT> __host__ __device__ inline size_t ring_tab_bytes(int dict, size_t sub_bytes) {
+  return (sizeof(typename RingLut<OUT>::entry) << RL_BITS) + 112 * 4 + ring_key_bytes(dict) + sub_bytes;
 }
-template <typename OUT> __host__ __device__ inline size_t ring_smem_bytes(int dict, int nsub, int slots) {
-  return ring_tab_bytes<OUT>(dict, nsub) + (size_t)RING * 16 * slots;
+template <typename OUT> __host__ __device__ inline size_t ring_smem_bytes(int dict, size_t sub_bytes, int slots) {
+  return ring_tab_bytes<OUT>(dict, sub_bytes) + (size_t)RING * 16 * slots;
 }
 
 template <typename OUT>
 __global__ void __launch_bounds__(1024)
-build_ring_lut_kernel(const u64 *__restrict__ decodebook, int dict, int nsub, unsigned char *__restrict__ g,
+build_ring_lut_kernel(const u64 *__restrict__ decodebook, int dict, unsigned sub_bytes, unsigned char *__restrict__ g,
                       OUT scale) {
   typedef typename RingLut<OUT>::entry E;
   __shared__ u64 s_first[64], s_entry[64];
-  const int tid = threadIdx.x;
+  __shared__ unsigned char s_depth[1 << RL_BITS]; // index bits of the prefix's second-level table (0: a hit)
+  __shared__ unsigned s_off[1 << RL_BITS];        // its byte offset in `sub`
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < 128)
     (tid < 64 ? s_first : s_entry)[tid & 63] = decodebook[tid];
   __syncthreads();
   E *lut = reinterpret_cast<E *>(g);
   unsigned *t32 = reinterpret_cast<unsigned *>(lut + (1 << RL_BITS)), *b32 = t32 + 36, *lstart = b32 + 36;
-  E *sub = reinterpret_cast<E *>(lstart + 40);
+  uint16_t *key16 = reinterpret_cast<uint16_t *>(lstart + 40);
+  unsigned char *sub = reinterpret_cast<unsigned char *>(key16) + ring_key_bytes(dict);
   auto t32_of = [&](int l) -> unsigned {
     const bool valid = l >= 1 && l <= 32 && s_first[l] != ~0ull && (s_first[l] >> l) == 0;
     return valid ? (unsigned)(s_first[l] << (32 - l)) : 0xffffffffu;
@@ -311,6 +315,8 @@ build_ring_lut_kernel(const u64 *__restrict__ decodebook, int dict, int nsub, un
       l++;
     lstart[tid] = (unsigned)l;
   }
+  for (int k = tid; k < dict; k += 1024)
+    key16[k] = (uint16_t)decodebook[128 + k];
   int lmin = 1;
   while (lmin < 63 && s_first[lmin] == ~0ull)
     lmin++;
@@ -327,24 +333,97 @@ build_ring_lut_kernel(const u64 *__restrict__ decodebook, int dict, int nsub, un
     }
     return 0u;
   };
-  // table entry of a codeword (e != 0) or of a miss that continues at byte offset `off`
-  auto entry_of = [&](unsigned e, unsigned off) -> E {
+  // table entry of a codeword (e != 0), or of a miss that continues in the table of 1 << d
+  // entries at byte offset `off`
+  auto entry_of = [&](unsigned e, unsigned off, unsigned d) -> E {
     if constexpr (sizeof(E) == 8) {
       const float val = scale * (float)((int)(e >> 8) - half);
-      return (e & 0xffu) ? make_uint2(__float_as_uint(val), e & 0xffu) : make_uint2(off, 0u);
+      return (e & 0xffu) ? make_uint2(__float_as_uint(val), e & 0xffu) : make_uint2(off | ((32 - d) << 24), 0u);
     } else {
-      return (e & 0xffu) ? e : (off << 8);
+      return (e & 0xffu) ? e : (((off >> 2) | ((32 - d) << 18)) << 8);
     }
   };
+  // which prefixes miss, and how deep their tables have to be (a warp per prefix)
   for (int x = tid; x < (1 << RL_BITS); x += 1024)
-    lut[x] = entry_of(lookup((unsigned)x, RL_BITS), (x < nsub ? (unsigned)x + 1 : 0u) * (unsigned)(sizeof(E) << RL2_BITS));
-  for (int x = tid; x < ((nsub + 1) << RL2_BITS); x += 1024) {
-    const unsigned e = x < (1 << RL2_BITS) ? 0u : lookup((unsigned)x - (1u << RL2_BITS), RL_BITS + RL2_BITS);
-    sub[x] = entry_of((e & 0xffu) > RL_BITS ? e : 0u, 0u); // (shorter: never looked up here)
+    s_depth[x] = (lookup((unsigned)x, RL_BITS) & 0xffu) ? 0 : 0xff;
+  __syncthreads();
+  for (int x = warp; x < (1 << RL_BITS); x += 32) {
+    if (s_depth[x] != 0xff)
+      continue;
+    bool deep = false;
+    for (int j = lane; j < (1 << RL2_BITS); j += 32) {
+      const unsigned len = lookup(((unsigned)x << RL2_BITS) | (unsigned)j, RL_BITS + RL2_BITS) & 0xffu;
+      deep = deep || len == 0 || len > RL_BITS + RL2_SHALLOW;
+    }
+    deep = __any_sync(0xffffffffu, deep);
+    __syncwarp();
+    if (lane == 0)
+      s_depth[x] = deep ? RL2_BITS : RL2_SHALLOW;
   }
-  uint16_t *key16 = reinterpret_cast<uint16_t *>(sub + ((size_t)(nsub + 1) << RL2_BITS));
-  for (int k = tid; k < dict; k += 1024)
-    key16[k] = (uint16_t)decodebook[128 + k];
+  __syncthreads();
+  // offsets (block-wide exclusive sum of the table sizes, four prefixes per thread): table 0
+  // is the single entry that misses; a prefix whose table does not fit gets it
+  {
+    __shared__ unsigned s_warp[32];
+    unsigned size[4], mine = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const unsigned d = s_depth[4 * tid + q];
+      size[q] = d ? (unsigned)sizeof(E) << d : 0u;
+      mine += size[q];
+    }
+    unsigned incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o)
+        incl += t;
+    }
+    if (lane == 31)
+      s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = s_warp[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o)
+          wi += t;
+      }
+      s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    unsigned run = 16 + s_warp[warp] + incl - mine;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (size[q]) {
+        if (run + size[q] <= sub_bytes) {
+          s_off[4 * tid + q] = run;
+        } else {
+          s_off[4 * tid + q] = 0;
+          s_depth[4 * tid + q] = 0xfe; // marks "table 0"
+        }
+      }
+      run += size[q];
+    }
+  }
+  __syncthreads();
+  if (tid < 16 / (int)sizeof(E))
+    reinterpret_cast<E *>(sub)[tid] = entry_of(0u, 0u, 0u);
+  for (int x = tid; x < (1 << RL_BITS); x += 1024) {
+    const unsigned d = s_depth[x];
+    lut[x] = d == 0 ? entry_of(lookup((unsigned)x, RL_BITS), 0u, 0u) : d == 0xfe ? entry_of(0u, 0u, 0u) : entry_of(0u, s_off[x], d);
+  }
+  for (int x = warp; x < (1 << RL_BITS); x += 32) {
+    const unsigned d = s_depth[x];
+    if (d == 0 || d == 0xfe)
+      continue;
+    E *tab = reinterpret_cast<E *>(sub + s_off[x]);
+    for (int j = lane; j < (1 << d); j += 32) {
+      const unsigned e = lookup(((unsigned)x << d) | (unsigned)j, RL_BITS + (int)d);
+      tab[j] = entry_of((e & 0xffu) > RL_BITS ? e : 0u, 0u, 0u); // a miss here: longer than RL_BITS + d bits
+    }
+  }
 }
 
 // helpers of the ring decoder's cold paths (inlined: a call in the kernel makes the compiler
@@ -393,7 +472,7 @@ template <typename OUT>
 __global__ void __launch_bounds__(RING_T)
 decode_ring_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__restrict__ bits,
                    const u64 *__restrict__ woff, u64 nchunk, int chunk, u64 n,
-                   const u64 *__restrict__ decodebook, int dict, int nsub, int lanes,
+                   const u64 *__restrict__ decodebook, int dict, unsigned sub_bytes, int lanes,
                    const unsigned char *__restrict__ gtab, OUT *__restrict__ out, OUT scale) {
   typedef typename RingLut<OUT>::entry E;
   constexpr bool VAL_LUT = sizeof(E) == 8; // the tables hold dequantized values
@@ -402,7 +481,7 @@ decode_ring_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__
   {
     const uint4 *g4 = reinterpret_cast<const uint4 *>(gtab);
     uint4 *s4 = reinterpret_cast<uint4 *>(s_tab);
-    const int n16 = (int)(ring_tab_bytes<OUT>(dict, nsub) / 16);
+    const int n16 = (int)(ring_tab_bytes<OUT>(dict, sub_bytes) / 16);
     for (int i = threadIdx.x; i < n16; i += blockDim.x)
       s4[i] = g4[i];
   }
@@ -423,11 +502,11 @@ decode_ring_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__
   unsigned a_lut = (unsigned)__cvta_generic_to_shared(s_tab);
   asm volatile("mov.u32 %0, %0;" : "+r"(a_lut));
   const unsigned a_t32 = a_lut + (unsigned)(sizeof(E) << RL_BITS);
-  unsigned a_sub = a_t32 + 112 * 4;
-  const unsigned a_key = a_sub + (unsigned)(sizeof(E) * ((size_t)(nsub + 1) << RL2_BITS));
+  const unsigned a_key = a_t32 + 112 * 4;
+  unsigned a_sub = a_key + (unsigned)ring_key_bytes(dict);
   // this thread's ring: 128 bytes; piece q at ((q ^ lane) & 7) * 16, half-word h (32 stream
   // bits, the HIGH half of a 64-bit word first) at ((4 * h) ^ cx) & 124
-  unsigned a_ring = a_lut + (unsigned)ring_tab_bytes<OUT>(dict, nsub) + (wib * lanes + lane) * (RING * 16u);
+  unsigned a_ring = a_lut + (unsigned)ring_tab_bytes<OUT>(dict, sub_bytes) + (wib * lanes + lane) * (RING * 16u);
   unsigned cx = 4u ^ ((lane & 7u) << 4);
   asm volatile("mov.u32 %0, %0;" : "+r"(a_sub));
   asm volatile("mov.u32 %0, %0;" : "+r"(a_ring));
@@ -514,20 +593,23 @@ decode_ring_kernel(const u64 *__restrict__ ddata, u64 total_words, const u64 *__
     const unsigned win = __funnelshift_l(w1, w0, o);
     unsigned l, e0;
     OUT v;
-    // first level, and the second one predicated on its miss (e0 = offset of the table)
-    const unsigned x2 = (win >> (32 - RL_BITS - RL2_BITS - ES)) & (((1u << RL2_BITS) - 1) << ES);
+    // first level, and the second one predicated on its miss: the entry then holds the
+    // offset of the prefix's table and 32 - (its index bits); PTX shifts by 32 give 0
+    const unsigned w12 = win << RL_BITS;
+    unsigned idx;
     if constexpr (VAL_LUT) {
       asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e0), "=r"(l) : "r"(a_lut + ((win >> (32 - RL_BITS)) << 3)));
+      asm("shr.u32 %0, %1, %2;" : "=r"(idx) : "r"(w12), "r"(e0 >> 24));
       asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, 0;\n\t@p ld.shared.v2.u32 {%0, %1}, [%2];\n\t}"
           : "+r"(e0), "+r"(l)
-          : "r"(a_sub + e0 + x2));
+          : "r"(a_sub + (e0 & 0xffffffu) + (idx << 3)));
       v = __uint_as_float(e0);
     } else {
       e0 = lds_u32(a_lut + ((win >> (32 - RL_BITS)) << 2));
-      asm("{\n\t.reg .pred p;\n\t.reg .u32 t;\n\tand.b32 t, %0, 255;\n\tsetp.eq.u32 p, t, 0;\n\tshr.u32 t, %0, 8;\n\t"
-          "add.u32 t, t, %1;\n\t@p ld.shared.u32 %0, [t];\n\t}"
+      asm("shr.u32 %0, %1, %2;" : "=r"(idx) : "r"(w12), "r"(e0 >> 26));
+      asm("{\n\t.reg .pred p;\n\t.reg .u32 t;\n\tand.b32 t, %0, 255;\n\tsetp.eq.u32 p, t, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}"
           : "+r"(e0)
-          : "r"(a_sub + x2));
+          : "r"(a_sub + ((e0 >> 6) & 0xffffcu) + (idx << 2)));
       l = e0 & 0xffu;
       v = value(e0 >> 8);
     }

@@ -15,6 +15,7 @@ ap.add_argument("shapes", nargs="+")
 ap.add_argument("--serial", default="0,-1")
 ap.add_argument("--tol", type=float, default=1e-3)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--plane0", type=int, default=0, help="first plane of the slab in the domain")
 ap.add_argument("--full-n0", type=int, default=0, help="planes of the domain the shape is a slab of (bench field of C5: 2049)")
 a = ap.parse_args()
 L = _lib.lib()
@@ -35,7 +36,7 @@ def families(reps):
 
 for sh in a.shapes:
     shape = tuple(int(x) for x in sh.split(","))
-    u = bench.field_torch(shape, dev, full_n0=a.full_n0 or None)
+    u = bench.field_torch(shape, dev, plane0=a.plane0, full_n0=a.full_n0 or None)
     p = mg.Plan(shape, np.float32)
     for serial in [int(x) for x in a.serial.split(",")]:
         mg.tune(mg.TUNE_SERIAL_MIN_CHUNKS, serial)

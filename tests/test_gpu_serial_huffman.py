@@ -142,3 +142,53 @@ def test_serial_decoder_survives_corrupted_chunk_fields(env):
     # the device is still healthy
     back = p.decompress(payload, mo.REL, 1e-3, np.inf, norm).cpu().numpy()
     assert np.abs(back - u).max() <= 1e-3 * np.abs(u).max()
+
+
+def test_ring_decoder_long_codewords(env):
+    """Fibonacci symbol counts give a code whose lengths run from 1 to beyond 32 bits: every
+    level of the ring decoder (first table, second-level tables of both depths, canonical
+    walk on the window, codewords of more than 32 bits from global memory) decodes what the
+    encoder wrote, and the first formulation of the decoder agrees."""
+    torch, mg, d = env
+    counts = [1, 1]
+    while len(counts) < 36:
+        counts.append(counts[-1] + counts[-2])
+    rng = np.random.default_rng(11)
+    sym = np.repeat(np.arange(36, dtype=np.int64), counts)
+    rng.shuffle(sym)
+    cfg = mg.Config()
+    cfg.huff_dict_size, cfg.huff_block_size = 64, 20480
+    p = mg.Plan((sym.size,), np.float32, config=cfg)
+    ds = torch.from_numpy(sym.astype(np.uint16).view(np.int16)).to(d)
+    hist = torch.from_numpy(np.bincount(sym, minlength=64).astype(np.uint32).view(np.int32)).to(d)
+    e = torch.empty(0, dtype=torch.int64, device=d)
+    pay = p.huffman_compress(ds, hist, e, e)
+    cb, _ = p.codebook(hist)
+    lens = (cb.cpu().numpy().view(np.uint64) >> np.uint64(56)).astype(np.int64)
+    assert lens[:36].max() > 32 and lens[:36].min() <= 2
+    outs = []
+    for ring in (1, 0):
+        mg.tune(mg.TUNE_RING_DECODER, ring)
+        back, _, _ = p.huffman_decompress(pay, sym.size)
+        outs.append(back.cpu().numpy().view(np.uint16).copy())
+    mg.tune(mg.TUNE_RING_DECODER, 1)
+    assert np.array_equal(outs[0], sym.astype(np.uint16))
+    assert np.array_equal(outs[1], outs[0])
+
+
+def test_ring_decoder_more_prefixes_than_tables(env):
+    """A nearly flat histogram over 8192 symbols: thousands of 12-bit prefixes continue in a
+    second-level table, far more than shared memory holds - the prefixes left without one
+    are decoded by the canonical walk; values equal the first formulation's."""
+    torch, mg, d = env
+    rng = np.random.default_rng(5)
+    n = 20480 * 600
+    sym = rng.integers(0, 8192, n).astype(np.int64)
+    sym[rng.random(n) < 0.3] = 4096  # one short codeword among 13 / 14-bit ones
+    p = mg.Plan((n,), np.float32)
+    ds = torch.from_numpy(sym.astype(np.uint16).view(np.int16)).to(d)
+    hist = torch.from_numpy(np.bincount(sym, minlength=8192).astype(np.uint32).view(np.int32)).to(d)
+    e = torch.empty(0, dtype=torch.int64, device=d)
+    pay = p.huffman_compress(ds, hist, e, e)
+    back, _, _ = p.huffman_decompress(pay, n)
+    assert np.array_equal(back.cpu().numpy().view(np.uint16), sym.astype(np.uint16))

@@ -342,8 +342,10 @@ int mgb_cpu_decompress(const void *in, size_t in_size, void **out, int *ndim,
  * encoded / decoded by the thread-per-chunk kernels, smaller ones by the
  * block-per-chunk kernels (0: always thread-per-chunk, negative: never).
  * MGB_TUNE_RING_DECODER: 1 (default): the thread-per-chunk decoder reads its bit
- * stream through a shared-memory ring; 0: the register-queue formulation. */
-enum { MGB_TUNE_SERIAL_MIN_CHUNKS = 0, MGB_TUNE_RING_DECODER = 1 };
+ * stream through a shared-memory ring; 0: the register-queue formulation.
+ * MGB_TUNE_SUB_ENCODER: 1 (default): eight threads encode a chunk (when its size is a
+ * multiple of 64 symbols); 0: one thread per chunk. */
+enum { MGB_TUNE_SERIAL_MIN_CHUNKS = 0, MGB_TUNE_RING_DECODER = 1, MGB_TUNE_SUB_ENCODER = 2 };
 int mgb_tune(int key, long long value);
 
 /* kernel launch counter (bench.py's gpu_launches) */

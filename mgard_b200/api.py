@@ -177,6 +177,7 @@ def unpin_memory(array):
 
 TUNE_SERIAL_MIN_CHUNKS = 0
 TUNE_RING_DECODER = 1
+TUNE_SUB_ENCODER = 2
 
 
 def tune(key, value):

@@ -1256,6 +1256,7 @@ u64 g_serial_min_chunks = getenv("MGB_SERIAL_MIN_CHUNKS") ? strtoull(getenv("MGB
 u64 serial_min_chunks() { return g_serial_min_chunks; }
 // the ring formulation of the thread-per-chunk decoder (MGB_TUNE_RING_DECODER; 0: first formulation)
 bool g_ring_decoder = !getenv("MGB_NO_RING_DECODER");
+bool g_sub_encoder = !getenv("MGB_NO_SUB_ENCODER");
 int g_ring_lanes = getenv("MGB_RING_LANES") ? std::min(32, std::max(1, atoi(getenv("MGB_RING_LANES")))) : 32;
 
 // Launches the decoders for one serialised block.  OUT = uint16_t: symbols;
@@ -1455,6 +1456,7 @@ int ensure_huff_workspace(mgb_plan *p) {
   MGB_CUDA_CHECK(cudaMalloc(&p->d_decodebook, (128 + dict) * sizeof(u64)));
   MGB_CUDA_CHECK(cudaMalloc(&p->d_chunk_bits, nchunk * sizeof(u64)));
   MGB_CUDA_CHECK(cudaMalloc(&p->d_chunk_woff, (nchunk + 1) * sizeof(u64)));
+  MGB_CUDA_CHECK(cudaMalloc(&p->d_chunk_sub, nchunk * serial::ESUB * sizeof(unsigned)));
   MGB_CUDA_CHECK(cudaMalloc(&p->d_scalars, 24 * sizeof(u64))); // [16..17]: grid barrier of the outlier sort
   MGB_CUDA_CHECK(cudaMemset(p->d_scalars, 0, 24 * sizeof(u64)));
   size_t cbw = npow2 * sizeof(u64) + (size_t)dict * (9 * 4 + 8) + 256;
@@ -1474,6 +1476,9 @@ extern "C" int mgb_tune(int key, long long value) {
     return MGB_SUCCESS;
   case MGB_TUNE_RING_DECODER:
     g_ring_decoder = value != 0;
+    return MGB_SUCCESS;
+  case MGB_TUNE_SUB_ENCODER:
+    g_sub_encoder = value != 0;
     return MGB_SUCCESS;
   default:
     return MGB_BAD_ARGUMENT;
@@ -1542,9 +1547,20 @@ int mgb_huffman_compress_async(mgb_plan *p, const uint16_t *d_sym, uint64_t n,
   const u64 fixed = 8 + 4 + 4 + 8 + 16 * nchunk + 8 + (1024 + 8ull * dict) + 8;
   u64 *scal = (u64 *)p->d_scalars;
   unsigned gb = (unsigned)std::min<u64>(nchunk, 148 * 8);
-  MGB_LAUNCH(MGB_K_CHUNK_BITS, st,
-             (chunk_bits_kernel<<<gb, 256, dict, st>>>(d_sym, n, chunk, p->d_codebook, dict,
-                                                      (u64 *)p->d_chunk_bits)));
+  // thread-per-chunk kernels, eight threads per chunk when the chunk divides that way
+  // (huffman_serial.cuh); MGB_NO_SUB_ENCODER / MGB_TUNE_SUB_ENCODER = 0: one thread per chunk
+  // (eight threads per chunk reach the thread count that pays with an eighth of the chunks)
+  const bool serial_enc = nchunk >= serial_min_chunks();
+  const bool sub_enc = g_sub_encoder && chunk >= 1024 && chunk % (8 * serial::ESUB) == 0 && (size_t)dict <= 65536 &&
+                       (serial_enc || (serial_min_chunks() != ~0ull && nchunk * serial::ESUB >= serial_min_chunks()));
+  if (sub_enc)
+    MGB_LAUNCH(MGB_K_CHUNK_BITS, st,
+               (serial::chunk_bits_sub_kernel<<<gb, 256, dict, st>>>(d_sym, n, chunk, p->d_codebook, dict,
+                                                                     (u64 *)p->d_chunk_bits, p->d_chunk_sub)));
+  else
+    MGB_LAUNCH(MGB_K_CHUNK_BITS, st,
+               (chunk_bits_kernel<<<gb, 256, dict, st>>>(d_sym, n, chunk, p->d_codebook, dict,
+                                                        (u64 *)p->d_chunk_bits)));
   MGB_LAUNCH(MGB_K_CHUNK_SCAN, st,
              (chunk_scan_kernel<<<1, 1024, 0, st>>>((u64 *)p->d_chunk_bits, nchunk,
                                                    (u64 *)p->d_chunk_woff, scal, fixed, cap,
@@ -1555,7 +1571,22 @@ int mgb_huffman_compress_async(mgb_plan *p, const uint16_t *d_sym, uint64_t n,
   // the codebook is read through L1 (measured faster than a shared-memory copy,
   // which limits the kernel to two blocks per SM); MGB_ENC_SHARED_CB=1 for A/B runs
   static const bool enc_shared = getenv("MGB_ENC_SHARED_CB") != nullptr;
-  if (nchunk >= serial_min_chunks()) {
+  if (sub_enc) {
+    const unsigned blocks = (unsigned)((nchunk * serial::ESUB + serial::ESUB_T - 1) / serial::ESUB_T);
+    const size_t smem = (size_t)dict * 8;
+    if (smem <= 72 * 1024) {
+      static bool configured[64] = {};
+      if (mgb_first_use_on_device(configured))
+        cudaFuncSetAttribute(serial::encode_sub_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+      MGB_LAUNCH(MGB_K_ENCODE, st,
+                 (serial::encode_sub_kernel<true><<<blocks, serial::ESUB_T, smem, st>>>(
+                     d_sym, n, chunk, p->d_codebook, dict, (u64 *)p->d_chunk_woff, p->d_chunk_sub, scal, ddata)));
+    } else {
+      MGB_LAUNCH(MGB_K_ENCODE, st,
+                 (serial::encode_sub_kernel<false><<<blocks, serial::ESUB_T, 0, st>>>(
+                     d_sym, n, chunk, p->d_codebook, dict, (u64 *)p->d_chunk_woff, p->d_chunk_sub, scal, ddata)));
+    }
+  } else if (serial_enc) {
     // thread per chunk (huffman_serial.cuh); codebook in shared memory when it fits
     const unsigned blocks = (unsigned)((nchunk + serial::ES_T - 1) / serial::ES_T);
     const bool vec = ((uintptr_t)d_sym & 31) == 0 && ((size_t)chunk * 2) % 32 == 0;

@@ -744,4 +744,160 @@ encode_serial_kernel(const uint16_t *__restrict__ sym, u64 n, int chunk, const u
     *dst = acc;
 }
 
+// ---------------------- encoder, eight threads per chunk --------------------
+// A chunk's bit string is sequential only because every codeword starts where the one
+// before it ends; with the bit count of each EIGHTH of a chunk known (a by-product of
+// the pass that sizes the chunks) eight threads write one chunk, each the words its
+// eighth ends in.  A word that straddles two eighths belongs to the later thread, which
+// first re-encodes the few symbols before its start whose codewords reach into that word
+// (no atomics, no zero-filled output).  Eight times the threads of encode_serial_kernel:
+// the latencies of one chunk's chain are hidden by the other chains of the SM instead of
+// setting the run time.
+constexpr int ESUB = 8;     // threads per chunk
+constexpr int ESUB_T = 256; // threads per block
+
+// bits of every eighth of every chunk (sub[c * ESUB + q]) and of the chunk (bits[c]);
+// a block per chunk at a time, warp q sums eighth q.  chunk % (8 * ESUB) == 0.
+__global__ void __launch_bounds__(256)
+chunk_bits_sub_kernel(const uint16_t *__restrict__ sym, u64 n, int chunk, const u64 *__restrict__ codebook, int dict,
+                      u64 *__restrict__ bits, unsigned *__restrict__ sub) {
+  extern __shared__ unsigned char s_len[];
+  __shared__ unsigned s_part[ESUB];
+  for (int i = threadIdx.x; i < dict; i += blockDim.x)
+    s_len[i] = (unsigned char)(codebook[i] >> 56);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+  const u64 nchunk = (n - 1) / chunk + 1;
+  const unsigned sublen = (unsigned)chunk / ESUB;
+  for (u64 c = blockIdx.x; c < nchunk; c += gridDim.x) {
+    const u64 lo = c * (u64)chunk;
+    const unsigned cnt = (unsigned)min((u64)chunk, n - lo);
+    const unsigned a = min(cnt, q * sublen), b = min(cnt, (q + 1) * sublen);
+    const uint16_t *base = sym + lo;
+    unsigned total = 0, done = a;
+    if ((((uintptr_t)base) & 15) == 0) {
+      for (unsigned i = a + 8 * lane; i + 8 <= b; i += 256) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base + i));
+        total += s_len[v.x & 0xffffu] + s_len[v.x >> 16] + s_len[v.y & 0xffffu] + s_len[v.y >> 16] +
+                 s_len[v.z & 0xffffu] + s_len[v.z >> 16] + s_len[v.w & 0xffffu] + s_len[v.w >> 16];
+      }
+      done = a + (b - a) / 8 * 8;
+    }
+    for (unsigned i = done + lane; i < b; i += 32)
+      total += s_len[base[i]];
+    for (int o = 16; o > 0; o >>= 1)
+      total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0) {
+      s_part[q] = total;
+      sub[c * ESUB + q] = total;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      u64 t = 0;
+      for (int k = 0; k < ESUB; k++)
+        t += s_part[k];
+      bits[c] = t;
+    }
+    __syncthreads();
+  }
+}
+
+template <bool CB_SHARED>
+__global__ void __launch_bounds__(ESUB_T)
+encode_sub_kernel(const uint16_t *__restrict__ sym, u64 n, int chunk, const u64 *__restrict__ codebook, int dict,
+                  const u64 *__restrict__ woff, const unsigned *__restrict__ sub, const u64 *__restrict__ scal,
+                  u64 *__restrict__ ddata) {
+  extern __shared__ u64 s_cb[];
+  if (scal[2])
+    return; // output too small / outlier overflow: nothing is written
+  if (CB_SHARED) {
+    for (int i = threadIdx.x; i < dict; i += ESUB_T)
+      s_cb[i] = codebook[i];
+    __syncthreads();
+  }
+  const u64 nchunk = (n - 1) / chunk + 1;
+  const u64 gid = (u64)blockIdx.x * ESUB_T + threadIdx.x;
+  const u64 c = gid / ESUB;
+  const unsigned q = (unsigned)(gid % ESUB);
+  if (c >= nchunk)
+    return;
+  const u64 lo = c * (u64)chunk;
+  const unsigned cnt = (unsigned)min((u64)chunk, n - lo), sublen = (unsigned)chunk / ESUB;
+  const unsigned start = min(cnt, q * sublen), end = min(cnt, (q + 1) * sublen);
+  // bit range [S, E) of this eighth inside the chunk; T: bits of the chunk
+  u64 S = 0, T = 0;
+  unsigned mine = 0;
+#pragma unroll
+  for (unsigned k = 0; k < ESUB; k++) {
+    const unsigned b = sub[c * ESUB + k];
+    S += k < q ? b : 0u;
+    mine = k == q ? b : mine;
+    T += b;
+  }
+  if (mine == 0)
+    return; // nothing of this eighth in the stream (beyond the end of the last chunk)
+  const u64 E = S + mine;
+  const bool last = E == T; // the final, partial word of the chunk is this thread's
+  const unsigned w_s = (unsigned)(S >> 6), need = (unsigned)(S & 63);
+  const uint16_t *src = sym + lo;
+  auto cw_of = [&](unsigned s) -> u64 { return CB_SHARED ? s_cb[s] : __ldg(codebook + s); };
+  // the symbols before `start` whose codewords reach into word w_s
+  unsigned i0 = start, back = 0;
+  while (back < need) {
+    i0--;
+    back += (unsigned)(cw_of(src[i0]) >> 56);
+  }
+  const u64 B0 = S - back; // where symbol i0 starts
+  u64 *const base = ddata + woff[c];
+  unsigned wi = (unsigned)(B0 >> 6); // word being filled
+  u64 acc = 0;
+  unsigned fill = (unsigned)(B0 & 63); // bits used in acc (< 64); the ones before B0 are not this thread's to write
+  // as in encode_serial_kernel; a completed word below w_s (the one symbol i0 starts in) is not stored
+  auto put = [&](unsigned s) {
+    const u64 cw = cw_of(s);
+    const unsigned len = (unsigned)(cw >> 56);
+    const u64 code = cw & 0x00ffffffffffffffull;
+    const int sh = 64 - (int)fill - (int)len; // >= 0: the codeword ends inside acc
+    u64 hi1, hi2, lo2;
+    asm("shl.b64 %0, %1, %2;" : "=l"(hi1) : "l"(code), "r"((unsigned)sh));
+    asm("shr.b64 %0, %1, %2;" : "=l"(hi2) : "l"(code), "r"((unsigned)-sh));
+    asm("shl.b64 %0, %1, %2;" : "=l"(lo2) : "l"(code), "r"((unsigned)(64 + sh)));
+    const u64 out = acc | hi1 | hi2;
+    const unsigned nf = fill + len;
+    const unsigned full = nf >= 64;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u64 [%0], %1;\n\t}" ::"l"(base + wi), "l"(out),
+                 "r"(full && wi >= w_s ? 1u : 0u)
+                 : "memory");
+    wi += full;
+    acc = full ? lo2 : out;
+    fill = full ? nf - 64 : nf;
+  };
+  for (unsigned i = i0; i < start; i++)
+    put(src[i]);
+  unsigned i = start;
+  if ((((uintptr_t)(src + start)) & 31) == 0 && end - start >= 16) {
+    auto load16 = [&](unsigned at, unsigned (&w)[8]) {
+      asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                   : "l"(src + at));
+    };
+    unsigned w[8], wn[8];
+    load16(i, w);
+    for (; i + 16 <= end; i += 16) {
+      if (i + 32 <= end)
+        load16(i + 16, wn);
+#pragma unroll
+      for (int k = 0; k < 16; k++)
+        put((w[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        w[k] = wn[k];
+    }
+  }
+  for (; i < end; i++)
+    put(src[i]);
+  if (last && fill)
+    base[wi] = acc;
+}
+
 } // namespace serial

@@ -418,6 +418,7 @@ extern "C" void mgb_plan_destroy(mgb_plan *p) {
   cudaFree(p->d_decodebook);
   cudaFree(p->d_chunk_bits);
   cudaFree(p->d_chunk_woff);
+  cudaFree(p->d_chunk_sub);
   cudaFree(p->d_scalars);
   cudaFree(p->d_oidx);
   cudaFree(p->d_oval);

@@ -65,6 +65,7 @@ struct mgb_plan {
   unsigned long long *d_decodebook = nullptr;
   unsigned long long *d_chunk_bits = nullptr;  // nchunk
   unsigned long long *d_chunk_woff = nullptr;  // nchunk + 1
+  unsigned *d_chunk_sub = nullptr;             // 8 per chunk: bits of every eighth (huffman_serial.cuh)
   unsigned long long *d_scalars = nullptr; // [0] outlier count, [1] total words, ...
   uint64_t *d_oidx = nullptr;
   int64_t *d_oval = nullptr;

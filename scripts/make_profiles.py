@@ -10,7 +10,7 @@ REPS = sys.argv[3:] if len(sys.argv) > 3 else ["r1_final_levels", "r1_final_huff
 FAM = [("norm_partial", "norm"), ("coef3d", "coef"), ("masstrans3d", "mass_trans"), ("thomas_tma", "thomas_contig"),
        ("thomas_smem", "thomas_contig"),
        ("thomas_strided", "thomas_strided"), ("restore3d", "restore"), ("quantize_linear", "quantize_hist"),
-       ("codebook", "codebook"), ("chunk_bits", "chunk_bits"), ("encode_kernel", "encode"), ("encode_serial", "encode"),
+       ("codebook", "codebook"), ("chunk_bits", "chunk_bits"), ("encode_kernel", "encode"), ("encode_serial", "encode"), ("encode_sub", "encode"),
        ("decode_fast", "decode"), ("decode_serial", "decode"), ("decode_ring", "decode"), ("thomas_stream", "thomas_contig"),
        ("sort_outliers", "outlier_sort")]
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",

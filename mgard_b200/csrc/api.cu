@@ -70,7 +70,9 @@ int ensure_lowlevel_workspace(mgb_plan *p) {
   if (rc)
     return rc;
   if (!p->d_coef)
-    MGB_CUDA_CHECK(cudaMalloc(&p->d_coef, p->N * p->tsize));
+    // + 16: the load-vector kernel's bulk copies move whole 16-byte pieces, the last of which
+    // may straddle the end of the array (masstrans3d.cuh)
+    MGB_CUDA_CHECK(cudaMalloc(&p->d_coef, p->N * p->tsize + 16));
   if (!p->d_sym)
     MGB_CUDA_CHECK(cudaMalloc(&p->d_sym, p->N * sizeof(uint16_t) + 64));
   if (!p->d_hist)

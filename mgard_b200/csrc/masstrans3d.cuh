@@ -254,7 +254,10 @@ template <typename T> struct WParams {
   i64 sin[3], sw[3];
   const T *mt[3];
   int ctiles, ftiles, rsegs, per; // per: coarse r indices per segment
-  i64 total; // elements of the coefficient array (reads stay below its 16-byte rounded end)
+  i64 total; // elements of the coefficient array.  Reads stay below its 16-byte rounded end: up to
+             // 12 bytes behind the array when its size is not a multiple of 16 - the library's own
+             // coefficient buffer is allocated 16 bytes larger; a caller's buffer (mgb_decompose)
+             // comes from an allocator with a granularity of 256 bytes or more
 };
 
 __device__ __forceinline__ unsigned w_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }

@@ -344,7 +344,7 @@ def algorithmic_bytes(shape, stream_bytes):
     }
 
 
-def roofline_tables(fam, shape, stream_bytes, peak, peak_src, ncu_file):
+def roofline_tables(fam, shape, stream_bytes, peak, peak_src, ncu_file, nsub=1):
     """roofline (dominant kernel) + per-kernel list from a kernel_table."""
     alg = algorithmic_bytes(shape, stream_bytes)
     ncu = {}
@@ -362,7 +362,7 @@ def roofline_tables(fam, shape, stream_bytes, peak, peak_src, ncu_file):
     N = shape[0] * shape[1] * shape[2]
     qshare = 1.0
     for f in fam:
-        if f["kernel"] == "quantize_hist" and f["launches_per_step"] > 1.5:
+        if f["kernel"] == "quantize_hist" and f["launches_per_step"] / nsub > 1.5:  # nsub sub-domains per step
             first = -(-(shape[0] // 2 + 1) * shape[1] * shape[2] // 8) * 8
             qshare = max(first, N - first) / N
     alg["quantize_hist"] *= qshare
@@ -625,7 +625,7 @@ def main():
         fam = kernel_table(L, 1)
         sub_stream = int(r1["records"].numel()) / max(count, 1)
         roof, per_kernel = roofline_tables(fam, (ext[first],) + gshape[1:], sub_stream, peak, peak_src,
-                                           "r2_ncu_c5_traffic.json")
+                                           "r2_ncu_c5_traffic.json", nsub=max(count, 1))
         if roof:
             line["roofline"] = roof
         line["roofline_kernels"] = per_kernel

@@ -137,7 +137,10 @@ static int compress_lowlevel_front(mgb_plan *p, const void *d_in, int ebtype, do
   }
   // s = inf, 3-D: the upper half of the coefficients is quantized while the coarse
   // levels are still being decomposed (refactor.cu: decompose_t)
-  p->early_q.armed = is_inf(s) && p->D == 3 && !p->force_generic && p->L >= 3 &&
+  // Only below 2^28 nodes: the two launches together take longer than one over the whole
+  // array (1.25 + 0.81 against 1.57 ms at 257 x 2049^2), which pays while the coarse levels are
+  // a latency-bound chain worth hiding (513^3) and costs 0.47 ms per compression at 257 x 2049^2.
+  p->early_q.armed = is_inf(s) && p->D == 3 && !p->force_generic && p->L >= 3 && p->N < (1ull << 28) &&
                      getenv("MGB_NO_EARLY_QUANTIZE") == nullptr && p->cfg.decomposition == 0;
   p->early_q.done = false;
   p->early_q.ebtype = ebtype;

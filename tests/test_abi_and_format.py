@@ -197,3 +197,14 @@ def test_header_records_reorder_and_single_dimension():
             hdr = hdr.replace(b"\x42\x02\x10\x01", b"\x42\x02\x10\x02")
         assert got == mo.encode_preamble(hdr)
         assert mg.peek_header(np.frombuffer(got, dtype=np.uint8))["header_bytes"] == len(got)
+
+
+def test_tuning_knobs():
+    """mgb_tune (include/mgard_b200.h): the three knobs are accepted without a device and
+    restore to their defaults; an unknown key is an argument error."""
+    import mgard_b200 as mg
+    for key, default in ((mg.TUNE_SERIAL_MIN_CHUNKS, 16384), (mg.TUNE_RING_DECODER, 1), (mg.TUNE_SUB_ENCODER, 1)):
+        mg.tune(key, 0)
+        mg.tune(key, default)
+    from mgard_b200 import _lib
+    assert _lib.lib().mgb_tune(99, 0) != 0
